@@ -1,0 +1,75 @@
+"""ctypes binding of librald_b200.so (the C ABI declared in include/rald_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "_C" / "librald_b200.so"
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_f32 = ctypes.c_float
+c_f64 = ctypes.c_double
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "rald_abi_version": [],
+    "rald_last_error": [],
+    "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
+                       c_int, c_int, c_int, c_int, c_int, c_void_p],
+}
+_RESTYPES = {"rald_last_error": ctypes.c_char_p}
+
+
+class RaldError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the shared library once. Raises if it has not been built (python -m rald_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            if os.environ.get("RALD_B200_AUTOBUILD", "1") == "1":
+                from . import build as _build
+                _build.build()
+            if not LIB_PATH.exists():
+                raise RaldError(f"{LIB_PATH} is missing: build it with `python -m rald_b200.build` "
+                                "(there is no fallback path)")
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _LIB = handle
+    return _LIB
+
+
+def exported_symbols():
+    return list(_SIGNATURES.keys())
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().rald_last_error()
+        raise RaldError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def cur_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

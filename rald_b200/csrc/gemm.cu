@@ -1,0 +1,303 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//     out[M, N] = epilogue( A[M, K] (bf16, K-major) x W[N, K]^T (bf16, K-major) ), fp32 accumulate in TMEM.
+//
+//   warp 0 (1 lane)  TMA producer: 128 x 64 A tile + BN x 64 W tile per stage, 128B-swizzled smem ring
+//   warp 1 (1 lane)  tcgen05.mma issuer (M=128, N=BN, K=16 per instruction), accumulators double-buffered in TMEM
+//   warps 2..5       epilogue: tcgen05.ld -> registers -> (+bias) (+fp32 residual) / GEGLU -> global
+//
+// Replaces, for every nn.Linear on the reference hot path, the cuBLAS sgemm + separate elementwise ops:
+//   model/models_radar_generation.py:58-64 (to_q/to_k/to_v), :76 (to_out + residual :166-168),
+//   :91-95 (GEGLU proj + gelu gate), :113 (ff out); model/models_ae.py:60-62, 78-80, 87-105.
+#include "host.cuh"
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace rald {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  void* out;
+  int64_t ldo;
+  const float* bias;   // [N] or null (GEGLU: packed order, see pack_geglu in the Python runtime)
+  const float* resid;  // [M, ldr] fp32 or null
+  int64_t ldr;
+  int M, N, K;
+  int num_m_blks, num_n_blks;
+};
+
+// OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
+template <int BN, int OUT_MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blks * p.num_n_blks;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blks;
+        const int n_blk = tile - m_blk * p.num_n_blks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_BF16, GEMM_BM, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
+            mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp is allowed to touch
+    const int row_in_tile = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.num_n_blks;
+      const int n_blk = tile - m_blk * p.num_n_blks;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * GEMM_BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+          }
+        }
+        if (OUT_MODE == 1) {
+          if (row_ok) {
+            if (p.resid != nullptr) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.resid + row * p.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = r4[j];
+                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + r.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
+              }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else if (OUT_MODE == 0) {
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                                  pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                  pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                  pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            }
+          }
+        } else {
+          // GEGLU: within every packed 32-column group, columns [0,16) are the value half and [16,32) the
+          // gate half of the same 16 output features (reference: x, gate = proj(x).chunk(2); x * gelu(gate)).
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_erf(__uint_as_float(v[16 + j]));
+          if (row_ok) {
+            uint4* dst =
+                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col0 >> 1));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              dst[j] = make_uint4(pack_bf16x2(o[8 * j + 0], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                                  pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int OUT_MODE>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int max_ctas,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE>;
+  static bool configured = false;
+  if (!configured) {
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = p.num_m_blks * p.num_n_blks;
+  int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  RALD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+              const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
+              cudaStream_t stream) {
+  RALD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  RALD_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  RALD_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
+  RALD_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm: out_mode %d", out_mode);
+  RALD_REQUIRE(out_mode != 2 || resid == nullptr, "gemm: GEGLU epilogue takes no residual");
+  RALD_REQUIRE(out_mode == 1 || resid == nullptr, "gemm: residual needs the fp32 output mode");
+  RALD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % (out_mode == 1 ? 4 : 8) == 0,
+               "gemm: output not 16-byte aligned");
+  RALD_REQUIRE(resid == nullptr || ((reinterpret_cast<uintptr_t>(resid) & 15) == 0 && ldr % 4 == 0),
+               "gemm: residual not 16-byte aligned");
+  RALD_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16-byte aligned");
+
+  const int sms = device_sm_count();
+  int bn = bn_hint;
+  if (bn == 0) {
+    // Prefer the 128x256 tile (full-rate MMA with the lowest smem traffic) unless it leaves most SMs idle.
+    const int m_blks = (M + GEMM_BM - 1) / GEMM_BM;
+    if (N % 256 == 0 && m_blks * (N / 256) >= sms) bn = 256;
+    else if (N % 128 == 0 && m_blks * (N / 128) >= sms / 2) bn = 128;
+    else if (N % 128 == 0 && N >= 512) bn = 128;
+    else if (N % 64 == 0) bn = 64;
+    else bn = 32;
+  }
+  RALD_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
+
+  GemmParams p;
+  p.out = out;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.resid = resid;
+  p.ldr = ldr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blks = (M + GEMM_BM - 1) / GEMM_BM;
+  p.num_n_blks = (N + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB;
+  RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
+  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
+
+#define RALD_GEMM_CASE(BN_)                                                              \
+  case BN_:                                                                              \
+    if (out_mode == 0) return launch_gemm<BN_, 0>(tmA, tmB, p, sms, stream);             \
+    if (out_mode == 1) return launch_gemm<BN_, 1>(tmA, tmB, p, sms, stream);             \
+    return launch_gemm<BN_, 2>(tmA, tmB, p, sms, stream);
+  switch (bn) {
+    RALD_GEMM_CASE(32)
+    RALD_GEMM_CASE(64)
+    RALD_GEMM_CASE(128)
+    RALD_GEMM_CASE(256)
+  }
+#undef RALD_GEMM_CASE
+  return -1;
+}
+
+}  // namespace rald

@@ -1,0 +1,52 @@
+// Host-side plumbing shared by all translation units: error reporting for the C ABI and
+// TMA tensor-map encoding (cuTensorMapEncodeTiled resolved through the runtime so the library
+// links without libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace rald {
+
+// thread-local last error string, read by rald_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define RALD_CHECK_CUDA(expr)                                                                        \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      ::rald::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+      return -static_cast<int>(_e) - 1000;                                                           \
+    }                                                                                                \
+  } while (0)
+
+#define RALD_REQUIRE(cond, ...)                  \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::rald::set_error(__VA_ARGS__);            \
+      return -1;                                 \
+    }                                            \
+  } while (0)
+
+#define RALD_TRY(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+// 2-D row-major matrix [rows, cols] of 16-bit elements (cols contiguous, row pitch ld elements),
+// box = box_rows x 64 columns, 128-byte swizzle, out-of-bounds reads return zero.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows);
+// same for 32-bit elements (tf32 operands): box = box_rows x 32 columns (128 bytes)
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows);
+// General tiled map over 16-bit elements: dims/strides innermost first (strides in BYTES for dims 1..rank-1).
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
+int device_sm_count();
+
+}  // namespace rald
