@@ -38,6 +38,100 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
                    int bn_hint, void* stream);
 
+/* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512, scores kept in TMEM.
+ * Q: [frames*Sq, >= heads*64] bf16 (ldq), K/V: [frames*Skv, ...] bf16, O: [frames*Sq, ...] bf16; head h uses
+ * columns [h*64, h*64+64). Replaces the two einsums + softmax of CrossAttention.forward
+ * (model/models_radar_generation.py:66-75) and Attention.forward (model/models_ae.py:91-104). */
+int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                  int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* stream);
+
+/* out = LN(x) * g + b over rows of 512 fp32 values (eps inside the rsqrt). gamma_plus_one=1 gives the adaLN
+ * modulation LN(x)*(1+scale)+shift of AdaLayerNorm.forward (model/models_radar_generation.py:127-131) with
+ * gamma/beta = scale/shift of frame f at gamma + f*mod_frame_stride (stride 0 = shared); gamma_plus_one=0 is
+ * nn.LayerNorm with affine weights (model/models_ae.py:38-47). out_f32=0 writes bf16. */
+int rald_ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,
+                 int rows_per_frame, int gamma_plus_one, void* out, int64_t ldo, int out_f32, int64_t rows, int D,
+                 float eps, void* stream);
+
+/* mod[s][n][i][0:dim] = scale, [dim:2dim] = shift of AdaLayerNorm i (norm1..3) in block n for sigma[s]:
+ * PositionalEmbedding + map_layer0/1 + SiLU (model/models_radar_generation.py:27-33, 217-219) followed by all
+ * depth*3 AdaLayerNorm.linear layers (:128-129). freqs = the fp32 frequency vector of :28-30 (length `half`).
+ * ada_w: fp32 [depth*3*2*dim, dim] rows ordered (block, norm index, out feature); t_emb_ws: scratch [S, dim]. */
+int rald_dit_mod_table(const float* sigma, int S, const float* freqs, int half, const float* map0_w,
+                       const float* map0_b, const float* map1_w, const float* map1_b, const float* ada_w,
+                       const float* ada_b, int depth, int dim, float* t_emb_ws, float* mod, void* stream);
+
+/* Fused "evaluation boundary" on [T, C] latent rows (C <= 32, dim 512):
+ *   F = proj_out(LayerNorm(h)) (model/models_radar_generation.py:230-232); D = c_skip x + c_out F (:422-429);
+ *   mode 0: x_out = D                                   (EDMPrecond.forward)
+ *   mode 1: d = (x - D)/sigma; x_out = x + (sigma_other - sigma) d; d_buf = d          (Euler, :265-266)
+ *   mode 2: d' = (x - D)/sigma; x_out = x_base + (sigma - sigma_other)(d_buf/2 + d'/2)  (Heun, :272-273)
+ *   mode 3: x_out = x * sigma (:252);  mode 4: nothing (projection only)
+ *   then, if h_next != NULL: h_next = proj_in(c_in(sigma_next) * x_out) (:221, :427) for the next evaluation.
+ * w_out_t: fp32 [dim][32] (proj_out transposed, zero padded); w_in_t: fp32 [C][dim]. */
+int rald_dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t,
+                      const float* w_in_t, const float* x_in, const float* x_base, float* d_buf, float* x_out,
+                      float* h_next, const float* sigma, int64_t sigma_stride, const float* sigma_other,
+                      int64_t sigma_other_stride, int mode, int rows_per_frame, int C, int64_t T, int dim,
+                      float sigma_data, void* stream);
+
+/* Radar conditioning tokens: Linear(cz -> dim) of the encoder output [B, nr, na, ne, cz] (channels last) plus the
+ * range / azimuth / elevation embeddings (model/models_radar_generation.py:390-405). Either output may be NULL. */
+int rald_radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const float* w, const float* b,
+                      const float* r_emb, const float* a_emb, const float* e_emb, int dim, float* tok_f32,
+                      void* tok_bf16, void* stream);
+
+/* ---- denoiser runtime: packed weights + workspace + whole-evaluation / whole-sampler entry points ---- */
+typedef struct rald_dit_weights {
+  int32_t depth, dim, heads, channels, n_latents, ctx_len;
+  float sigma_data;
+  int32_t _pad;
+  /* bf16, stacked over depth */
+  const void* w_qkv;   /* [depth][3*dim][dim]  rows: to_q | to_k | to_v of attn1 */
+  const void* w_o1;    /* [depth][dim][dim]    attn1.to_out.0.weight */
+  const void* w_q2;    /* [depth][dim][dim]    attn2.to_q.weight */
+  const void* w_o2;    /* [depth][dim][dim]    attn2.to_out.0.weight */
+  const void* w_ff1;   /* [depth][8*dim][dim]  ff.net.0.proj.weight, GEGLU-packed (16 value + 16 gate rows) */
+  const void* w_ff2;   /* [depth][dim][4*dim]  ff.net.2.weight */
+  /* fp32 */
+  const float* b_o1;   /* [depth][dim] */
+  const float* b_o2;   /* [depth][dim] */
+  const float* b_ff1;  /* [depth][8*dim] GEGLU-packed */
+  const float* b_ff2;  /* [depth][dim] */
+  const float* ln_w;   /* [dim] model.norm.weight */
+  const float* ln_b;   /* [dim] */
+  const float* proj_in_t;   /* [channels][dim]  proj_in.weight transposed */
+  const float* proj_out_t;  /* [dim][32]        proj_out.weight transposed, zero padded to 32 */
+} rald_dit_weights;
+
+typedef struct rald_dit_workspace {
+  int32_t max_frames;  /* micro-batch size the buffers below are sized for; T = max_frames * n_latents */
+  int32_t _pad;
+  float* h;      /* [T][dim]   fp32 residual stream */
+  void* xn;      /* [T][dim]   bf16 normalised operand */
+  void* qkv;     /* [T][3*dim] bf16 */
+  void* att;     /* [T][dim]   bf16 */
+  void* ff;      /* [T][4*dim] bf16 */
+  float* x_tmp;  /* [T][channels] */
+  float* d_tmp;  /* [T][channels] */
+} rald_dit_workspace;
+
+/* One EDMPrecond.forward (model/models_radar_generation.py:412-430) for `frames` frames given precomputed
+ * conditioning: mod = adaLN table rows for each frame's sigma ([frames or 1][depth][3][2*dim], frame stride
+ * mod_frame_stride, 0 = shared), ctxkv = bf16 [frames*ctx_len][depth*2*dim] (per block: K | V projections of
+ * the conditioning tokens, attn2.to_k / to_v). x, out: fp32 [frames][n_latents][channels]. */
+int rald_dit_forward(const rald_dit_weights* w, const rald_dit_workspace* ws, const float* x, const float* sigma,
+                     int64_t sigma_stride, const float* mod, int64_t mod_frame_stride, const void* ctxkv,
+                     float* out, int frames, void* stream);
+
+/* edm_sampler (model/models_radar_generation.py:235-275, S_churn = 0): sigmas = device fp32 [num_steps + 1]
+ * (last = 0), mod = [num_steps][depth][3][2*dim], latents = unit normal fp32 [frames][n_latents][channels].
+ * x_out receives the final latents; trace (optional) [num_steps][frames][n_latents][channels] receives x_next
+ * after every step. */
+int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspace* ws, const float* latents,
+                    const float* sigmas, int num_steps, const float* mod, const void* ctxkv, float* x_out,
+                    float* trace, int frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

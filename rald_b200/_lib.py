@@ -23,6 +23,20 @@ _SIGNATURES = {
     "rald_last_error": [],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
+                      c_f32, c_void_p],
+    "rald_ln_rows": [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_int,
+                     c_f32, c_void_p],
+    "rald_dit_mod_table": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "rald_dit_boundary": [c_void_p] * 10 + [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_i64, c_int, c_f32,
+                                            c_void_p],
+    "rald_radar_tokens": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "rald_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_int,
+                         c_void_p],
+    "rald_dit_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                        c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p}
 

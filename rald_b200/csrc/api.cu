@@ -17,4 +17,41 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                          static_cast<cudaStream_t>(stream));
 }
 
+int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                  int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* stream) {
+  return rald::attn_d64(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, Skv, scale,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int rald_ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,
+                 int rows_per_frame, int gamma_plus_one, void* out, int64_t ldo, int out_f32, int64_t rows, int D,
+                 float eps, void* stream) {
+  return rald::ln_rows(x, ldx, gamma, beta, mod_frame_stride, rows_per_frame, gamma_plus_one, out, ldo, out_f32, rows,
+                       D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int rald_dit_mod_table(const float* sigma, int S, const float* freqs, int half, const float* map0_w,
+                       const float* map0_b, const float* map1_w, const float* map1_b, const float* ada_w,
+                       const float* ada_b, int depth, int dim, float* t_emb_ws, float* mod, void* stream) {
+  return rald::dit_mod_table(sigma, S, freqs, half, map0_w, map0_b, map1_w, map1_b, ada_w, ada_b, depth, dim,
+                             t_emb_ws, mod, static_cast<cudaStream_t>(stream));
+}
+
+int rald_dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t,
+                      const float* w_in_t, const float* x_in, const float* x_base, float* d_buf, float* x_out,
+                      float* h_next, const float* sigma, int64_t sigma_stride, const float* sigma_other,
+                      int64_t sigma_other_stride, int mode, int rows_per_frame, int C, int64_t T, int dim,
+                      float sigma_data, void* stream) {
+  return rald::dit_boundary(h, ln_w, ln_b, w_out_t, w_in_t, x_in, x_base, d_buf, x_out, h_next, sigma, sigma_stride,
+                            sigma_other, sigma_other_stride, mode, rows_per_frame, C, T, dim, sigma_data,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int rald_radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const float* w, const float* b,
+                      const float* r_emb, const float* a_emb, const float* e_emb, int dim, float* tok_f32,
+                      void* tok_bf16, void* stream) {
+  return rald::radar_tokens(feat, B, nr, na, ne, cz, w, b, r_emb, a_emb, e_emb, dim, tok_f32, tok_bf16,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -14,4 +14,27 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
               const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
               cudaStream_t stream);
 
+// attn.cu ------------------------------------------------------------------------------------------
+// O[f, :, h*64:(h+1)*64] = softmax(Q K^T * scale) V per (frame f, head h); head_dim 64; Skv <= 512.
+// Q rows = frames*Sq, K/V rows = frames*Skv; head h lives at columns [h*64, h*64+64) of each operand.
+int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+             int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, cudaStream_t stream);
+
+// norm.cu ------------------------------------------------------------------------------------------
+int ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,
+            int rows_per_frame, int gamma_plus_one, void* out, int64_t ldo, int out_f32, int64_t rows, int D,
+            float eps, cudaStream_t stream);
+
+// dit_misc.cu --------------------------------------------------------------------------------------
+int dit_mod_table(const float* sigma, int S, const float* freqs, int half, const float* map0_w, const float* map0_b,
+                  const float* map1_w, const float* map1_b, const float* ada_w, const float* ada_b, int depth,
+                  int dim, float* t_emb_ws, float* mod, cudaStream_t stream);
+int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t,
+                 const float* x_in, const float* x_base, float* d_buf, float* x_out, float* h_next,
+                 const float* sigma, int64_t sigma_stride, const float* sigma_other, int64_t sigma_other_stride,
+                 int mode, int rows_per_frame, int C, int64_t T, int dim, float sigma_data, cudaStream_t stream);
+int radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const float* w, const float* b,
+                 const float* r_emb, const float* a_emb, const float* e_emb, int dim, float* tok_f32, void* tok_bf16,
+                 cudaStream_t stream);
+
 }  // namespace rald

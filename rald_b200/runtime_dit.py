@@ -1,0 +1,210 @@
+"""Host-side runtime of the denoiser: packs the fp32 nn.Parameters of ``EDMPrecond`` into the layouts the
+sm_100a kernels consume, owns the (torch-allocated) workspaces and calls the C ABI (include/rald_b200.h).
+
+Packing happens on the device with torch indexing/cat ops at load time (plumbing); nothing here computes the
+hot path itself.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import c_void_p
+
+
+
+class DitWeights(ctypes.Structure):
+    _fields_ = [("depth", ctypes.c_int32), ("dim", ctypes.c_int32), ("heads", ctypes.c_int32),
+                ("channels", ctypes.c_int32), ("n_latents", ctypes.c_int32), ("ctx_len", ctypes.c_int32),
+                ("sigma_data", ctypes.c_float), ("_pad", ctypes.c_int32),
+                ("w_qkv", c_void_p), ("w_o1", c_void_p), ("w_q2", c_void_p), ("w_o2", c_void_p),
+                ("w_ff1", c_void_p), ("w_ff2", c_void_p),
+                ("b_o1", c_void_p), ("b_o2", c_void_p), ("b_ff1", c_void_p), ("b_ff2", c_void_p),
+                ("ln_w", c_void_p), ("ln_b", c_void_p), ("proj_in_t", c_void_p), ("proj_out_t", c_void_p)]
+
+
+class DitWorkspace(ctypes.Structure):
+    _fields_ = [("max_frames", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("h", c_void_p), ("xn", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("ff", c_void_p),
+                ("x_tmp", c_void_p), ("d_tmp", c_void_p)]
+
+
+def geglu_pack_index(inner: int, device) -> torch.Tensor:
+    """Row permutation for a GEGLU projection [2*inner, K] (rows 0..inner-1 = value, inner.. = gate) so that
+    every group of 32 packed rows holds 16 value rows followed by the 16 matching gate rows (the layout the
+    GEMM's GEGLU epilogue expects)."""
+    p = torch.arange(2 * inner, device=device)
+    group, within = p // 32, p % 32
+    feat = group * 16 + within % 16
+    return torch.where(within < 16, feat, inner + feat)
+
+
+def default_microbatch() -> int:
+    return int(os.environ.get("RALD_B200_MICROBATCH", "8"))
+
+
+class DitRuntime:
+    """Packed weights + workspaces for one EDMPrecond instance on one CUDA device."""
+
+    def __init__(self, module):
+        self.module = module
+        self._sig = None
+        self._ws = None
+        self._ws_frames = 0
+        self._mod_cache = {}
+
+    # ------------------------------------------------------------------ packing
+    def _signature(self):
+        m = self.module.model
+        ps = list(m.parameters())
+        return (ps[0].device, sum(p._version for p in ps), len(ps))
+
+    def ensure_packed(self):
+        sig = self._signature()
+        if sig == self._sig:
+            return
+        m = self.module.model
+        dev = sig[0]
+        if dev.type != "cuda":
+            raise _lib.RaldError("rald_b200 runs on CUDA devices only: move the module to a B200 (no CPU fallback)")
+        blocks = m.transformer_blocks
+        depth = len(blocks)
+        dim = m.proj_in.weight.shape[0]
+        heads = blocks[0].attn1.heads
+        if dim != 512 or dim // heads != 64:
+            raise _lib.RaldError(f"unsupported denoiser width {dim} / heads {heads}: kernels are built for 512 = 8 x 64")
+        bf = torch.bfloat16
+        with torch.no_grad():
+            def stack(fn, dtype):
+                return torch.stack([fn(b).detach() for b in blocks]).to(dtype).contiguous()
+            idx = geglu_pack_index(blocks[0].ff.net[2].weight.shape[1], dev)
+            self.w_qkv = stack(lambda b: torch.cat([b.attn1.to_q.weight, b.attn1.to_k.weight, b.attn1.to_v.weight]), bf)
+            self.w_o1 = stack(lambda b: b.attn1.to_out[0].weight, bf)
+            self.b_o1 = stack(lambda b: b.attn1.to_out[0].bias, torch.float32)
+            self.w_q2 = stack(lambda b: b.attn2.to_q.weight, bf)
+            self.w_kv2 = torch.cat([torch.cat([b.attn2.to_k.weight, b.attn2.to_v.weight]).detach() for b in blocks]
+                                   ).to(bf).contiguous()
+            self.w_o2 = stack(lambda b: b.attn2.to_out[0].weight, bf)
+            self.b_o2 = stack(lambda b: b.attn2.to_out[0].bias, torch.float32)
+            self.w_ff1 = stack(lambda b: b.ff.net[0].proj.weight[idx], bf)
+            self.b_ff1 = stack(lambda b: b.ff.net[0].proj.bias[idx], torch.float32)
+            self.w_ff2 = stack(lambda b: b.ff.net[2].weight, bf)
+            self.b_ff2 = stack(lambda b: b.ff.net[2].bias, torch.float32)
+            self.ada_w = torch.cat([torch.cat([b.norm1.linear.weight, b.norm2.linear.weight, b.norm3.linear.weight])
+                                    .detach() for b in blocks]).float().contiguous()
+            self.ada_b = torch.cat([torch.cat([b.norm1.linear.bias, b.norm2.linear.bias, b.norm3.linear.bias])
+                                    .detach() for b in blocks]).float().contiguous()
+            self.map0_w = m.map_layer0.weight.detach().float().contiguous()
+            self.map0_b = m.map_layer0.bias.detach().float().contiguous()
+            self.map1_w = m.map_layer1.weight.detach().float().contiguous()
+            self.map1_b = m.map_layer1.bias.detach().float().contiguous()
+            self.ln_w = m.norm.weight.detach().float().contiguous()
+            self.ln_b = m.norm.bias.detach().float().contiguous()
+            C = m.proj_in.weight.shape[1]
+            self.proj_in_t = m.proj_in.weight.detach().float().t().contiguous()
+            pot = torch.zeros(dim, 32, device=dev, dtype=torch.float32)
+            pot[:, :C] = m.proj_out.weight.detach().float().t()
+            self.proj_out_t = pot
+            half = m.t_channels // 2
+            # frequencies exactly as the reference computes them (models_radar_generation.py:28-30), fp32
+            fr = torch.arange(half, dtype=torch.float32, device=dev) / half
+            self.freqs = ((1.0 / m.map_noise.max_positions) ** fr).contiguous()
+            self.half = half
+        self.depth, self.dim, self.heads, self.channels = depth, dim, heads, C
+        self.device = dev
+        self._mod_cache.clear()
+        self._sig = sig
+
+    def _weights_struct(self, ctx_len: int) -> DitWeights:
+        w = DitWeights()
+        w.depth, w.dim, w.heads, w.channels = self.depth, self.dim, self.heads, self.channels
+        w.n_latents, w.ctx_len = self.module.n_latents, ctx_len
+        w.sigma_data = float(self.module.sigma_data)
+        for name in ("w_qkv", "w_o1", "w_q2", "w_o2", "w_ff1", "w_ff2", "b_o1", "b_o2", "b_ff1", "b_ff2", "ln_w", "ln_b",
+                     "proj_in_t", "proj_out_t"):
+            setattr(w, name, getattr(self, name).data_ptr())
+        return w
+
+    def _workspace(self, frames: int):
+        mb = max(1, min(default_microbatch(), frames))
+        if self._ws is None or self._ws_frames != mb:
+            T = mb * self.module.n_latents
+            dev, dim = self.device, self.dim
+            bufs = dict(h=torch.empty(T, dim, device=dev, dtype=torch.float32),
+                        xn=torch.empty(T, dim, device=dev, dtype=torch.bfloat16),
+                        qkv=torch.empty(T, 3 * dim, device=dev, dtype=torch.bfloat16),
+                        att=torch.empty(T, dim, device=dev, dtype=torch.bfloat16),
+                        ff=torch.empty(T, 4 * dim, device=dev, dtype=torch.bfloat16),
+                        x_tmp=torch.empty(T, self.channels, device=dev, dtype=torch.float32),
+                        d_tmp=torch.empty(T, self.channels, device=dev, dtype=torch.float32))
+            ws = DitWorkspace()
+            ws.max_frames = mb
+            for k, v in bufs.items():
+                setattr(ws, k, v.data_ptr())
+            self._ws, self._ws_bufs, self._ws_frames = ws, bufs, mb
+        return self._ws
+
+    # ------------------------------------------------------------------ pieces
+    def mod_table(self, sigmas: torch.Tensor) -> torch.Tensor:
+        """[S] fp32 sigmas (device) -> adaLN table [S, depth, 3, 2*dim] fp32."""
+        S = sigmas.numel()
+        t_emb = torch.empty(S, self.dim, device=self.device, dtype=torch.float32)
+        mod = torch.empty(S, self.depth, 3, 2 * self.dim, device=self.device, dtype=torch.float32)
+        _lib.call("rald_dit_mod_table", sigmas.data_ptr(), S, self.freqs.data_ptr(), self.half, self.map0_w.data_ptr(),
+                  self.map0_b.data_ptr(), self.map1_w.data_ptr(), self.map1_b.data_ptr(), self.ada_w.data_ptr(),
+                  self.ada_b.data_ptr(), self.depth, self.dim, t_emb.data_ptr(), mod.data_ptr(), _lib.cur_stream())
+        return mod
+
+    def context_kv(self, tokens_bf16: torch.Tensor) -> torch.Tensor:
+        """bf16 tokens [B*L, dim] -> K/V projections for all blocks [B*L, depth*2*dim] bf16 in ONE GEMM
+        (the reference recomputes attn2.to_k / to_v per block and per network evaluation)."""
+        rows = tokens_bf16.shape[0]
+        n = self.depth * 2 * self.dim
+        out = torch.empty(rows, n, device=self.device, dtype=torch.bfloat16)
+        _lib.call("rald_gemm_bf16", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim, out.data_ptr(), n,
+                  0, 0, 0, rows, n, self.dim, 0, 0, _lib.cur_stream())
+        return out
+
+    # ------------------------------------------------------------------ entry points
+    def forward(self, x: torch.Tensor, sigma: torch.Tensor, tokens_bf16: torch.Tensor) -> torch.Tensor:
+        self.ensure_packed()
+        B, M, C = x.shape
+        L = tokens_bf16.shape[0] // B
+        x = x.contiguous().float()
+        sigma = sigma.to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        if sigma.numel() not in (1, B):
+            raise ValueError(f"sigma must have 1 or {B} elements, got {sigma.numel()}")
+        per_frame = sigma.numel() == B and B > 1
+        mod = self.mod_table(sigma)
+        ctxkv = self.context_kv(tokens_bf16)
+        out = torch.empty_like(x)
+        w, ws = self._weights_struct(L), self._workspace(B)
+        _lib.call("rald_dit_forward", ctypes.addressof(w), ctypes.addressof(ws), x.data_ptr(), sigma.data_ptr(),
+                  1 if per_frame else 0, mod.data_ptr(), self.depth * 3 * 2 * self.dim if per_frame else 0,
+                  ctxkv.data_ptr(), out.data_ptr(), B, _lib.cur_stream())
+        return out
+
+    def sample(self, latents: torch.Tensor, tokens_bf16: torch.Tensor, sigmas: torch.Tensor,
+               trace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """latents: unit normal [B, M, C]; sigmas: fp32 [num_steps + 1] ending in 0 (host or device tensor)."""
+        self.ensure_packed()
+        B, M, C = latents.shape
+        L = tokens_bf16.shape[0] // B
+        latents = latents.contiguous().float()
+        key = tuple(float(s) for s in sigmas.tolist())
+        sig_dev = sigmas.to(device=self.device, dtype=torch.float32).contiguous()
+        num_steps = sig_dev.numel() - 1
+        if key not in self._mod_cache:
+            self._mod_cache.clear()
+            self._mod_cache[key] = self.mod_table(sig_dev[:num_steps])
+        mod = self._mod_cache[key]
+        ctxkv = self.context_kv(tokens_bf16)
+        out = torch.empty_like(latents)
+        w, ws = self._weights_struct(L), self._workspace(B)
+        _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
+                  num_steps, mod.data_ptr(), ctxkv.data_ptr(), out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
+        return out
