@@ -132,6 +132,50 @@ int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspace* ws, con
                     const float* sigmas, int num_steps, const float* mod, const void* ctxkv, float* x_out,
                     float* trace, int frames, void* stream);
 
+/* ---- VecSet autoencoder (model/models_ae.py) ---- */
+typedef struct rald_ae_weights {
+  int32_t depth, dim, heads, latent_dim, n_latents, _pad;
+  /* bf16, stacked over depth */
+  const void* w_qkv;   /* [depth][3*dim][dim]  layers.N.0.fn: to_q | to_kv (k rows, then v rows) */
+  const void* w_o;     /* [depth][dim][dim]    layers.N.0.fn.to_out.weight */
+  const void* w_ff1;   /* [depth][8*dim][dim]  layers.N.1.fn.net.0.weight, GEGLU-packed */
+  const void* w_ff2;   /* [depth][dim][4*dim]  layers.N.1.fn.net.2.weight */
+  /* fp32 */
+  const float* b_o;    /* [depth][dim] */
+  const float* b_ff1;  /* [depth][8*dim] GEGLU-packed */
+  const float* b_ff2;  /* [depth][dim] */
+  const float* ln1_w;  /* [depth][dim] layers.N.0.norm */
+  const float* ln1_b;
+  const float* ln2_w;  /* [depth][dim] layers.N.1.norm */
+  const float* ln2_b;
+  const float* proj_wt; /* [latent_dim][dim] proj.weight transposed */
+  const float* proj_b;  /* [dim] */
+} rald_ae_weights;
+
+/* x_out[frames*n_latents][dim] (fp32) = latent stack of KLAutoEncoder.decode: proj followed by depth x
+ * (self-attention, GEGLU feed-forward) with pre-LayerNorm and residuals (model/models_ae.py:410-414).
+ * z: fp32 [frames][n_latents][latent_dim]. Uses the same workspace layout as the denoiser. */
+int rald_ae_stack(const rald_ae_weights* w, const rald_dit_workspace* ws, const float* z, float* x_out,
+                  int frames, void* stream);
+
+/* out[T][512] = x[T][K] @ wt[K][512] + b in fp32 (K <= 64): KLAutoEncoder.proj (model/models_ae.py:346, 410). */
+int rald_linear_smallk(const float* x, int K, const float* wt, const float* b, float* out, int64_t T, int N,
+                       void* stream);
+
+/* out[row] = (LayerNorm(x[row]) * g + b) . w over 512-wide fp32 rows: the folded value path
+ * v' = LN_ctx(x) (W_v^T W_out^T w_o^T) of the decoder cross-attention (model/models_ae.py:89, 103-105, 424). */
+int rald_ln_dot_rows(const float* x, const float* g, const float* b, const float* w, float* out, int64_t rows,
+                     int D, float eps, void* stream);
+
+/* Decoder queries (model/models_ae.py:417-424), folded form: logits[b][q] = softmax(LN(point_embed(q)) K'_b^T /
+ * sqrt(dim)) . v'_b + c0_b. queries fp32 [B][Q][3]; wpe_bf16 [512][64] = point_embed.mlp.weight zero-padded
+ * from 51 to 64 inputs; pe_bias = point_embed.mlp.bias; ln_g/ln_b = decoder_cross_attn.norm; kprime_bf16
+ * [B*512][512]; vprime [B][512]; c0 [B]; freq24_host = HOST pointer to the 24 non-zero entries of
+ * point_embed.basis (x, y, z blocks of 8). */
+int rald_ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, const float* pe_bias,
+                  const float* ln_g, const float* ln_b, const void* kprime_bf16, const float* vprime,
+                  const float* c0, const float* freq24_host, float* logits, int dim, int n_latents, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,11 @@ _SIGNATURES = {
                          c_void_p],
     "rald_dit_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                         c_void_p],
+    "rald_ae_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "rald_linear_smallk": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p],
+    "rald_ln_dot_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],
+    "rald_ae_query": [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_void_p, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p}
 

@@ -37,4 +37,13 @@ int radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const
                  const float* r_emb, const float* a_emb, const float* e_emb, int dim, float* tok_f32, void* tok_bf16,
                  cudaStream_t stream);
 
+// ae.cu / ae_query.cu ---------------------------------------------------------------------------------
+int linear_smallk(const float* x, int K, const float* wt, const float* b, float* out, int64_t T, int N,
+                  cudaStream_t stream);
+int ln_dot_rows(const float* x, const float* g, const float* b, const float* w, float* out, int64_t rows, int D,
+                float eps, cudaStream_t stream);
+int ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, const float* pe_bias, const float* ln_g,
+             const float* ln_b, const void* kprime_bf16, const float* vprime, const float* c0, const float* freq24,
+             float* logits, int dim, int n_latents, cudaStream_t stream);
+
 }  // namespace rald
