@@ -176,6 +176,76 @@ int rald_ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, 
                   const float* ln_g, const float* ln_b, const void* kprime_bf16, const float* vprime,
                   const float* c0, const float* freq24_host, float* logits, int dim, int n_latents, void* stream);
 
+/* ---- radar-cube encoder (model/models_radar_encoder.py) ---- */
+
+/* out[B, D/s, H/s, W/s, Cout] (fp32, channels last) = Conv3d 3x3x3 of x[B, D, H, W, Cin] (bf16, channels last) on
+ * tcgen05 as an implicit GEMM; stride 1 pads 1 on both sides (ResnetBlock convs :63-72, conv_out :208-214), stride 2
+ * pads 1 on the HIGH side only (Downsample :34-41). w_packed: bf16 [w_rows][27*Cin] with K index = tap*Cin + ci,
+ * tap = kd*9 + kh*3 + kw, w_rows = Cout rounded up to the N tile (32 / 64 / 128) with zero rows; bias padded
+ * likewise. resid (optional, fp32, same shape as out, may alias out) is added in the epilogue. Cin % 64 == 0. */
+int rald_conv3d_cl(const void* x_bf16, const void* w_packed, int w_rows, const float* bias, const float* resid,
+                   float* out, int B, int D, int H, int W, int Cin, int Cout, int stride, void* stream);
+
+/* conv_in (:161-163): x fp32 [B, D, H, W, Cin<=4] -> out fp32 [B, D, H, W, Cout]; w = PyTorch layout
+ * [Cout][Cin][3][3][3] fp32. */
+int rald_enc_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int D, int H, int W,
+                     int Cin, int Cout, void* stream);
+
+/* GroupNorm(groups, eps) statistics of x fp32 [B, V, C]: stats[b][g] = {sum, sum of squares} in double. */
+int rald_gn_stats(const float* x, int B, int64_t V, int C, int groups, double* stats, void* stream);
+
+/* out bf16 [B, V, C] = mode 0: swish(GN(x)) (Normalize + nonlinearity :5-12); 1: GN(x); 2: x (cast only). */
+int rald_gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out_bf16, int B,
+                  int64_t V, int C, int groups, float eps, int mode, void* stream);
+
+/* AttnBlock core (:121-133): qkv fp32 [B*n, 3C] (q | k | v), one head of width C over the n <= 64 voxels of each
+ * frame; out bf16 [B*n, C] = softmax(q k^T C^-0.5) v. */
+int rald_enc_attn(const float* qkv, void* out_bf16, int B, int n, int C, void* stream);
+
+typedef struct rald_enc_conv {   /* 3x3x3 conv (packed as for rald_conv3d_cl) or 1x1x1 conv (bf16 [cout][cin]) */
+  const void* w;                 /* NULL = layer absent */
+  const float* b;
+  int32_t cin, cout, w_rows, _pad;
+} rald_enc_conv;
+typedef struct rald_enc_norm { const float* g; const float* b; } rald_enc_norm;
+typedef struct rald_enc_resblock { rald_enc_norm n1; rald_enc_conv c1; rald_enc_norm n2; rald_enc_conv c2;
+                                   rald_enc_conv nin; } rald_enc_resblock;
+typedef struct rald_enc_attnblock { rald_enc_norm n; rald_enc_conv qkv; rald_enc_conv proj; } rald_enc_attnblock;
+#define RALD_ENC_MAX_LEVELS 8
+#define RALD_ENC_MAX_BLOCKS 4
+typedef struct rald_enc_level {
+  int32_t n_blocks, n_attn;      /* n_attn is 0 or n_blocks */
+  rald_enc_resblock block[RALD_ENC_MAX_BLOCKS];
+  rald_enc_attnblock attn[RALD_ENC_MAX_BLOCKS];
+  rald_enc_conv down;            /* stride-2 conv, absent on the last level */
+} rald_enc_level;
+typedef struct rald_enc_weights {
+  int32_t n_levels, in_ch, ch, z_ch, groups, _pad;
+  float eps;
+  int32_t _pad2;
+  const float* conv_in_w;        /* fp32 [ch][in_ch][3][3][3] */
+  const float* conv_in_b;
+  rald_enc_level level[RALD_ENC_MAX_LEVELS];
+  rald_enc_resblock mid1, mid2;
+  rald_enc_attnblock mid_attn;
+  rald_enc_norm norm_out;
+  rald_enc_conv conv_out;
+} rald_enc_weights;
+typedef struct rald_enc_workspace {
+  int32_t max_frames, _pad;
+  int64_t elems;                 /* capacity of each buffer below in elements (>= max_frames * D*H*W * widest C) */
+  float* x;                      /* fp32 residual stream */
+  float* y;                      /* fp32 second stream buffer (shortcut / downsample output) */
+  float* t;                      /* fp32 conv1 output, attention qkv */
+  void* xb;                      /* bf16 normalised operand */
+  double* stats;                 /* [max_frames][groups][2] */
+} rald_enc_workspace;
+
+/* Encoder.forward (model/models_radar_encoder.py:216-241) for channels-last input x fp32 [B, D, H, W, in_ch]:
+ * out fp32 [B, D/2^(L-1), H/2^(L-1), W/2^(L-1), z_ch]. Frames are processed in micro-batches of ws->max_frames. */
+int rald_radar_encoder(const rald_enc_weights* w, const rald_enc_workspace* ws, const float* x, float* out, int B,
+                       int D, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,14 @@ _SIGNATURES = {
     "rald_ln_dot_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],
     "rald_ae_query": [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                       c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "rald_conv3d_cl": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                       c_int, c_void_p],
+    "rald_enc_conv_in": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_gn_stats": [c_void_p, c_int, c_i64, c_int, c_int, c_void_p, c_void_p],
+    "rald_gn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_f32, c_int,
+                      c_void_p],
+    "rald_enc_attn": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rald_radar_encoder": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p}
 

@@ -1,0 +1,310 @@
+// SIMT kernels of the radar-cube encoder around the tcgen05 convolutions (all channels-last, [B, V, C]):
+//   conv_in_kernel     3x3x3 Conv3d with 1..4 input channels (conv_in)        model/models_radar_encoder.py:161-163, 217
+//   gn_stats_kernel    per (frame, group) sum / sum of squares                 GroupNorm(32, eps 1e-6) :9-12
+//   gn_apply_kernel    y = swish?(GN(x)) -> bf16 operand of the next conv; or plain fp32 -> bf16 cast
+//   enc_attn_kernel    single-head attention over <= 64 voxels, head_dim = C   AttnBlock :112-135
+// These are HBM-bound passes (stats: 4 B/elem read; apply: 4 B read + 2 B written per element).
+#include "host.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace rald {
+
+// ---------------------------------------------------------------------------------------------------
+// conv_in: x [B, D, H, W, Cin] fp32 -> out [B, D, H, W, Cout] fp32, padding 1. One thread = one voxel x 4
+// output channels, so a voxel's Cout floats are written by consecutive threads (coalesced).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               float* __restrict__ out, int B, int D, int H, int W, int Cin, int Cout) {
+  extern __shared__ float s_w[];  // [27*Cin][Cout] (transposed so a thread's 4 channels are contiguous)
+  const int K = 27 * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;       // k = tap * Cin + ci
+    const int tap = k / Cin, ci = k - tap * Cin;
+    s_w[i] = w[((int64_t)co * Cin + ci) * 27 + tap];  // PyTorch layout [Cout][Cin][3][3][3]
+  }
+  __syncthreads();
+  const int quads = Cout >> 2;
+  const int64_t total = (int64_t)B * D * H * W * quads;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(idx % quads);
+    int64_t v = idx / quads;
+    const int wz = (int)(v % W); v /= W;
+    const int hy = (int)(v % H); v /= H;
+    const int dz = (int)(v % D);
+    const int b = (int)(v / D);
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + cq);
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int d = dz + kd - 1;
+      if (d < 0 || d >= D) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = hy + kh - 1;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = wz + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const float* xp = x + ((((int64_t)b * D + d) * H + h) * W + ww) * Cin;
+          const int tap = kd * 9 + kh * 3 + kw;
+          for (int ci = 0; ci < Cin; ++ci) {
+            const float xv = __ldg(xp + ci);
+            const float4 wv = *reinterpret_cast<const float4*>(s_w + (tap * Cin + ci) * Cout + 4 * cq);
+            acc.x = fmaf(xv, wv.x, acc.x);
+            acc.y = fmaf(xv, wv.y, acc.y);
+            acc.z = fmaf(xv, wv.z, acc.z);
+            acc.w = fmaf(xv, wv.w, acc.w);
+          }
+        }
+      }
+    }
+    reinterpret_cast<float4*>(out)[idx] = acc;
+  }
+}
+
+int enc_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int D, int H, int W, int Cin,
+                int Cout, cudaStream_t stream) {
+  RALD_REQUIRE(Cin >= 1 && Cin <= 4, "conv_in: Cin=%d must be in [1, 4]", Cin);
+  RALD_REQUIRE(Cout % 4 == 0 && Cout <= 256, "conv_in: Cout=%d must be a multiple of 4 <= 256", Cout);
+  const int smem = 27 * Cin * Cout * sizeof(float);
+  static int configured = 48 * 1024;
+  if (smem > configured) {
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int64_t total = (int64_t)B * D * H * W * (Cout / 4);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)device_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  conv_in_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x, w, bias, out, B, D, H, W, Cin, Cout);
+  RALD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[b][g] = {sum, sum of squares} (double, accumulated with atomics; zeroed here by a
+// memset node issued before the kernel). grid = (chunks, B).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, int64_t V, int C, int groups, int64_t vox_per_block,
+                double* __restrict__ stats) {
+  __shared__ float s_sum[256];
+  __shared__ float s_sq[256];
+  const int quads = C >> 2;             // float4 columns per voxel (16 / 32 / 64)
+  const int vlanes = blockDim.x / quads;
+  const int cq = threadIdx.x % quads;
+  const int vl = threadIdx.x / quads;
+  const int b = blockIdx.y;
+  const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v1 = (v0 + vox_per_block) < V ? (v0 + vox_per_block) : V;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  __syncthreads();
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vl < vlanes) {
+    const float4* xb = reinterpret_cast<const float4*>(x + (int64_t)b * V * C);
+    for (int64_t v = v0 + vl; v < v1; v += vlanes) {
+      const float4 a = xb[v * quads + cq];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
+    }
+    atomicAdd(&s_sum[4 * cq + 0], s.x); atomicAdd(&s_sum[4 * cq + 1], s.y);
+    atomicAdd(&s_sum[4 * cq + 2], s.z); atomicAdd(&s_sum[4 * cq + 3], s.w);
+    atomicAdd(&s_sq[4 * cq + 0], q.x); atomicAdd(&s_sq[4 * cq + 1], q.y);
+    atomicAdd(&s_sq[4 * cq + 2], q.z); atomicAdd(&s_sq[4 * cq + 3], q.w);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int cpg = C / groups;
+    double gs = 0.0, gq = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      gs += (double)s_sum[threadIdx.x * cpg + j];
+      gq += (double)s_sq[threadIdx.x * cpg + j];
+    }
+    atomicAdd(&stats[((int64_t)b * groups + threadIdx.x) * 2 + 0], gs);
+    atomicAdd(&stats[((int64_t)b * groups + threadIdx.x) * 2 + 1], gq);
+  }
+}
+
+int gn_stats(const float* x, int B, int64_t V, int C, int groups, double* stats, cudaStream_t stream) {
+  RALD_REQUIRE(C % 4 == 0 && C <= 256 && C >= 4 && 256 % (C / 4) == 0, "gn_stats: C=%d unsupported", C);
+  RALD_REQUIRE(groups > 0 && groups <= 256 && C % groups == 0, "gn_stats: groups=%d does not divide C=%d", groups, C);
+  RALD_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, stream));
+  // ~16 K elements per thread block keeps >= 2 waves at the large levels and one block at the small ones
+  int64_t vox_per_block = (16384 * 4) / C;
+  if (vox_per_block < 1) vox_per_block = 1;
+  const int64_t chunks = (V + vox_per_block - 1) / vox_per_block;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, V, C, groups, vox_per_block, stats);
+  RALD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm apply: mode 0 = GN + swish, 1 = GN only, 2 = cast only (stats/gamma/beta unused). Output bf16.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int64_t V, int C, int groups,
+                float eps, int mode, int64_t quads_per_block) {
+  __shared__ float s_a[256];
+  __shared__ float s_d[256];
+  const int b = blockIdx.y;
+  if (mode != 2) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int cpg = C / groups;
+      const int g = c / cpg;
+      const double n = (double)V * cpg;
+      const double mean = stats[((int64_t)b * groups + g) * 2 + 0] / n;
+      double var = stats[((int64_t)b * groups + g) * 2 + 1] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float a = rstd * gamma[c];
+      s_a[c] = a;
+      s_d[c] = beta[c] - (float)mean * a;
+    }
+    __syncthreads();
+  }
+  const int quads = C >> 2;
+  const int64_t nq = V * quads;  // float4s of this frame
+  const int64_t q0 = (int64_t)blockIdx.x * quads_per_block;
+  const int64_t q1 = (q0 + quads_per_block) < nq ? (q0 + quads_per_block) : nq;
+  const float4* xb = reinterpret_cast<const float4*>(x + (int64_t)b * V * C);
+  uint2* ob = reinterpret_cast<uint2*>(out + (int64_t)b * V * C);
+  for (int64_t i = q0 + threadIdx.x; i < q1; i += blockDim.x) {
+    float4 v = xb[i];
+    if (mode != 2) {
+      const int c = (int)(i % quads) * 4;
+      v.x = fmaf(v.x, s_a[c + 0], s_d[c + 0]);
+      v.y = fmaf(v.y, s_a[c + 1], s_d[c + 1]);
+      v.z = fmaf(v.z, s_a[c + 2], s_d[c + 2]);
+      v.w = fmaf(v.w, s_a[c + 3], s_d[c + 3]);
+      if (mode == 0) {
+        v.x = v.x / (1.0f + __expf(-v.x));
+        v.y = v.y / (1.0f + __expf(-v.y));
+        v.z = v.z / (1.0f + __expf(-v.z));
+        v.w = v.w / (1.0f + __expf(-v.w));
+      }
+    }
+    ob[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+int gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out_bf16, int B,
+             int64_t V, int C, int groups, float eps, int mode, cudaStream_t stream) {
+  RALD_REQUIRE(C % 4 == 0 && C <= 256, "gn_apply: C=%d unsupported", C);
+  RALD_REQUIRE(mode >= 0 && mode <= 2, "gn_apply: mode %d", mode);
+  RALD_REQUIRE(mode == 2 || (groups > 0 && C % groups == 0), "gn_apply: groups=%d does not divide C=%d", groups, C);
+  const int64_t nq = V * (C / 4);
+  const int64_t quads_per_block = 256 * 16;
+  const int64_t chunks = (nq + quads_per_block - 1) / quads_per_block;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), V, C,
+                                            groups == 0 ? 1 : groups, eps, mode, quads_per_block);
+  RALD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AttnBlock core: qkv fp32 [B*n, 3C] (q | k | v), one head of width C over the n <= 64 voxels of a frame.
+// out bf16 [B*n, C] = softmax(q k^T / sqrt(C)) v. One CTA per frame; everything in shared memory, fp32.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+enc_attn_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n, int C, float scale) {
+  extern __shared__ float sm[];
+  const int ldc = C + 4;  // pad: rows start on different banks
+  float* s_q = sm;
+  float* s_k = s_q + 64 * ldc;
+  float* s_v = s_k + 64 * ldc;
+  float* s_p = s_v + 64 * ldc;  // [64][65]
+  const int b = blockIdx.x;
+  const float* base = qkv + (int64_t)b * n * 3 * C;
+  const int quads = C >> 2;
+  for (int i = threadIdx.x; i < n * 3 * quads; i += blockDim.x) {
+    const int row = i / (3 * quads);
+    const int col4 = i - row * 3 * quads;
+    const float4 v = reinterpret_cast<const float4*>(base + (int64_t)row * 3 * C)[col4];
+    const int which = col4 / quads, c = (col4 - which * quads) * 4;
+    float* dst = (which == 0 ? s_q : which == 1 ? s_k : s_v) + row * ldc + c;
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+  __syncthreads();
+  // scores: thread (i, jq) computes 16 columns of row i
+  {
+    const int i = threadIdx.x >> 2, jq = threadIdx.x & 3;
+    if (i < n) {
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = jq * 16 + jj;
+        float acc = 0.f;
+        if (j < n) {
+          const float4* qa = reinterpret_cast<const float4*>(s_q + i * ldc);
+          const float4* kb = reinterpret_cast<const float4*>(s_k + j * ldc);
+          for (int c = 0; c < quads; ++c) {
+            const float4 a = qa[c], k4 = kb[c];
+            acc = fmaf(a.x, k4.x, acc); acc = fmaf(a.y, k4.y, acc);
+            acc = fmaf(a.z, k4.z, acc); acc = fmaf(a.w, k4.w, acc);
+          }
+          acc *= scale;
+        } else {
+          acc = -INFINITY;
+        }
+        s_p[i * 65 + j] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // softmax over j: 4 threads per row
+  {
+    const int i = threadIdx.x >> 2, jq = threadIdx.x & 3;
+    const bool ok = i < n;  // rows >= n hold no data; every lane still takes part in the shuffles
+    float e[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      e[jj] = ok ? s_p[i * 65 + jq * 16 + jj] : 0.f;
+      mx = fmaxf(mx, e[jj]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      e[jj] = expf(e[jj] - mx);
+      sum += e[jj];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    if (ok) {
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) s_p[i * 65 + jq * 16 + jj] = e[jj] * inv;
+    }
+  }
+  __syncthreads();
+  // out[i][c] = sum_j p[i][j] v[j][c]; thread handles channel c for 64/(256/C)... generic strided loop
+  for (int idx = threadIdx.x; idx < n * C; idx += blockDim.x) {
+    const int i = idx / C, c = idx - i * C;
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc = fmaf(s_p[i * 65 + j], s_v[j * ldc + c], acc);
+    out[((int64_t)b * n + i) * C + c] = __float2bfloat16_rn(acc);
+  }
+}
+
+int enc_attn(const float* qkv, void* out_bf16, int B, int n, int C, cudaStream_t stream) {
+  RALD_REQUIRE(n >= 1 && n <= 64, "enc_attn: %d voxels per frame (the kernel handles <= 64)", n);
+  RALD_REQUIRE(C % 4 == 0 && C <= 256, "enc_attn: C=%d unsupported", C);
+  const int smem = (3 * 64 * (C + 4) + 64 * 65) * sizeof(float);
+  static int configured = 48 * 1024;
+  if (smem > configured) {
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  enc_attn_kernel<<<B, 256, smem, stream>>>(qkv, reinterpret_cast<__nv_bfloat16*>(out_bf16), n, C,
+                                            1.0f / sqrtf((float)C));
+  RALD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rald

@@ -46,4 +46,14 @@ int ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, const
              const float* ln_b, const void* kprime_bf16, const float* vprime, const float* c0, const float* freq24,
              float* logits, int dim, int n_latents, cudaStream_t stream);
 
+// conv3d.cu / enc_misc.cu ------------------------------------------------------------------------------
+int conv3d_cl(const void* x_bf16, const void* w_packed, int w_rows, const float* bias, const float* resid, float* out,
+              int B, int D, int H, int W, int Cin, int Cout, int stride, cudaStream_t stream);
+int enc_conv_in(const float* x, const float* w, const float* bias, float* out, int B, int D, int H, int W, int Cin,
+                int Cout, cudaStream_t stream);
+int gn_stats(const float* x, int B, int64_t V, int C, int groups, double* stats, cudaStream_t stream);
+int gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out_bf16, int B,
+             int64_t V, int C, int groups, float eps, int mode, cudaStream_t stream);
+int enc_attn(const float* qkv, void* out_bf16, int B, int n, int C, cudaStream_t stream);
+
 }  // namespace rald
