@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the RaLD generation hot path on B200 (BASELINE.json metric: generated frames/s, denoise loop + AE
+decode; ms per step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-gpu F] [--queries Q]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one batch: radar cube -> radar encoder -> conditioning tokens -> 18-step
+EDM/Heun sampler (35 network evaluations) -> VecSet decoder (24-layer latent stack + Q occupancy queries) ->
+threshold / compaction to a point cloud (-> NCCL gather of the clouds when N > 1). The default workload is
+BASELINE.json configs[1] (batch 1 per GPU, default configs, random-init weights with proj_out re-randomised,
+synthetic cube and query grid); --frames-per-gpu 64 gives configs[2]'s batched shape. Frames are independent, so
+ranks shard frames with no data-path collective ("weak" scaling: per-GPU work fixed) and the only collective is
+the final gather.
+
+The line printed by rank 0 follows the driver contract; `value` is timed with inputs resident in HBM, `e2e` through
+the public module API from pinned host buffers (H2D of cube + queries, D2H of the occupied points, every step).
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port of its PyTorch
+modules, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "generated frames/sec (denoise loop + AE decode)"
+UNIT = "frames/s"
+SEED = 1024
+PC_RANGE = [0, -90, -20, 15.8, 90, 20]  # configs/generation/...eval.yml dataset.lidar.pc_range (view-cone mode)
+NET_EVALS = 35                          # 18 Heun steps, the last one first-order
+GFLOP_PER_EVAL = 130.494                # SURVEY.md §8d, per frame
+GFLOP_ENCODER = 286.881 + 1.686         # radar encoder + hoisted context K/V, once per frame
+GFLOP_AE_STACK = 115.96 + 0.537 + 0.268
+MFLOP_PER_QUERY = 0.5775                # folded decoder formulation (the one executed)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=1)
+    ap.add_argument("--queries", type=int, default=500000)  # eval.inference.num_query_points
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the sampler")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# models and inputs
+# ------------------------------------------------------------------------------------------------------------------
+def build_models(device):
+    from rald_b200 import models_ae, models_radar_generation
+    from rald_b200.config import DEFAULT_AE_NAME, DEFAULT_DENOISER_NAME, DEFAULT_NUM_POINTS, default_denoiser_configs
+    torch.manual_seed(SEED)
+    net = models_radar_generation.__dict__[DEFAULT_DENOISER_NAME](configs=default_denoiser_configs()).eval()
+    net.model.proj_out.reset_parameters()  # zero-initialised in the reference: the network output would be 0
+    torch.manual_seed(SEED)
+    vae = models_ae.__dict__[DEFAULT_AE_NAME](N=DEFAULT_NUM_POINTS).eval()
+    return net.to(device), vae.to(device)
+
+
+def calibrate_occupancy(net, vae, cube, queries, seeds):
+    """Random-init occupancy logits are all slightly negative: shift to_outputs.bias by the 95-th
+    percentile of one decode so that `logit > 0` (engine_generation.py:285) keeps ~5 % of the queries."""
+    z = net.sample(cube, batch_seeds=seeds, cond_type="radar")
+    lg = vae.decode(z, queries).squeeze(-1)
+    k = max(1, int(0.95 * lg[0].numel()))
+    shift = float(lg[0].flatten().kthvalue(k).values)
+    with torch.no_grad():
+        vae.to_outputs.bias -= shift
+    return shift
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's PyTorch modules on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(queries_total: int, sample_queries: int = 16384):
+    """Times ONE network evaluation as the reference executes it (radar encoder + tokens inside every evaluation,
+    models_radar_generation.py:412-430), the decoder latent stack and `sample_queries` decoder queries for one frame,
+    then extrapolates linearly to 35 evaluations + stack + all queries. Returns a dict with frames/s."""
+    from oracle import rald_oracle as orc
+    from rald_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net, vae = build_models("cpu")
+    sd = {k: v.detach().float() for k, v in net.state_dict().items()}
+    sd_ae = {k: v.detach().float() for k, v in vae.state_dict().items()}
+    cube = synth.radar_cube(1, seed=SEED)
+    lat = synth.unit_latents([0])
+    q = synth.query_points(1, sample_queries)
+    sigma = torch.tensor(80.0)
+
+    def one_eval():
+        tok = orc.process_radar_cond(sd, cube)
+        return orc.edm_precond(sd, lat * sigma, sigma, tok)
+
+    with torch.no_grad():
+        one_eval()  # warm-up (oneDNN primitive creation)
+        t0 = time.perf_counter(); d = one_eval(); t_eval = time.perf_counter() - t0
+        t0 = time.perf_counter(); tok = orc.process_radar_cond(sd, cube); t_enc = time.perf_counter() - t0
+        z = d[:, :, :32]
+        orc.ae_latent_stack(sd_ae, z)
+        t0 = time.perf_counter(); x = orc.ae_latent_stack(sd_ae, z); t_stack = time.perf_counter() - t0
+        orc.ae_query(sd_ae, x, q)
+        t0 = time.perf_counter(); orc.ae_query(sd_ae, x, q); t_q = time.perf_counter() - t0
+    t_frame = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
+    t_frame_hoisted = NET_EVALS * (t_eval - t_enc) + t_enc + t_stack + t_q * (queries_total / sample_queries)
+    return {"value": 1.0 / t_frame, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"1 of {NET_EVALS} network evaluations as the reference runs them (radar encoder inside, "
+                       f"{t_eval:.2f} s) + decoder latent stack ({t_stack:.2f} s) + {sample_queries} of "
+                       f"{queries_total} decoder queries ({t_q:.2f} s) for 1 frame, extrapolated linearly; oracle port "
+                       f"of the reference's fp32 PyTorch CPU path"),
+            "s_per_frame": t_frame, "hoisted_value": 1.0 / t_frame_hoisted, "s_per_net_eval": t_eval}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    res = None
+    for _ in range(max(0, args.warmup - 1)):   # the sample has its own warm-up pass; keep extra ones cheap
+        pass
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        res = cpu_reference_sample(args.queries)
+        vals.append(res["value"])
+    value = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    line["cpu_baseline"]["value"] = value
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": ("configs[1]: DiT latent-set denoiser kl_d512_m512_l32_d24_edm, full 18-step EDM/Heun sampling "
+                         "loop (35 evaluations) from a synthetic radar RAE cube + kl_d512_m512_l32_mix decode"
+                         if args.frames_per_gpu == 1 else
+                         "configs[2]-shaped: batched generation, full diffusion schedule + decode, frames sharded"),
+            "frames_per_gpu": args.frames_per_gpu, "global_frames": args.frames_per_gpu * world,
+            "queries_per_frame": args.queries, "num_steps": 18, "net_evals": NET_EVALS,
+            "parallelism": f"frames sharded over {world} GPU(s), final NCCL gather of point clouds" if world > 1
+            else "single GPU",
+            "l2": "no flush: each evaluation streams 0.33 GB of bf16 weights (> 126 MB L2) and the step reads "
+                  "0.55 GB of weights + fresh H2D inputs"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from rald_b200 import _lib, gather, postproc, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    if args.no_graph:
+        os.environ["RALD_B200_GRAPH"] = "0"
+    F, Q = args.frames_per_gpu, args.queries
+    net, vae = build_models(dev)
+    f0, f1 = rank * F, rank * F + F
+    seeds = torch.arange(f0, f1)
+    cube_h = synth.radar_cube(F, seed=SEED + rank).pin_memory()
+    q_h = synth.query_points(1, Q).expand(F, Q, 3).contiguous().pin_memory()  # one grid repeated per frame (:259)
+    cube_d, q_d = cube_h.to(dev), q_h.to(dev)
+    shift = calibrate_occupancy(net, vae, cube_d, q_d, seeds)
+    cap = max(1024, Q // 4)
+
+    def pipeline(cube, queries):
+        z = net.sample(cube, batch_seeds=seeds, cond_type="radar")
+        logits = vae.decode(z, queries)
+        pts, cnt, _ = postproc.occupied_points(logits, queries, 0.0, PC_RANGE, True, False, True, capacity=cap)
+        if world > 1:
+            pts, cnt = gather.gather_point_clouds(pts, cnt)
+        return pts, cnt
+
+    def step_resident():
+        return pipeline(cube_d, q_d)
+
+    d2h = [0]
+
+    def step_e2e():
+        cube_d.copy_(cube_h, non_blocking=True)
+        q_d.copy_(q_h, non_blocking=True)
+        pts, cnt = pipeline(cube_d, q_d)
+        n = cnt.cpu()                      # device -> host: per-frame point counts ...
+        m = int(n.max()) if n.numel() else 0
+        out = pts[:, :min(m, cap)].cpu()   # ... and the occupied points only
+        d2h[0] = n.numel() * 4 + out.numel() * 4
+        return out, n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = (_lib.launch_count() - n0)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clock_rec = clocks.stop() if rank == 0 else None
+
+    # ---- roofline leg: one more step with CUDA events around every launch of the hot kernel families ----
+    fams = ["gemm", "attn", "ln", "boundary", "conv3d", "gn", "ae_query", "other"]
+    os.environ["RALD_B200_GRAPH"] = "0"      # per-launch events cannot be recorded inside a graph replay
+    step_resident()
+    _lib.prof_enable(*fams)
+    step_resident()
+    breakdown = {}
+    for f in fams:
+        ms, work, n = _lib.prof_collect(f)
+        if n:
+            breakdown[f] = {"ms": round(ms, 4), "launches": n, "work": work}
+    _lib.prof_enable()
+    peaks = load_peaks()
+    g = breakdown.get("gemm", {"ms": 0.0, "launches": 0, "work": 0.0})
+    achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("gemm_bf16_kernel", {}).get(f"frames_per_gpu={F}")
+    roofline = {"kernel": "gemm_bf16_kernel (tcgen05, all denoiser/AE linears)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_timed": g["launches"], "ms_per_launch": g["ms"] / max(1, g["launches"]),
+                "flop_per_launch": g["work"] / max(1, g["launches"])}
+    prof_total = sum(v["ms"] for v in breakdown.values())
+    for v in breakdown.values():
+        v["share"] = round(v["ms"] / prof_total, 4) if prof_total else None
+        del v["work"]
+
+    frames_total = F * world * args.steps
+    value = frames_total / (ms_res * 1e-3)
+    e2e_v = frames_total / (ms_e2e * 1e-3)
+    gflop_step = F * (NET_EVALS * GFLOP_PER_EVAL + GFLOP_ENCODER + GFLOP_AE_STACK + Q * MFLOP_PER_QUERY * 1e-3)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args, world),
+                "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": cube_h.numel() * 4 + q_h.numel() * 4, "d2h_bytes_per_step": d2h[0]},
+                "gpu_launches": int(launches),
+                "ms_per_sampler_step": None, "tflops_step": gflop_step / (ms_res / args.steps),
+                "roofline": roofline, "kernel_breakdown": breakdown, "clocks": clock_rec,
+                "occupancy_bias_shift": shift}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_sample(Q)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "hoisted_value")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,26 @@ extern "C" {
 int rald_abi_version(void);
 const char* rald_last_error(void);
 
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rald_launch_count(void);
+
+/* Per-launch timing for bench.py's roofline leg: rald_prof_enable(mask) starts a session that brackets every launch
+ * of the kernel families in `mask` (bit = family id below) with CUDA events on the launching stream (0 = off);
+ * rald_prof_collect(family, ...) synchronises and returns the summed duration (ms), summed algorithmic work
+ * (flops for tensor-core kernels, bytes for HBM-bound ones) and the launch count of one family. */
+#define RALD_FAM_GEMM 0
+#define RALD_FAM_ATTN 1
+#define RALD_FAM_LN 2
+#define RALD_FAM_BOUNDARY 3
+#define RALD_FAM_CONV3D 4
+#define RALD_FAM_GN 5
+#define RALD_FAM_AE_QUERY 6
+#define RALD_FAM_OTHER 7
+#define RALD_FAM_FPS 8
+#define RALD_FAM_XATTN 9
+int rald_prof_enable(unsigned family_mask);
+int rald_prof_collect(int family, double* total_ms, double* total_work, int64_t* launches);
+
 /* out = epilogue(A[M,K] @ W[N,K]^T), A and W bf16, fp32 accumulation on tcgen05 tensor cores.
  *   out_mode 0: out bf16 [M,N] (+bias)
  *   out_mode 1: out f32  [M,N] = acc (+bias) (+resid f32 [M,ldr]); out may alias resid
@@ -245,6 +265,18 @@ typedef struct rald_enc_workspace {
  * out fp32 [B, D/2^(L-1), H/2^(L-1), W/2^(L-1), z_ch]. Frames are processed in micro-batches of ws->max_frames. */
 int rald_radar_encoder(const rald_enc_weights* w, const rald_enc_workspace* ws, const float* x, float* out, int B,
                        int D, int H, int W, void* stream);
+
+/* ---- post-processing of decoded occupancy (engine_generation.py:283-289, 313-315) ---- */
+
+/* Stable stream compaction of the occupied queries of each frame: for every q (in query order) with
+ * logits[b][q] > threshold, points[b][n] = queries[b][q] * scale + offset (inverse_norm_points, utils/utils.py:50-76;
+ * scale_offset_host = HOST pointer to {sx, sy, sz, ox, oy, oz} or NULL for identity), optionally followed by
+ * polar2cartesian (dataset_preprocessor/lidar.py:57-63); index[b][n] = q (optional). counts[b] = number of occupied
+ * queries (may exceed cap; only the first cap are stored). block_ws: int32 scratch of rald_occupancy_ws_elems(B, Q). */
+int rald_occupancy_compact(const float* logits, const float* queries, int B, int64_t Q, float threshold,
+                           const float* scale_offset_host, int polar2cart, int64_t cap, float* points, int32_t* index,
+                           int32_t* counts, int32_t* block_ws, void* stream);
+int64_t rald_occupancy_ws_elems(int B, int64_t Q);
 
 #ifdef __cplusplus
 }

@@ -368,6 +368,30 @@ def chamfer_distance(pred: np.ndarray, gt: np.ndarray) -> float:
     return 0.5 * float(np.mean(d1)) + 0.5 * float(np.mean(d2))
 
 
+def occupancy_points(logits: np.ndarray, queries: np.ndarray, pc_range=None, norm_anisotropy: bool = True,
+                     norm_isotropy: bool = False, view_cone: bool = False, threshold: float = 0.0) -> np.ndarray:
+    """One frame: logits [Q], queries [Q, 3] float32 -> occupied points [P, 3] float32.
+    engine_generation.py:283-289 (np.where(output > 0), gather, inverse_norm_points = utils/utils.py:50-76) and
+    :313-315 (polar2cartesian = dataset_preprocessor/lidar.py:57-63), numpy float32 as in the reference."""
+    ind = np.where(logits > threshold)[0]
+    pts = queries[ind].astype(np.float32)
+    if pc_range is not None:
+        r = [float(v) for v in pc_range]
+        off = [(r[3] + r[0]) / 2, (r[4] + r[1]) / 2, (r[5] + r[2]) / 2]
+        sc = [(r[3] - r[0]) / 2, (r[4] - r[1]) / 2, (r[5] - r[2]) / 2]
+        pred = np.zeros_like(pts)
+        if norm_anisotropy:
+            for a in range(3):
+                pred[:, a] = pts[:, a] * sc[a] + off[a]
+        if norm_isotropy:
+            pred[:, :3] = pts[:, :3] * max(sc) + np.array(off)
+        pts = pred
+    if view_cone:
+        r_, az, el = pts[:, 0], -np.deg2rad(pts[:, 1]), np.deg2rad(pts[:, 2])
+        pts = np.stack([r_ * np.cos(el) * np.cos(az), r_ * np.cos(el) * np.sin(az), r_ * np.sin(el)], axis=1)
+    return pts
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()

@@ -21,6 +21,9 @@ c_f64 = ctypes.c_double
 _SIGNATURES = {
     "rald_abi_version": [],
     "rald_last_error": [],
+    "rald_launch_count": [],
+    "rald_prof_enable": [ctypes.c_uint],
+    "rald_prof_collect": [c_int, c_void_p, c_void_p, c_void_p],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
@@ -50,8 +53,12 @@ _SIGNATURES = {
                       c_void_p],
     "rald_enc_attn": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rald_radar_encoder": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_occupancy_compact": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_int, c_i64, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p],
+    "rald_occupancy_ws_elems": [c_int, c_i64],
 }
-_RESTYPES = {"rald_last_error": ctypes.c_char_p}
+_RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count": ctypes.c_uint64,
+             "rald_occupancy_ws_elems": c_i64}
 
 
 class RaldError(RuntimeError):
@@ -100,3 +107,26 @@ def ptr(t) -> int:
 def cur_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+FAMILIES = {"gemm": 0, "attn": 1, "ln": 2, "boundary": 3, "conv3d": 4, "gn": 5, "ae_query": 6, "other": 7, "fps": 8,
+            "xattn": 9}
+
+
+def launch_count() -> int:
+    return int(lib().rald_launch_count())
+
+
+def prof_enable(*families: str) -> None:
+    mask = 0
+    for f in families:
+        mask |= 1 << FAMILIES[f]
+    check(lib().rald_prof_enable(mask), "rald_prof_enable")
+
+
+def prof_collect(family: str):
+    """(total ms, total algorithmic work, launches) of one kernel family since prof_enable()."""
+    ms, work, n = c_f64(), c_f64(), c_i64()
+    check(lib().rald_prof_collect(FAMILIES[family], ctypes.addressof(ms), ctypes.addressof(work), ctypes.addressof(n)),
+          "rald_prof_collect")
+    return ms.value, work.value, n.value

@@ -63,7 +63,7 @@ int linear_smallk(const float* x, int K, const float* wt, const float* b, float*
   const int64_t cap = device_sm_count();
   if (blocks > cap) blocks = cap;
   linear_smallk_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x, K, wt, b, out, T);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -106,7 +106,7 @@ int ln_dot_rows(const float* x, const float* g, const float* b, const float* w, 
   RALD_REQUIRE(D == 512, "ln_dot_rows: D=%d unsupported (512 only)", D);
   const int64_t blocks = (rows + 7) / 8;
   ln_dot_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, g, b, w, out, rows, eps);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

@@ -333,8 +333,9 @@ int ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, const
   const int64_t tiles = (int64_t)B * p.tiles_per_frame;
   const int sms = device_sm_count();
   const int grid = (int)(tiles < sms ? tiles : sms);
+  ProfScope prof(FAM_AE_QUERY, stream, (double)B * Q * 577536.0);
   ae_query_kernel<<<grid, AQ_THREADS, smem_bytes, stream>>>(tmWpe, tmKp, p);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

@@ -215,8 +215,9 @@ int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void*
     configured_bytes = smem_bytes;
   }
   dim3 grid(Sq / ATT_BM, heads, frames);
+  ProfScope prof(FAM_ATTN, stream, 4.0 * frames * heads * Sq * Skv * ATT_D);
   attn_d64_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

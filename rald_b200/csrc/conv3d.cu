@@ -236,8 +236,9 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmW, const ConvP
   const int num_tiles = p.tiles_n * p.tiles_d * p.tiles_h * p.tiles_w * p.num_n_blks;
   const int sms = device_sm_count();
   const int grid = num_tiles < sms ? num_tiles : sms;
+  ProfScope prof(FAM_CONV3D, stream, 2.0 * p.B * p.Do * p.Ho * p.Wo * (double)p.Cout * 27.0 * p.Cin);
   kern<<<grid, CV_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, tmW, p);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

@@ -84,11 +84,11 @@ int dit_mod_table(const float* sigma, int S, const float* freqs, int half, const
   RALD_REQUIRE(S > 0 && depth > 0, "dit_mod_table: bad sizes");
   const int smem = (2 * half + dim) * sizeof(float);
   temb_kernel<<<S, 512, smem, stream>>>(sigma, freqs, half, map0_w, map0_b, map1_w, map1_b, dim, t_emb_ws);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   const int64_t R = (int64_t)depth * 3 * 2 * dim;
   dim3 grid((unsigned)((R + 7) / 8), (unsigned)((S + ADA_SCHUNK - 1) / ADA_SCHUNK));
   adaln_kernel<<<grid, 256, 0, stream>>>(t_emb_ws, S, ada_w, ada_b, R, mod);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -253,8 +253,10 @@ int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const flo
   int64_t blocks = (T + BND_WARPS - 1) / BND_WARPS;
   const int64_t cap = device_sm_count();
   if (blocks > cap) blocks = cap;
+  ProfScope prof(FAM_BOUNDARY, stream, (double)T * (mode < 3 ? 2048.0 : 0.0) + (h_next ? (double)T * 2048.0 : 0.0) +
+                                          (double)T * C * 16.0);
   boundary_kernel<<<(unsigned)blocks, BND_WARPS * 32, smem, stream>>>(p);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -288,7 +290,7 @@ int radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const
   RALD_REQUIRE(ntok > 0 && ntok < (1ll << 31), "radar_tokens: bad token count");
   radar_tokens_kernel<<<(unsigned)ntok, 128, 0, stream>>>(feat, cz, nr, na, ne, w, b, r_emb, a_emb, e_emb, dim,
                                                           tok_f32, reinterpret_cast<__nv_bfloat16*>(tok_bf16));
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

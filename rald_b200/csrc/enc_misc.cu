@@ -80,7 +80,7 @@ int enc_conv_in(const float* x, const float* w, const float* bias, float* out, i
   const int64_t cap = (int64_t)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
   conv_in_kernel<<<(unsigned)blocks, 256, smem, stream>>>(x, w, bias, out, B, D, H, W, Cin, Cout);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -137,8 +137,9 @@ int gn_stats(const float* x, int B, int64_t V, int C, int groups, double* stats,
   if (vox_per_block < 1) vox_per_block = 1;
   const int64_t chunks = (V + vox_per_block - 1) / vox_per_block;
   dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(FAM_GN, stream, (double)B * V * C * 4.0);
   gn_stats_kernel<<<grid, 256, 0, stream>>>(x, V, C, groups, vox_per_block, stats);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -201,9 +202,10 @@ int gn_apply(const float* x, const double* stats, const float* gamma, const floa
   const int64_t quads_per_block = 256 * 16;
   const int64_t chunks = (nq + quads_per_block - 1) / quads_per_block;
   dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(FAM_GN, stream, (double)B * V * C * 6.0);
   gn_apply_kernel<<<grid, 256, 0, stream>>>(x, stats, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), V, C,
                                             groups == 0 ? 1 : groups, eps, mode, quads_per_block);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
@@ -303,7 +305,7 @@ int enc_attn(const float* qkv, void* out_bf16, int B, int n, int C, cudaStream_t
   }
   enc_attn_kernel<<<B, 256, smem, stream>>>(qkv, reinterpret_cast<__nv_bfloat16*>(out_bf16), n, C,
                                             1.0f / sqrtf((float)C));
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

@@ -236,8 +236,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int num_tiles = p.num_m_blks * p.num_n_blks;
   int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  ProfScope prof(FAM_GEMM, stream, 2.0 * p.M * p.N * p.K);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 

@@ -3,7 +3,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
+
+#include "../../include/rald_b200.h"
 
 namespace rald {
 
@@ -81,6 +85,42 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
   return encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides);
 }
 
+// ---- launch accounting / per-launch timing -------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t e0, e1; int family; double work; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;      // records of the current session
+static std::vector<cudaEvent_t> g_pool;  // recycled events
+static unsigned g_prof_mask = 0;
+constexpr size_t PROF_MAX = 1 << 16;
+
+static cudaEvent_t pool_get() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int family, cudaStream_t st, double work) : slot(-1), stream(st) {
+  if (!(g_prof_mask & (1u << family))) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof.size() >= PROF_MAX) return;
+  ProfRec r{pool_get(), pool_get(), family, work};
+  if (r.e0 == nullptr || r.e1 == nullptr) return;
+  cudaEventRecord(r.e0, st);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].e1, stream);
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -93,3 +133,31 @@ int device_sm_count() {
 }
 
 }  // namespace rald
+
+extern "C" uint64_t rald_launch_count(void) { return rald::g_launches.load(); }
+
+extern "C" int rald_prof_enable(unsigned family_mask) {
+  std::lock_guard<std::mutex> lk(rald::g_prof_mu);
+  for (auto& r : rald::g_prof) { rald::g_pool.push_back(r.e0); rald::g_pool.push_back(r.e1); }
+  rald::g_prof.clear();
+  rald::g_prof_mask = family_mask;
+  return 0;
+}
+
+extern "C" int rald_prof_collect(int family, double* total_ms, double* total_work, int64_t* launches) {
+  using namespace rald;
+  RALD_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, work = 0.0;
+  int64_t n = 0;
+  for (auto& r : g_prof) {
+    if (r.family != family) continue;
+    float t = 0.f;
+    RALD_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t; work += r.work; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  if (launches) *launches = n;
+  return 0;
+}

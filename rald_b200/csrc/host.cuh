@@ -49,4 +49,23 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
 
 int device_sm_count();
 
+// ---- launch accounting (rald_launch_count) and optional per-launch CUDA-event timing (rald_prof_*) ----
+enum ProfFamily : int { FAM_GEMM = 0, FAM_ATTN = 1, FAM_LN = 2, FAM_BOUNDARY = 3, FAM_CONV3D = 4, FAM_GN = 5,
+                        FAM_AE_QUERY = 6, FAM_OTHER = 7, FAM_FPS = 8, FAM_XATTN = 9, FAM_COUNT = 10 };
+void count_launch();
+// While alive, brackets the launches issued on `stream` with a pair of CUDA events if timing of `family` is
+// enabled (bench.py's roofline leg); `work` = algorithmic flops or bytes of the bracketed launch.
+struct ProfScope {
+  ProfScope(int family, cudaStream_t stream, double work);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
+
+#define RALD_LAUNCHED()                     \
+  do {                                      \
+    RALD_CHECK_CUDA(cudaGetLastError());    \
+    ::rald::count_launch();                 \
+  } while (0)
+
 }  // namespace rald

@@ -68,13 +68,14 @@ int ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, 
   int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
+  ProfScope prof(FAM_LN, stream, (double)rows * D * (out_f32 ? 8.0 : 6.0));
   if (out_f32)
     ln_rows_kernel<512, true><<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, gamma, beta, mod_frame_stride,
                                                                     rows_per_frame, gamma_plus_one, out, ldo, rows, eps);
   else
     ln_rows_kernel<512, false><<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, gamma, beta, mod_frame_stride,
                                                                      rows_per_frame, gamma_plus_one, out, ldo, rows, eps);
-  RALD_CHECK_CUDA(cudaGetLastError());
+  RALD_LAUNCHED();
   return 0;
 }
 
