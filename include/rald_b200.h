@@ -49,7 +49,7 @@ int rald_prof_enable(unsigned family_mask);
 int rald_prof_collect(int family, double* total_ms, double* total_work, int64_t* launches);
 
 /* out = epilogue(A[M,K] @ W[N,K]^T), A and W bf16, fp32 accumulation on tcgen05 tensor cores.
- *   out_mode 0: out bf16 [M,N] (+bias)
+ *   out_mode 0: out bf16 [M,N] (+bias) (+resid f32, added before rounding)
  *   out_mode 1: out f32  [M,N] = acc (+bias) (+resid f32 [M,ldr]); out may alias resid
  *   out_mode 2: GEGLU, out bf16 [M,N/2]; W rows / bias packed in groups of 32 = 16 value + 16 gate rows
  * Replaces nn.Linear (+ residual add / GEGLU) at model/models_radar_generation.py:58-64, 76, 91-95, 113,
@@ -195,6 +195,69 @@ int rald_ln_dot_rows(const float* x, const float* g, const float* b, const float
 int rald_ae_query(const float* queries, int B, int64_t Q, const void* wpe_bf16, const float* pe_bias,
                   const float* ln_g, const float* ln_b, const void* kprime_bf16, const float* vprime,
                   const float* c0, const float* freq24_host, float* logits, int dim, int n_latents, void* stream);
+
+/* ---- VecSet autoencoder, encode side (model/models_ae.py:351-405) ---- */
+
+/* feat bf16 [rows, 64] = [sin(p f) (24), cos(p f) (24), p (3), 0 (13)] of PointEmbed (:128-137) for pts fp32
+ * [B, N, 3]; with idx (int64 [B, M], indices into each cloud) the rows are the gathered points pts[b][idx[b][i]]
+ * (also copied to `gathered` [B, M, 3] when given). freq24_host: HOST pointer, see rald_ae_query. */
+int rald_point_features(const float* pts, const int64_t* idx, int B, int64_t N, int64_t M, const float* freq24_host,
+                        void* feat_bf16, float* gathered, void* stream);
+
+/* Farthest point sampling of M of the N points of each of B clouds (pts fp32 [B, N, 3]) -> out_idx int64 [B, M],
+ * indices INTO EACH CLOUD in selection order. Replaces torch_cluster.fps (model/models_ae.py:243, 368; the global
+ * index of the reference is b*N + out_idx[b][i]). Deterministic: start index 0, squared distance
+ * (dx*dx + dy*dy) + dz*dz in individually rounded fp32 operations, ties -> lowest index. N <= 16384. */
+int rald_fps(const float* pts, int B, int N, int M, int64_t* out_idx, void* stream);
+
+/* DiagonalGaussianDistribution (:141-163): ml fp32 [B*rows, ld] = (mean | logvar) columns [0,C) and [C,2C); writes
+ * mean, clamp(logvar, -30, 20), z = mean + exp(logvar/2) noise (when z != NULL) and kl[b]. */
+int rald_ae_posterior(const float* ml, int64_t ld, const float* noise, int B, int rows_per_frame, int C, float* mean,
+                      float* logvar, float* z, float* kl, void* stream);
+
+typedef struct rald_ae_enc_weights {
+  int32_t dim, n_latents, latent_dim, heads;
+  int32_t query_type;            /* 0 = point (FPS), 1 = learnable, 2 = mix */
+  int32_t stats_rows;            /* 2*latent_dim rounded up to a multiple of 32 */
+  float freq24[24];              /* non-zero entries of point_embed.basis */
+  const void* wpe;               /* bf16 [dim][64] point_embed.mlp.weight zero padded */
+  const float* pe_bias;
+  const void* mix_q;             /* bf16 [n_latents][dim] = to_q(LN(d_latents)) (batch independent) */
+  const void* mix_wkv;           /* bf16 [2*dim][dim] mix_attn_layer.fn.to_kv.weight (k rows, then v rows) */
+  const void* mix_wo;            /* bf16 [dim][dim] */
+  const float* mix_bo;
+  const float* s_latents;        /* fp32 [n_latents][dim] */
+  const void* wproj;             /* bf16 [dim][dim] query_proj */
+  const float* bproj;
+  const float* latents;          /* fp32 [n_latents][dim] (learnable queries) */
+  const float* ca_ln_w; const float* ca_ln_b;      /* cross_attend_blocks.0.norm */
+  const float* ca_lnc_w; const float* ca_lnc_b;    /* cross_attend_blocks.0.norm_context */
+  const void* ca_wq; const void* ca_wkv; const void* ca_wo; const float* ca_bo;
+  const float* ff_ln_w; const float* ff_ln_b;      /* cross_attend_blocks.1 */
+  const void* ff_w1; const float* ff_b1; const void* ff_w2; const float* ff_b2;   /* GEGLU-packed w1/b1 */
+  const void* w_stats;           /* bf16 [stats_rows][dim]: mean_fc rows, logvar_fc rows, zero rows */
+  const float* b_stats;
+} rald_ae_enc_weights;
+
+typedef struct rald_ae_enc_workspace {
+  int32_t max_points, _pad;      /* buffers below are sized for one frame of max_points (n_pad = ceil32) */
+  void* feat;                    /* bf16 [max_points][64] */
+  float* pe32;                   /* fp32 [max_points][dim] */
+  void* pe16;                    /* bf16 [max_points][dim] */
+  void* kbuf;                    /* bf16 [max_points][dim] */
+  void* vt;                      /* bf16 [dim][n_pad] */
+  float* scores;                 /* fp32 [n_latents][n_pad] */
+  void* prob;                    /* bf16 [n_latents][n_pad] */
+  float* x;                      /* fp32 [n_latents][dim] */
+  void* xq; void* att; void* xn; /* bf16 [n_latents][dim] */
+  void* ff;                      /* bf16 [n_latents][4*dim] */
+} rald_ae_enc_workspace;
+
+/* KLAutoEncoder.encode up to the posterior parameters (:351-399): pc fp32 [B, N, 3] -> ml_out fp32
+ * [B*n_latents][stats_rows] = (mean | logvar | padding). fps_idx (int64 [B, n_latents]) receives the sampled indices
+ * for query_type 0 and may be NULL otherwise. */
+int rald_ae_encode_stats(const rald_ae_enc_weights* w, const rald_ae_enc_workspace* ws, const float* pc, int B, int N,
+                         int64_t* fps_idx, float* ml_out, void* stream);
 
 /* ---- radar-cube encoder (model/models_radar_encoder.py) ---- */
 

@@ -146,7 +146,7 @@ def stacked_randn(seeds: Sequence[int], shape: Sequence[int]) -> torch.Tensor:
 
 def edm_sample(sd: SD, latents: torch.Tensor, cond_tokens: torch.Tensor, num_steps: int = 18,
                sigma_min: float = 0.002, sigma_max: float = 80.0, rho: float = 7.0, heads: int = 8,
-               trace: Optional[list] = None) -> torch.Tensor:
+               trace: Optional[list] = None, stop_after: Optional[int] = None) -> torch.Tensor:
     """edm_sampler with S_churn = 0 (gamma = 0, x_hat = x_cur), models_radar_generation.py:235-275.
     `cond_tokens` is process_radar_cond(cube): it depends only on the cube, so evaluating it once instead of
     inside every net() call (reference :414-415) is bit-identical."""
@@ -164,6 +164,8 @@ def edm_sample(sd: SD, latents: torch.Tensor, cond_tokens: torch.Tensor, num_ste
             x_next = x_hat + (t_next - t_cur) * (0.5 * d_cur + 0.5 * d_prime)
         if trace is not None:
             trace.append(x_next.clone())
+        if stop_after is not None and i + 1 >= stop_after:  # tests: only the first steps of the full schedule
+            break
     return x_next
 
 
@@ -396,3 +398,18 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def fps_indices_c(pc: torch.Tensor, m: int) -> torch.Tensor:
+    """Same as fps_indices through the plain-C restatement oracle/fps_oracle.c (fast enough for 64 clouds of 10000
+    points); oracle/build_oracle.py compiles it with gcc -ffp-contract=off."""
+    import ctypes
+    from oracle import build_oracle
+    lib = ctypes.CDLL(str(build_oracle.build()))
+    pts = np.ascontiguousarray(pc.detach().cpu().numpy().astype(np.float32))
+    B, N, _ = pts.shape
+    out = np.zeros((B, m), dtype=np.int64)
+    rc = lib.fps_oracle(pts.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(m),
+                        out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return torch.from_numpy(out)

@@ -53,6 +53,11 @@ _SIGNATURES = {
                       c_void_p],
     "rald_enc_attn": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rald_radar_encoder": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_point_features": [c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rald_fps": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "rald_ae_posterior": [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p],
+    "rald_ae_encode_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "rald_occupancy_compact": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_int, c_i64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p],
     "rald_occupancy_ws_elems": [c_int, c_i64],

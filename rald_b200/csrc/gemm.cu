@@ -35,6 +35,7 @@ struct GemmParams {
   const float* bias;   // [N] or null (GEGLU: packed order, see pack_geglu in the Python runtime)
   const float* resid;  // [M, ldr] fp32 or null
   int64_t ldr;
+  int64_t resid_mod;   // > 0: residual row = row % resid_mod (a [resid_mod, N] table broadcast over frames)
   int M, N, K;
   int num_m_blks, num_n_blks;
 };
@@ -164,19 +165,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
           }
         }
+        if (OUT_MODE != 2 && p.resid != nullptr && row_ok) {
+          const int64_t rrow = p.resid_mod > 0 ? row % p.resid_mod : row;
+          const float4* r4 = reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = r4[j];
+            v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + r.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
+          }
+        }
         if (OUT_MODE == 1) {
           if (row_ok) {
-            if (p.resid != nullptr) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.resid + row * p.ldr + col0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = r4[j];
-                v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + r.x);
-                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
-                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
-                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
-              }
-            }
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -245,12 +247,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
               const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
               cudaStream_t stream) {
+  return gemm_bf16_ex(A, lda, W, ldw, out, ldo, bias, resid, ldr, 0, M, N, K, out_mode, bn_hint, stream);
+}
+
+int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                 const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
+                 cudaStream_t stream) {
   RALD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RALD_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   RALD_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
   RALD_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm: out_mode %d", out_mode);
   RALD_REQUIRE(out_mode != 2 || resid == nullptr, "gemm: GEGLU epilogue takes no residual");
-  RALD_REQUIRE(out_mode == 1 || resid == nullptr, "gemm: residual needs the fp32 output mode");
   RALD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % (out_mode == 1 ? 4 : 8) == 0,
                "gemm: output not 16-byte aligned");
   RALD_REQUIRE(resid == nullptr || ((reinterpret_cast<uintptr_t>(resid) & 15) == 0 && ldr % 4 == 0),
@@ -276,6 +283,7 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
   p.bias = bias;
   p.resid = resid;
   p.ldr = ldr;
+  p.resid_mod = resid_mod;
   p.M = M;
   p.N = N;
   p.K = K;

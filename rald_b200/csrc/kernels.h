@@ -14,6 +14,12 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
               const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
               cudaStream_t stream);
 
+// same with the fp32 residual taken from row (row % resid_mod) of a [resid_mod, N] table when resid_mod > 0;
+// the residual is also honoured by the bf16 output mode (added before rounding).
+int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                 const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
+                 cudaStream_t stream);
+
 // attn.cu ------------------------------------------------------------------------------------------
 // O[f, :, h*64:(h+1)*64] = softmax(Q K^T * scale) V per (frame f, head h); head_dim 64; Skv <= 512.
 // Q rows = frames*Sq, K/V rows = frames*Skv; head h lives at columns [h*64, h*64+64) of each operand.

@@ -193,10 +193,12 @@ class KLAutoEncoder(nn.Module):
 
     def encode(self, pc):
         """pc [B, N, 3] -> (kl [B], z [B, M, latent_dim]) (reference :351-405)."""
+        B, N, D = pc.shape
+        assert N == self.num_inputs
         with torch.no_grad():
-            mean, logvar = self.encode_stats(pc)
-            posterior = DiagonalGaussianDistribution(mean, logvar)
-            return posterior.kl(), posterior.sample()
+            # the reference draws the posterior noise from the global CPU generator and moves it over (:153)
+            noise = torch.randn(B, self.num_latents, self.latent_dim)
+            return self._runtime().encode(pc, noise)
 
     def decode(self, x, queries):
         """latents [B, M, latent_dim], queries [B, Q, 3] -> occupancy logits [B, Q, 1] (reference :408-424)."""

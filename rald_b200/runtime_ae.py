@@ -189,7 +189,33 @@ class AeRuntime:
         return self.query(self.context(z), queries).unsqueeze(-1)
 
     # ------------------------------------------------------------------ encode
+    def _check_cuda(self):
+        p = next(self.module.parameters())
+        if p.device.type != "cuda":
+            raise _lib.RaldError("rald_b200 runs on CUDA devices only: move the module to a B200 (no CPU fallback)")
+
     def encode_stats(self, pc: torch.Tensor):
         from .runtime_ae_encode import encode_stats
+        self._check_cuda()
         self.ensure_packed()
         return encode_stats(self, pc)
+
+    def encode(self, pc: torch.Tensor, noise: torch.Tensor):
+        """(kl [B], z [B, M, latent_dim]) with the posterior noise injected (drawn by the caller exactly as the
+        reference does, from the global CPU generator: models_ae.py:153)."""
+        from .runtime_ae_encode import encode_raw, posterior
+        self._check_cuda()
+        self.ensure_packed()
+        ml, _ = encode_raw(self, pc)
+        _, _, z, kl = posterior(self, ml, pc.shape[0], noise)
+        return kl, z
+
+    def fps(self, pc: torch.Tensor, m: int) -> torch.Tensor:
+        """int64 [B, m] farthest-point indices into each cloud of pc [B, N, 3]."""
+        if pc.device.type != "cuda":
+            raise _lib.RaldError("rald_b200 runs on CUDA devices only (no CPU fallback)")
+        B, N, _ = pc.shape
+        pc = pc.contiguous().float()
+        idx = torch.empty(B, m, device=pc.device, dtype=torch.int64)
+        _lib.call("rald_fps", pc.data_ptr(), B, N, m, idx.data_ptr(), _lib.cur_stream())
+        return idx

@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library builds for sm_100a, loads without a GPU, exports every symbol include/rald_b200.h declares,
+and its structs have the layout the ctypes mirrors assume. No compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+from rald_b200 import _lib, build
+from rald_b200.runtime_ae import AeWeights
+from rald_b200.runtime_dit import DitWeights, DitWorkspace
+from rald_b200.runtime_encoder import EncWeights, EncWorkspace
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+HEADER = os.path.join(ROOT, "include", "rald_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rald_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    path = build.build()
+    assert path.exists()
+    assert _lib.lib().rald_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(str(build.LIB_PATH))
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    unbound = [n for n in names if n not in _lib.exported_symbols()]
+    assert not unbound, f"declared in the header but without a ctypes signature: {unbound}"
+    undeclared = [n for n in _lib.exported_symbols() if n not in names]
+    assert not undeclared, f"bound by ctypes but missing from the header: {undeclared}"
+
+
+def test_sass_is_sm100a_with_tcgen05_and_tma():
+    out = subprocess.run(["cuobjdump", "-sass", str(build.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UTCHMMA" in out or "UTCMMA" in out       # tcgen05.mma
+    assert "UTMALDG" in out                            # TMA tensor loads
+    assert "LDTM" in out                               # tcgen05.ld
+    assert "HMMA." not in out.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+def test_struct_layouts_match_c():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "rald_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(rald_dit_weights), sizeof(rald_dit_workspace), sizeof(rald_ae_weights),
+         sizeof(rald_enc_weights), sizeof(rald_enc_workspace));
+  printf("%zu %zu %zu %zu\n", offsetof(rald_dit_weights, w_qkv), offsetof(rald_enc_weights, level),
+         offsetof(rald_enc_weights, conv_out), offsetof(rald_enc_level, down));
+  return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    sizes = [int(v) for v in lines[0].split()]
+    assert sizes == [ctypes.sizeof(DitWeights), ctypes.sizeof(DitWorkspace), ctypes.sizeof(AeWeights),
+                     ctypes.sizeof(EncWeights), ctypes.sizeof(EncWorkspace)]
+    from rald_b200.runtime_encoder import EncLevel
+    offs = [int(v) for v in lines[1].split()]
+    assert offs == [DitWeights.w_qkv.offset, EncWeights.level.offset, EncWeights.conv_out.offset, EncLevel.down.offset]
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device instead of computing somewhere else."""
+    import torch
+    from helpers import build_ae, build_denoiser
+    from rald_b200 import synth
+    if torch.cuda.is_available():
+        pytest.skip("checks the CPU-only failure mode")
+    net = build_denoiser("kl_d512_m512_l32_d12_edm")
+    with pytest.raises(_lib.RaldError):
+        net.sample(synth.radar_cube(1), cond_type="radar")
+    with pytest.raises(_lib.RaldError):
+        net(torch.zeros(1, 512, 32), torch.tensor(1.0), synth.radar_cube(1), "radar")
+    ae = build_ae()
+    with pytest.raises(_lib.RaldError):
+        ae.decode(torch.zeros(1, 512, 32), torch.zeros(1, 16, 3))
+    with pytest.raises(_lib.RaldError):
+        ae.encode(synth.lidar_points(1))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rald_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                bad = re.findall(r"^\s*(?:from|import)\s+[\w.]*oracle|#include\s+\S*oracle|liboracle|CDLL\([^)]*oracle",
+                                 text, flags=re.M)
+                assert not bad, f"{f} uses the oracle: {bad}"

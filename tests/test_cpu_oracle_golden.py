@@ -1,0 +1,129 @@
+"""CPU: the oracle (oracle/rald_oracle.py) against the fixtures produced by the UNMODIFIED reference modules
+(tests/golden/make_golden.py, run in the authoring container where /root/reference is mounted), and the drop-in
+modules' seeded initialisation against the reference's (state-dict hashes). No GPU, no reference tree needed."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_ae, build_denoiser, cpu_state_dict, rel_l2, sd_hash
+from oracle import rald_oracle as orc
+from rald_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def den_sd():
+    return cpu_state_dict(build_denoiser())
+
+
+def test_seeded_init_is_the_references(den_sd, golden_meta):
+    assert len(den_sd) == 637
+    assert sd_hash(den_sd) == golden_meta["hashes"]["denoiser"]
+    for name in ("kl_d512_m512_l32_mix", "kl_d512_m512_l32"):
+        sd = cpu_state_dict(build_ae(name))
+        assert sd_hash(sd) == golden_meta["hashes"][name]
+    assert len(cpu_state_dict(build_ae("kl_d512_m512_l32_mix"))) == 331
+
+
+def test_golden_generation_recorded_exact_agreement(golden_meta):
+    # make_golden.py asserts oracle == reference while it writes the fixtures; the recorded deviations are ~0
+    assert max(golden_meta["oracle_vs_reference"].values()) < 1e-6
+
+
+@torch.no_grad()
+def test_radar_tokens(den_sd, golden):
+    g = golden("radar_cond")
+    cube = synth.radar_cube(1, seed=1024)
+    enc = orc.radar_encoder(den_sd, cube[..., 0:1].permute(0, 4, 1, 2, 3))
+    assert rel_l2(enc, g["enc_dense"]) < 1e-5
+    assert rel_l2(orc.process_radar_cond(den_sd, cube), g["tokens_dense"]) < 1e-5
+
+
+@torch.no_grad()
+def test_denoiser_evaluation(den_sd, golden):
+    g = golden("denoiser_eval")
+    lat = synth.unit_latents([0, 1])
+    sg = torch.tensor([3.0, 0.2]).reshape(2, 1, 1)
+    out = orc.edm_precond(den_sd, lat * sg, sg, g["tokens2"])
+    assert rel_l2(out, g["denoised_per_sample"]) < 2e-5
+
+
+@torch.no_grad()
+def test_first_heun_step(den_sd, golden):
+    trace = golden("sampler_trace")["trace"]
+    tokens = golden("radar_cond")["tokens_dense"]
+    tr = []
+    orc.edm_sample(den_sd, synth.unit_latents([0]), tokens, num_steps=18, trace=tr, stop_after=1)
+    assert rel_l2(tr[0][0], trace[0]) < 1e-4
+
+
+def test_karras_schedule():
+    t = orc.karras_sigmas()
+    assert t.shape == (19,) and float(t[0]) == pytest.approx(80.0, rel=1e-6) and float(t[-1]) == 0.0
+    assert float(t[17]) == pytest.approx(0.002, rel=1e-4)
+    assert torch.all(t[:-1] > t[1:])
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("name,qtype,pts", [("kl_d512_m512_l32_mix", "mix", "uniform"),
+                                            ("kl_d512_m512_l32", "point", "frustum")])
+def test_ae_encode_stats(golden, name, qtype, pts):
+    g = golden("ae")
+    sd = cpu_state_dict(build_ae(name))
+    pc = synth.lidar_points(1, 10000, seed=1024) if pts == "uniform" else synth.frustum_points(1, 10000, seed=1024)
+    mean, logvar = orc.ae_encode_stats(sd, pc, qtype)
+    assert rel_l2(mean, g[f"{qtype}_mean"]) < 1e-5
+    assert rel_l2(logvar, g[f"{qtype}_logvar"]) < 1e-5
+    torch.manual_seed(7)
+    kl, _ = orc.ae_posterior(mean, logvar, torch.randn(mean.shape))
+    assert rel_l2(kl, g[f"{qtype}_kl"]) < 1e-5
+
+
+@torch.no_grad()
+def test_ae_decode_logits(golden):
+    g = golden("ae")
+    sd = cpu_state_dict(build_ae("kl_d512_m512_l32_mix"))
+    z = synth.posterior_noise(1, seed=11)
+    q = synth.query_points(1, 8192)
+    x = orc.ae_latent_stack(sd, z)
+    assert rel_l2(x[0, :64], g["decode_stack_rows"]) < 1e-5
+    assert rel_l2(orc.ae_query(sd, x, q[:, :2048]), g["decode_logits"][:, :2048]) < 1e-4
+
+
+def test_fps_fixture_and_properties(golden):
+    g = golden("ae")
+    pc = synth.frustum_points(1, 10000, seed=1024)
+    idx = orc.fps_indices(pc, 512)
+    assert torch.equal(idx, g["point_fps_idx"])
+    assert idx[0, 0] == 0 and len(set(idx[0].tolist())) == 512
+    # greedy property: every pick maximises the distance to the previous picks
+    p = pc[0].numpy()
+    d = np.full(10000, np.inf, dtype=np.float32)
+    for i in range(8):
+        diff = p - p[int(idx[0, i])]
+        d = np.minimum(d, (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2])
+        assert int(idx[0, i + 1]) == int(np.argmax(d))
+
+
+def test_fps_ties_pick_lowest_index():
+    lattice = torch.stack(torch.meshgrid(*[torch.arange(4.0)] * 3, indexing="ij"), -1).reshape(1, 64, 3)
+    idx = orc.fps_indices(lattice, 8)
+    assert idx[0, 0] == 0 and idx[0, 1] == 63      # the unique farthest corner
+    dup = torch.zeros(1, 16, 3)                    # all points identical: ties everywhere -> index 0 repeated
+    assert orc.fps_indices(dup, 4)[0].tolist() == [0, 0, 0, 0]
+
+
+def test_occupancy_points_oracle():
+    rng = np.random.default_rng(0)
+    lg = rng.standard_normal(1000).astype(np.float32)
+    q = rng.uniform(-1, 1, (1000, 3)).astype(np.float32)
+    pts = orc.occupancy_points(lg, q, [0, -90, -20, 15.8, 90, 20], True, False, True)
+    assert pts.shape == (int((lg > 0).sum()), 3) and pts.dtype == np.float32
+    r = np.linalg.norm(pts, axis=1)
+    assert np.allclose(r, q[lg > 0][:, 0] * np.float32(7.9) + np.float32(7.9), rtol=1e-5)
+
+
+def test_chamfer_definition():
+    a = np.zeros((4, 3), dtype=np.float32)
+    b = np.ones((2, 3), dtype=np.float32)
+    assert orc.chamfer_distance(a, b) == pytest.approx(np.sqrt(3.0))
+    assert orc.chamfer_distance(a[:0], b) == float("inf")
