@@ -30,6 +30,9 @@ const char* rald_last_error(void);
 
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t rald_launch_count(void);
+/* Accounts for kernels launched by replaying a CUDA graph captured from this library's calls (the host runtime adds
+ * the number of launches it counted during capture at every replay). */
+void rald_launch_count_add(uint64_t n);
 
 /* Per-launch timing for bench.py's roofline leg: rald_prof_enable(mask) starts a session that brackets every launch
  * of the kernel families in `mask` (bit = family id below) with CUDA events on the launching stream (0 = off);
@@ -57,6 +60,10 @@ int rald_prof_collect(int family, double* total_ms, double* total_work, int64_t*
 int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                    const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
                    int bn_hint, void* stream);
+
+/* Debug hook: when dev_buf != NULL every GEMM CTA stores %globaltimer stamps of its first tile at dev_buf[cta*8 + i]
+ * (0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done, 6 exit). */
+int rald_gemm_debug_buffer(unsigned long long* dev_buf);
 
 /* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512, scores kept in TMEM.
  * Q: [frames*Sq, >= heads*64] bf16 (ldq), K/V: [frames*Skv, ...] bf16, O: [frames*Sq, ...] bf16; head h uses

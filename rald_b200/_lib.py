@@ -22,10 +22,12 @@ _SIGNATURES = {
     "rald_abi_version": [],
     "rald_last_error": [],
     "rald_launch_count": [],
+    "rald_launch_count_add": [ctypes.c_uint64],
     "rald_prof_enable": [ctypes.c_uint],
     "rald_prof_collect": [c_int, c_void_p, c_void_p, c_void_p],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                       c_f32, c_void_p],
     "rald_ln_rows": [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_int,
@@ -62,7 +64,7 @@ _SIGNATURES = {
                                c_void_p, c_void_p, c_void_p],
     "rald_occupancy_ws_elems": [c_int, c_i64],
 }
-_RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count": ctypes.c_uint64,
+_RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
              "rald_occupancy_ws_elems": c_i64}
 
 

@@ -76,6 +76,8 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -216,7 +218,7 @@ int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void*
   }
   dim3 grid(Sq / ATT_BM, heads, frames);
   ProfScope prof(FAM_ATTN, stream, 4.0 * frames * heads * Sq * Skv * ATT_D);
-  attn_d64_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+  RALD_CHECK_CUDA(launch_pdl(attn_d64_kernel, grid, dim3(ATT_THREADS), smem_bytes, stream, tmQ, tmK, tmV, p));
   RALD_LAUNCHED();
   return 0;
 }

@@ -134,6 +134,8 @@ boundary_kernel(const BoundaryParams p) {
     for (int i = threadIdx.x; i < p.C * 512 / 4; i += blockDim.x)
       reinterpret_cast<float4*>(s_win)[i] = __ldg(reinterpret_cast<const float4*>(p.w_in_t) + i);
   }
+  pdl_wait();  // the weights staged above are constants; h / x / d come from the preceding kernels
+  pdl_launch_dependents();
   __syncthreads();
   float* my_row = s_row + warp * 512;
   const float sd = p.sigma_data;
@@ -255,7 +257,7 @@ int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const flo
   if (blocks > cap) blocks = cap;
   ProfScope prof(FAM_BOUNDARY, stream, (double)T * (mode < 3 ? 2048.0 : 0.0) + (h_next ? (double)T * 2048.0 : 0.0) +
                                           (double)T * C * 16.0);
-  boundary_kernel<<<(unsigned)blocks, BND_WARPS * 32, smem, stream>>>(p);
+  RALD_CHECK_CUDA(launch_pdl(boundary_kernel, dim3((unsigned)blocks), dim3(BND_WARPS * 32), smem, stream, p));
   RALD_LAUNCHED();
   return 0;
 }

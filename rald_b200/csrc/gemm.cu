@@ -3,7 +3,15 @@
 //
 //   warp 0 (1 lane)  TMA producer: 128 x 64 A tile + BN x 64 W tile per stage, 128B-swizzled smem ring
 //   warp 1 (1 lane)  tcgen05.mma issuer (M=128, N=BN, K=16 per instruction), accumulators double-buffered in TMEM
-//   warps 2..5       epilogue: tcgen05.ld -> registers -> (+bias) (+fp32 residual) / GEGLU -> global
+//   warps 2..5       epilogue: tcgen05.ld -> registers -> (+bias) / GEGLU -> 128B-swizzled smem staging ->
+//                    TMA tensor store (bf16 / fp32) or TMA reduce-add (fp32 `out += tile`: the residual add
+//                    h += f(h) happens in the L2, the residual is never read by the SM)
+//
+// Epilogue latency matters as much as the main loop here (K = 512 for most layers: 8 k-blocks per tile): the bias
+// of a tile is fetched while its MMAs run, all global traffic of the epilogue is asynchronous (TMA), and the TMEM
+// accumulator is released as soon as its last column has been read so the next tile's MMAs overlap the stores.
+// A generic direct-store epilogue remains for the rarely used combinations (residual that is not in place or a
+// broadcast table, bf16 output narrower than a 128-byte row).
 //
 // Replaces, for every nn.Linear on the reference hot path, the cuBLAS sgemm + separate elementwise ops:
 //   model/models_radar_generation.py:58-64 (to_q/to_k/to_v), :76 (to_out + residual :166-168),
@@ -17,39 +25,119 @@ namespace rald {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
+constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int NBUF = BN >= 256 ? 1 : 2;              // staging tiles per epilogue warp
+  static constexpr int STG_TOTAL = 4 * NBUF * STG_BYTES;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int FIXED = 1024 /*align slack*/ + 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES;
+  static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
 };
 
 struct GemmParams {
   void* out;
   int64_t ldo;
-  const float* bias;   // [N] or null (GEGLU: packed order, see pack_geglu in the Python runtime)
-  const float* resid;  // [M, ldr] fp32 or null
+  const float* bias;   // [N] or null (GEGLU: packed order, see geglu_pack_index in the Python runtime)
+  const float* resid;  // [M, ldr] fp32 or null (generic epilogue only)
   int64_t ldr;
   int64_t resid_mod;   // > 0: residual row = row % resid_mod (a [resid_mod, N] table broadcast over frames)
   int M, N, K;
   int num_m_blks, num_n_blks;
+  unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
+static unsigned long long* g_gemm_dbg = nullptr;
+#define GEMM_STAMP(slot)                                                        \
+  do {                                                                          \
+    if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + (slot)] = global_timer_ns();   \
+  } while (0)
+
+// ---- generic epilogue for one 32-column chunk already in registers (direct global loads / stores) ----
+template <int OUT_MODE>
+__device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmParams& p, int64_t row, bool row_ok,
+                                                int col0) {
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+    }
+  }
+  if (OUT_MODE != 2 && p.resid != nullptr && row_ok) {
+    const int64_t rrow = p.resid_mod > 0 ? row % p.resid_mod : row;
+    const float4* r4 = reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r = r4[j];
+      v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + r.x);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
+    }
+  }
+  if (OUT_MODE == 1) {
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else if (OUT_MODE == 0) {
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
+                            pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                            pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                            pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+      }
+    }
+  } else {
+    // GEGLU: within every packed 32-column group, columns [0,16) are the value half and [16,32) the gate half
+    // of the same 16 output features (reference: x, gate = proj(x).chunk(2); x * gelu(gate)).
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_erf(__uint_as_float(v[16 + j]));
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col0 >> 1));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        dst[j] = make_uint4(pack_bf16x2(o[8 * j + 0], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                            pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+      }
+    }
+  }
+}
+
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE>
+template <int BN, int OUT_MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NBUF = Cfg::NBUF;
+  // accumulator columns consumed per staged 128-byte output row
+  constexpr int CHUNK = OUT_MODE == 1 ? 32 : (OUT_MODE == 0 ? 64 : 128);
+  static_assert(EPI == EPI_GENERIC || BN % CHUNK == 0, "tile narrower than one staged output row");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES;                    // 1024-byte aligned (stage sizes are)
+  float* s_bias = reinterpret_cast<float*>(stg + Cfg::STG_TOTAL);     // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -61,8 +149,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (threadIdx.x == 0) {
+    GEMM_STAMP(0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -81,10 +171,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // A (and an in-place residual) come from the preceding kernel
+  pdl_launch_dependents();  // the next kernel may set itself up on idle SMs while this one runs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      GEMM_STAMP(1);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -117,6 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (it == 0 && kb == 0) GEMM_STAMP(2);
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
@@ -130,92 +224,119 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (it == 0) GEMM_STAMP(3);
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp is allowed to touch
     const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
     int it = 0;
+    int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.num_n_blks;
       const int n_blk = tile - m_blk * p.num_n_blks;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
+      float* bias_s = s_bias + acc * BN;
+      if (EPI != EPI_GENERIC) {
+        // bias of this tile -> smem while the MMAs of the tile are still running
+        for (int j = et; j < BN; j += 128) {
+          const int col = n_blk * BN + j;
+          bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * GEMM_BM + row_in_tile;
-      const bool row_ok = row < p.M;
+      if (it == 0 && threadIdx.x == 64) GEMM_STAMP(4);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (EPI == EPI_GENERIC) {
+        const int64_t row = static_cast<int64_t>(m_blk) * GEMM_BM + row_in_tile;
+        const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
-          }
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          epilogue_direct<OUT_MODE>(v, p, row, row_ok, col0);
         }
-        if (OUT_MODE != 2 && p.resid != nullptr && row_ok) {
-          const int64_t rrow = p.resid_mod > 0 ? row % p.resid_mod : row;
-          const float4* r4 = reinterpret_cast<const float4*>(p.resid + rrow * p.ldr + col0);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      } else {
+        constexpr int NCHUNK = BN / CHUNK;
+        const int row0 = m_blk * GEMM_BM + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int acol0 = c * CHUNK;                 // accumulator column inside the tile
+          const bool live = n_blk * BN + acol0 < p.N;  // chunks past N are read (uniform TMEM hand-off) but not stored
+          uint32_t o[32];                              // one 128-byte output row
+          if (OUT_MODE == 1) {
+            tmem_ld32(t_row + acol0, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 r = r4[j];
-            v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + r.x);
-            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + r.y);
-            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + r.z);
-            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + r.w);
-          }
-        }
-        if (OUT_MODE == 1) {
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col0);
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + bias_s[acol0 + j]);
+          } else if (OUT_MODE == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        } else if (OUT_MODE == 0) {
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0);
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld32(t_row + acol0 + 32 * h, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1])),
-                                  pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                  pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                  pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+              for (int j = 0; j < 16; ++j)
+                o[16 * h + j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bias_s[acol0 + 32 * h + 2 * j],
+                                            __uint_as_float(v[2 * j + 1]) + bias_s[acol0 + 32 * h + 2 * j + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              uint32_t v[32];
+              tmem_ld32(t_row + acol0 + 32 * h, v);
+              tmem_ld_wait();
+              const float* bs = bias_s + acol0 + 32 * h;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = (__uint_as_float(v[2 * j]) + bs[2 * j]) *
+                                 gelu_erf(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
+                const float a1 = (__uint_as_float(v[2 * j + 1]) + bs[2 * j + 1]) *
+                                 gelu_erf(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
+                o[8 * h + j] = pack_bf16x2(a0, a1);
+              }
             }
           }
-        } else {
-          // GEGLU: within every packed 32-column group, columns [0,16) are the value half and [16,32) the
-          // gate half of the same 16 output features (reference: x, gate = proj(x).chunk(2); x * gelu(gate)).
-          float o[16];
+          if (c == NCHUNK - 1) {
+            // every TMEM read of this accumulator has completed -> hand it back to the MMA warp now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          if (live) {
+            if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the staging tile about to be overwritten was read
+            __syncwarp();
+            const uint32_t sdst = smem_u32(stg + (q * NBUF + sbuf) * STG_BYTES) + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_erf(__uint_as_float(v[16 + j]));
-          if (row_ok) {
-            uint4* dst =
-                reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col0 >> 1));
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              dst[j] = make_uint4(pack_bf16x2(o[8 * j + 0], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                                  pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
+              const void* src = stg + (q * NBUF + sbuf) * STG_BYTES;
+              if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, src, ocol, row0);
+              else tma_store_2d(&tmO, src, ocol, row0);
+              bulk_commit_group();
             }
+            if (NBUF == 2) sbuf ^= 1;
           }
         }
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (it == 0 && threadIdx.x == 64) GEMM_STAMP(5);
     }
+    if (EPI != EPI_GENERIC && lane == 0) bulk_wait_group<0>();  // smem must outlive the last store
   }
 
   tc_fence_before();
@@ -223,14 +344,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (lane == 0) GEMM_STAMP(6);
   }
 }
 
-template <int BN, int OUT_MODE>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int max_ctas,
-                       cudaStream_t stream) {
+template <int BN, int OUT_MODE, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+                       int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -239,7 +361,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int num_tiles = p.num_m_blks * p.num_n_blks;
   int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
   ProfScope prof(FAM_GEMM, stream, 2.0 * p.M * p.N * p.K);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  RALD_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmO, p));
   RALD_LAUNCHED();
   return 0;
 }
@@ -265,17 +387,33 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   RALD_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16-byte aligned");
 
   const int sms = device_sm_count();
+  const int m_blks = (M + GEMM_BM - 1) / GEMM_BM;
+  const int min_bn = out_mode == 1 ? 32 : (out_mode == 0 ? 64 : 128);  // narrowest tile of the TMA epilogue
   int bn = bn_hint;
   if (bn == 0) {
-    // Prefer the 128x256 tile (full-rate MMA with the lowest smem traffic) unless it leaves most SMs idle.
-    const int m_blks = (M + GEMM_BM - 1) / GEMM_BM;
-    if (N % 256 == 0 && m_blks * (N / 256) >= sms) bn = 256;
-    else if (N % 128 == 0 && m_blks * (N / 128) >= sms / 2) bn = 128;
-    else if (N % 128 == 0 && N >= 512) bn = 128;
-    else if (N % 64 == 0) bn = 64;
-    else bn = 32;
+    // Cost model: waves x (fixed per-tile cost + tile width). Wide tiles re-read the operands least and amortise the
+    // epilogue, but a small problem wants many narrow tiles so that every SM streams operands (one wave), and a
+    // medium one wants the width whose last wave is not mostly empty.
+    long best = -1;
+    for (int cand = 256; cand >= min_bn; cand >>= 1) {
+      if (N % cand != 0) continue;
+      const long tiles = (long)m_blks * (N / cand);
+      const long cost = ((tiles + sms - 1) / sms) * (64 + cand);
+      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
+    if (bn == 0) bn = N % 64 == 0 ? 64 : 32;
   }
   RALD_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
+
+  int epi = EPI_GENERIC;
+  if (out_mode == 1) {
+    if (resid == nullptr) epi = EPI_TMA_STORE;
+    else if (resid == out && ldr == ldo && resid_mod == 0) epi = EPI_TMA_REDUCE;
+  } else if (out_mode == 0) {
+    if (resid == nullptr && bn >= 64) epi = EPI_TMA_STORE;
+  } else if (bn >= 128) {
+    epi = EPI_TMA_STORE;
+  }
 
   GemmParams p;
   p.out = out;
@@ -287,26 +425,56 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.M = M;
   p.N = N;
   p.K = K;
-  p.num_m_blks = (M + GEMM_BM - 1) / GEMM_BM;
+  p.num_m_blks = m_blks;
   p.num_n_blks = (N + bn - 1) / bn;
+  p.dbg = g_gemm_dbg;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
   RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
-
-#define RALD_GEMM_CASE(BN_)                                                              \
-  case BN_:                                                                              \
-    if (out_mode == 0) return launch_gemm<BN_, 0>(tmA, tmB, p, sms, stream);             \
-    if (out_mode == 1) return launch_gemm<BN_, 1>(tmA, tmB, p, sms, stream);             \
-    return launch_gemm<BN_, 2>(tmA, tmB, p, sms, stream);
-  switch (bn) {
-    RALD_GEMM_CASE(32)
-    RALD_GEMM_CASE(64)
-    RALD_GEMM_CASE(128)
-    RALD_GEMM_CASE(256)
+  if (epi != EPI_GENERIC) {
+    RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1));
+  } else {
+    tmO = tmA;
   }
-#undef RALD_GEMM_CASE
+
+#define RALD_GEMM_LAUNCH(BN_, MODE_, EPI_) return launch_gemm<BN_, MODE_, EPI_>(tmA, tmB, tmO, p, sms, stream)
+#define RALD_GEMM_BN(MODE_, EPI_)                   \
+  switch (bn) {                                     \
+    case 32: RALD_GEMM_LAUNCH(32, MODE_, EPI_);     \
+    case 64: RALD_GEMM_LAUNCH(64, MODE_, EPI_);     \
+    case 128: RALD_GEMM_LAUNCH(128, MODE_, EPI_);   \
+    default: RALD_GEMM_LAUNCH(256, MODE_, EPI_);    \
+  }
+  if (out_mode == 1) {
+    if (epi == EPI_TMA_REDUCE) { RALD_GEMM_BN(1, EPI_TMA_REDUCE) }
+    if (epi == EPI_TMA_STORE) { RALD_GEMM_BN(1, EPI_TMA_STORE) }
+    RALD_GEMM_BN(1, EPI_GENERIC)
+  }
+  if (out_mode == 0) {
+    if (epi == EPI_TMA_STORE) {
+      switch (bn) {
+        case 64: RALD_GEMM_LAUNCH(64, 0, EPI_TMA_STORE);
+        case 128: RALD_GEMM_LAUNCH(128, 0, EPI_TMA_STORE);
+        default: RALD_GEMM_LAUNCH(256, 0, EPI_TMA_STORE);
+      }
+    }
+    RALD_GEMM_BN(0, EPI_GENERIC)
+  }
+  if (epi == EPI_TMA_STORE) {
+    if (bn == 128) RALD_GEMM_LAUNCH(128, 2, EPI_TMA_STORE);
+    RALD_GEMM_LAUNCH(256, 2, EPI_TMA_STORE);
+  }
+  RALD_GEMM_BN(2, EPI_GENERIC)
+#undef RALD_GEMM_BN
+#undef RALD_GEMM_LAUNCH
   return -1;
 }
 
 }  // namespace rald
+
+// Debug hook (tools/gemm_phases.py): when set, every GEMM CTA stores %globaltimer at its phase boundaries.
+extern "C" int rald_gemm_debug_buffer(unsigned long long* dev_buf) {
+  rald::g_gemm_dbg = dev_buf;
+  return 0;
+}

@@ -1,6 +1,7 @@
 #include "host.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -80,6 +81,14 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box, nullptr);
 }
 
+int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * (f32 ? 4u : 2u)};
+  uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+  return encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 2, dims, strides,
+                box, nullptr);
+}
+
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   return encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides);
@@ -121,6 +130,15 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g_prof[slot].e1, stream);
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RALD_B200_PDL");
+    on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -135,6 +153,7 @@ int device_sm_count() {
 }  // namespace rald
 
 extern "C" uint64_t rald_launch_count(void) { return rald::g_launches.load(); }
+extern "C" void rald_launch_count_add(uint64_t n) { rald::g_launches.fetch_add(n); }
 
 extern "C" int rald_prof_enable(unsigned family_mask) {
   std::lock_guard<std::mutex> lk(rald::g_prof_mu);

@@ -43,11 +43,31 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // same for 32-bit elements (tf32 operands): box = box_rows x 32 columns (128 bytes)
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows);
+// Output tiles for TMA stores: box = 32 rows x 128 bytes (32 fp32 or 64 bf16 columns), 128-byte swizzle.
+int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32);
 // General tiled map over 16-bit elements: dims/strides innermost first (strides in BYTES for dims 1..rank-1).
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
 int device_sm_count();
+bool pdl_enabled();  // RALD_B200_PDL != 0 (default on)
+
+// Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before touching memory
+// written by its predecessor in the stream).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- launch accounting (rald_launch_count) and optional per-launch CUDA-event timing (rald_prof_*) ----
 enum ProfFamily : int { FAM_GEMM = 0, FAM_ATTN = 1, FAM_LN = 2, FAM_BOUNDARY = 3, FAM_CONV3D = 4, FAM_GN = 5,

@@ -19,6 +19,8 @@ ln_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t row = warp_global; row < rows; row += warps_total) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
     float4 v[NCH];
@@ -70,11 +72,11 @@ int ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, 
   if (blocks > cap) blocks = cap;
   ProfScope prof(FAM_LN, stream, (double)rows * D * (out_f32 ? 8.0 : 6.0));
   if (out_f32)
-    ln_rows_kernel<512, true><<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, gamma, beta, mod_frame_stride,
-                                                                    rows_per_frame, gamma_plus_one, out, ldo, rows, eps);
+    RALD_CHECK_CUDA(launch_pdl(ln_rows_kernel<512, true>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ldx, gamma, beta,
+                               mod_frame_stride, rows_per_frame, gamma_plus_one, out, ldo, rows, eps));
   else
-    ln_rows_kernel<512, false><<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, gamma, beta, mod_frame_stride,
-                                                                     rows_per_frame, gamma_plus_one, out, ldo, rows, eps);
+    RALD_CHECK_CUDA(launch_pdl(ln_rows_kernel<512, false>, dim3((unsigned)blocks), dim3(256), 0, stream, x, ldx, gamma,
+                               beta, mod_frame_stride, rows_per_frame, gamma_plus_one, out, ldo, rows, eps));
   RALD_LAUNCHED();
   return 0;
 }

@@ -44,7 +44,22 @@ def geglu_pack_index(inner: int, device) -> torch.Tensor:
 
 
 def default_microbatch() -> int:
-    return int(os.environ.get("RALD_B200_MICROBATCH", "8"))
+    return int(os.environ.get("RALD_B200_MICROBATCH", "16"))
+
+
+def graphs_enabled() -> bool:
+    return os.environ.get("RALD_B200_GRAPH", "1") == "1"
+
+
+class _SamplerGraph:
+    """One captured sampling loop (context K/V GEMM + rald_dit_sample) for a fixed (frames, context length, schedule):
+    static input / output buffers and the CUDA graph that replays the ~9 300 launches without host work."""
+
+    def __init__(self):
+        self.graph = None
+        self.tokens = self.latents = self.out = None
+        self.launches = 0
+        self.warm = False
 
 
 class DitRuntime:
@@ -56,6 +71,7 @@ class DitRuntime:
         self._ws = None
         self._ws_frames = 0
         self._mod_cache = {}
+        self._graphs = {}
 
     # ------------------------------------------------------------------ packing
     def _signature(self):
@@ -117,6 +133,7 @@ class DitRuntime:
         self.depth, self.dim, self.heads, self.channels = depth, dim, heads, C
         self.device = dev
         self._mod_cache.clear()
+        self._graphs.clear()
         self._sig = sig
 
     def _weights_struct(self, ctx_len: int) -> DitWeights:
@@ -130,8 +147,12 @@ class DitRuntime:
         return w
 
     def _workspace(self, frames: int):
+        """Workspace for micro-batches of min(frames, RALD_B200_MICROBATCH) frames; one per size, kept alive because
+        captured graphs hold their addresses."""
         mb = max(1, min(default_microbatch(), frames))
-        if self._ws is None or self._ws_frames != mb:
+        if self._ws is None:
+            self._ws = {}
+        if mb not in self._ws:
             T = mb * self.module.n_latents
             dev, dim = self.device, self.dim
             bufs = dict(h=torch.empty(T, dim, device=dev, dtype=torch.float32),
@@ -145,8 +166,8 @@ class DitRuntime:
             ws.max_frames = mb
             for k, v in bufs.items():
                 setattr(ws, k, v.data_ptr())
-            self._ws, self._ws_bufs, self._ws_frames = ws, bufs, mb
-        return self._ws
+            self._ws[mb] = (ws, bufs)
+        return self._ws[mb][0]
 
     # ------------------------------------------------------------------ pieces
     def mod_table(self, sigmas: torch.Tensor) -> torch.Tensor:
@@ -188,23 +209,61 @@ class DitRuntime:
                   ctxkv.data_ptr(), out.data_ptr(), B, _lib.cur_stream())
         return out
 
+    def _sample_eager(self, latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L):
+        ctxkv = self.context_kv(tokens_bf16)
+        w, ws = self._weights_struct(L), self._workspace(B)
+        _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
+                  num_steps, mod.data_ptr(), ctxkv.data_ptr(), out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
+        return ctxkv
+
     def sample(self, latents: torch.Tensor, tokens_bf16: torch.Tensor, sigmas: torch.Tensor,
                trace: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """latents: unit normal [B, M, C]; sigmas: fp32 [num_steps + 1] ending in 0 (host or device tensor)."""
+        """latents: unit normal [B, M, C]; sigmas: fp32 [num_steps + 1] ending in 0 (host or device tensor).
+        The launch sequence is static, so for batches of at most two micro-batches it is captured into a CUDA graph on
+        the second call with the same shape and replayed afterwards (RALD_B200_GRAPH=0 disables this)."""
         self.ensure_packed()
         B, M, C = latents.shape
         L = tokens_bf16.shape[0] // B
         latents = latents.contiguous().float()
         key = tuple(float(s) for s in sigmas.tolist())
-        sig_dev = sigmas.to(device=self.device, dtype=torch.float32).contiguous()
-        num_steps = sig_dev.numel() - 1
         if key not in self._mod_cache:
             self._mod_cache.clear()
-            self._mod_cache[key] = self.mod_table(sig_dev[:num_steps])
-        mod = self._mod_cache[key]
-        ctxkv = self.context_kv(tokens_bf16)
-        out = torch.empty_like(latents)
-        w, ws = self._weights_struct(L), self._workspace(B)
-        _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
-                  num_steps, mod.data_ptr(), ctxkv.data_ptr(), out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
-        return out
+            self._graphs.clear()
+            sig_dev = sigmas.to(device=self.device, dtype=torch.float32).contiguous()
+            self._mod_cache[key] = (sig_dev, self.mod_table(sig_dev[:-1]))
+        sig_dev, mod = self._mod_cache[key]
+        num_steps = sig_dev.numel() - 1
+        mb = max(1, min(default_microbatch(), B))
+        if trace is not None or not graphs_enabled() or B > 2 * mb:
+            out = torch.empty_like(latents)
+            self._sample_eager(latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L)
+            return out
+        gkey = (B, L, mb)
+        g = self._graphs.get(gkey)
+        if g is None:
+            g = self._graphs[gkey] = _SamplerGraph()
+        if not g.warm:
+            # first call: eager (one-time kernel attribute setup, workspace allocation)
+            g.warm = True
+            out = torch.empty_like(latents)
+            self._sample_eager(latents, tokens_bf16, sig_dev, num_steps, mod, out, None, B, L)
+            return out
+        if g.graph is None:
+            g.tokens = torch.empty_like(tokens_bf16)
+            g.latents = torch.empty_like(latents)
+            g.out = torch.empty_like(latents)
+            g.tokens.copy_(tokens_bf16)
+            g.latents.copy_(latents)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                g.ctxkv = self._sample_eager(g.latents, g.tokens, sig_dev, num_steps, mod, g.out, None, B, L)
+            g.launches = _lib.launch_count() - n0
+            g.graph = graph
+        else:
+            g.tokens.copy_(tokens_bf16)
+            g.latents.copy_(latents)
+            _lib.lib().rald_launch_count_add(g.launches)
+        g.graph.replay()
+        return g.out.clone()

@@ -8,7 +8,7 @@ torch.manual_seed(0)
 dev = "cuda"
 
 
-def run(M, N, K, mode, bn=0, bias=True, resid=False):
+def run(M, N, K, mode, bn=0, bias=True, resid=False, inplace=False):
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev) if bias else None
@@ -24,7 +24,9 @@ def run(M, N, K, mode, bn=0, bias=True, resid=False):
     elif mode == 1:
         if r is not None:
             ref = ref + r
-        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+        out = r.clone() if (inplace and r is not None) else torch.empty(M, N, device=dev, dtype=torch.float32)
+        if inplace and r is not None:
+            r = out   # h += A W^T + b : TMA reduce-add epilogue
     else:
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     _lib.call("rald_gemm_bf16", A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), out.shape[1],
@@ -33,7 +35,7 @@ def run(M, N, K, mode, bn=0, bias=True, resid=False):
     err = (out.float() - ref).norm() / ref.norm()
     mx = (out.float() - ref).abs().max()
     ok = err < (1e-5 if mode == 1 else 6e-3)
-    print(f"gemm M={M} N={N} K={K} mode={mode} bn={bn} bias={bias} resid={resid}: rel={err:.3e} max={mx:.3e} "
+    print(f"gemm M={M} N={N} K={K} mode={mode} bn={bn} bias={bias} resid={resid} inplace={inplace}: rel={err:.3e} max={mx:.3e} "
           f"{'OK' if ok else 'FAIL'}", flush=True)
     return ok
 
@@ -42,8 +44,8 @@ def bench(M, N, K, mode, bn=0, iters=20):
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev)
-    r = torch.randn(M, N, device=dev) if mode == 1 else None
-    out = torch.empty(M, N if mode != 2 else N // 2, device=dev, dtype=torch.float32 if mode == 1 else torch.bfloat16)
+    out = torch.zeros(M, N if mode != 2 else N // 2, device=dev, dtype=torch.float32 if mode == 1 else torch.bfloat16)
+    r = out if mode == 1 else None   # in-place residual, as every residual GEMM of the denoiser / AE stack
     args = (A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), out.shape[1], _lib.ptr(b), _lib.ptr(r), N, M, N, K,
             mode, bn, _lib.cur_stream())
     for _ in range(3):
@@ -80,6 +82,17 @@ if __name__ == "__main__":
     ok &= run(512, 1536, 512, 0)
     ok &= run(512, 1536, 512, 0, bn=256)
     ok &= run(512, 512, 512, 1, resid=True)
+    for bn_ in (0, 32, 64, 128, 256):
+        ok &= run(512, 512, 512, 1, resid=True, inplace=True, bn=bn_)
+        ok &= run(1000, 512, 2048, 1, resid=True, inplace=True, bn=bn_)   # ragged M through the TMA reduce
+        ok &= run(300, 512, 512, 1, bn=bn_)                                # plain fp32 TMA store
+    for bn_ in (64, 128, 256):
+        ok &= run(1000, 1536, 512, 0, bn=bn_)
+    for bn_ in (128, 256):
+        ok &= run(1000, 4096, 512, 2, bn=bn_)
+    ok &= run(512, 10016, 64, 1)         # N multiple of 32 only (long-context scores)
+    ok &= run(512, 10016, 512, 0)        # bf16 output, N % 64 != 0 -> generic epilogue
+    ok &= run(40000, 512, 512, 1, resid=True, inplace=True)
     ok &= run(512, 512, 2048, 1, resid=True, bn=256)
     ok &= run(512, 4096, 512, 2)
     ok &= run(512, 4096, 512, 2, bn=256)
