@@ -65,6 +65,11 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
  * (0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done, 6 exit). */
 int rald_gemm_debug_buffer(unsigned long long* dev_buf);
 
+/* Debug hook like rald_gemm_debug_buffer for the attention kernel: CTA 0 stores, for its first 16 query tiles and both
+ * softmax groups, stamps at dev_buf[(tile*2+group)*8 + i]: 0 tile start, 1 S ready, 2 P written, 3 stats merged,
+ * 4 O ready, 5 stored. */
+int rald_attn_debug_buffer(unsigned long long* dev_buf);
+
 /* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512, scores kept in TMEM.
  * Q: [frames*Sq, >= heads*64] bf16 (ldq), K/V: [frames*Skv, ...] bf16, O: [frames*Sq, ...] bf16; head h uses
  * columns [h*64, h*64+64). Replaces the two einsums + softmax of CrossAttention.forward

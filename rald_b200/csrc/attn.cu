@@ -1,14 +1,22 @@
 // Fused softmax(Q K^T * scale) V for head_dim 64 and a key set that fits TMEM (Skv <= 512), tcgen05 + TMA.
 //
-// One CTA = 128 query rows of one (frame, head):
-//   warp 0 lane 0 : TMA loads Q [128x64], K [Skv x 64], V [Skv x 64] (128B swizzle), then issues
-//                   S = Q K^T   (tcgen05.mma SS, N = Skv in chunks of <=256, S fp32 in TMEM columns [0, Skv))
-//                   O = P V     (tcgen05.mma TS: P read from TMEM, V as MN-major smem operand)
-//   warps 1..4    : row r = TMEM lane r. sweep 1: row max over S; sweep 2: p = exp2((s - max) * scale*log2e),
-//                   packed to bf16 pairs and written back INTO TMEM over the already-consumed S columns
-//                   ([0, Skv/2)), row sum kept in fp32; after O is ready: O / sum -> bf16 -> global.
-// The score matrix never leaves the SM (the reference materialises [B*h, Sq, Skv] fp32 in HBM:
-// model/models_radar_generation.py:66-75, model/models_ae.py:91-104).
+// Persistent CTAs (one per SM). A work item = TQ consecutive 128-query tiles of one (frame, head): K and V of the
+// head are loaded ONCE per item and stay in shared memory while the query tiles stream through a 2-deep Q ring.
+// The keys are split in two halves that are processed CONCURRENTLY by two softmax warp groups and merged at the end
+// (exact: each half keeps its own max / sum, the epilogue rescales):
+//   warp 0 lane 0 : TMA producer   (K, V per item; Q per tile, prefetched one tile ahead)
+//   warp 1 lane 0 : tcgen05 issuer  S_h = Q K_h^T  (SS, fp32 S in TMEM), O_h = P_h V_h (TS: P from TMEM, V MN-major)
+//   warps 2..5    : softmax of key half 0      } thread <-> query row <-> TMEM lane; ONE sweep over S with a lazily
+//   warps 6..9    : softmax of key half 1      } raised shift: p = exp2(s*scale*log2e - m) packed to bf16 pairs written
+//                   back INTO TMEM over the consumed S columns, row sum in fp32 (TMEM -> register bandwidth, 64 B/clk
+//                   per SM, is what bounds this kernel, so S is read exactly once). TMEM loads are software-pipelined
+//                   and the reductions use four independent chains. Then both groups exchange (shift, sum) through
+//                   shared memory and each normalises and stores 32 of the 64 output columns:
+//                   O = (w0 O_0 + w1 O_1) / (w0 l_0 + w1 l_1),  w_h = exp2(m_h - max(m_0, m_1)).
+// With 8 softmax warps every SM sub-partition has two warps to hide TMEM-load and MUFU latency; the tensor pipe works
+// on one half while the other is in its softmax. For short contexts (Skv <= 128, the cross-attention case) the TMEM
+// regions are double-buffered so consecutive query tiles overlap as well. The score matrix never leaves the SM (the
+// reference materialises [B*h, Sq, Skv] fp32 in HBM: model/models_radar_generation.py:66-75, models_ae.py:91-104).
 #include "host.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -17,16 +25,32 @@ namespace rald {
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 160;
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_QBYTES = ATT_BM * ATT_D * 2;
 
 struct AttnParams {
   __nv_bfloat16* out;
   int64_t ldo;
   int Sq, Skv;
-  float scale_log2;  // scale * log2(e)
-  uint32_t tmem_cols;
-  uint32_t o_col;
+  int frames, heads;
+  int q_tiles;         // Sq / 128
+  int tq;              // query tiles per work item
+  int items_per_head;  // q_tiles / tq
+  int num_items;
+  float scale_log2;    // scale * log2(e)
+  int half;            // keys per half = Skv / 2
+  uint32_t o_col;      // O accumulator column inside a half region
+  uint32_t region;     // TMEM columns per half region
+  int nbuf;            // query tiles in flight in TMEM (1 or 2); a tile uses 2 * region columns
+  unsigned long long* dbg;  // optional [tile < 16][group 2][8] %globaltimer stamps of CTA 0 (tools/attn_phases.py)
 };
+
+static unsigned long long* g_attn_dbg = nullptr;
+#define ATT_STAMP(slot_)                                                                              \
+  do {                                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && qn < 16 && q == 0 && lane == 0)                        \
+      p.dbg[(qn * 2 + g) * 8 + (slot_)] = global_timer_ns();                                          \
+  } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -34,42 +58,54 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Skv = p.Skv;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_BM * ATT_D * 2;
-  uint8_t* sV = sK + Skv * ATT_D * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Skv * ATT_D * 2);
-  uint64_t* bar_qk = bars + 0;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sQ = smem;                       // [2][128 x 64]
+  uint8_t* sK = sQ + 2 * ATT_QBYTES;        // [Skv x 64]
+  uint8_t* sV = sK + Skv * ATT_D * 2;       // [Skv x 64]
+  float* s_stat = reinterpret_cast<float*>(sV + Skv * ATT_D * 2);  // [nbuf 2][half 2][m, l][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 2 * 2 * ATT_BM);
+  uint64_t* k_full = bars + 0;
+  uint64_t* k_empty = bars + 1;
+  uint64_t* q_full = bars + 2;    // [2]
+  uint64_t* q_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;    // [slot 2][half 2]
+  uint64_t* p_full = bars + 10;   // [slot 2][half 2]
+  uint64_t* o_full = bars + 14;   // [slot 2][half 2]
+  uint64_t* o_empty = bars + 18;  // [slot 2]
+  uint64_t* v_full = bars + 20;
+  uint64_t* v_empty = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x;
-  const int head = blockIdx.y;
-  const int frame = blockIdx.z;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&o_empty[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -80,121 +116,253 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_launch_dependents();
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      const int q_row0 = frame * p.Sq + q_blk * ATT_BM;
-      const int kv_row0 = frame * Skv;
-      mbar_arrive_expect_tx(bar_qk, (ATT_BM + Skv) * ATT_D * 2);
-      tma_load_2d(sQ, &tmQ, bar_qk, head * ATT_D, q_row0);
-      for (int r = 0; r < Skv; r += 256) tma_load_2d(sK + r * ATT_D * 2, &tmK, bar_qk, head * ATT_D, kv_row0 + r);
-      mbar_arrive_expect_tx(bar_v, Skv * ATT_D * 2);
-      for (int r = 0; r < Skv; r += 256) tma_load_2d(sV + r * ATT_D * 2, &tmV, bar_v, head * ATT_D, kv_row0 + r);
-
-      // ---- S = Q K^T ----
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
-      for (int n0 = 0; n0 < Skv; n0 += 256) {
-        const int n = (Skv - n0) < 256 ? (Skv - n0) : 256;
-        const uint32_t idesc = make_idesc(FMT_BF16, ATT_BM, n, 0, 0);
-        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + n0 * ATT_D * 2), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) mma_f16_ss(tmem_base + n0, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
+      uint32_t kv_ph = 0;
+      int qn = 0;  // running tile counter -> Q ring slot / phase
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int fh = item / p.items_per_head;
+        const int frame = fh / p.heads, head = fh - frame * p.heads;
+        const int qt0 = (item - fh * p.items_per_head) * p.tq;
+        const int kv_row0 = frame * Skv;
+        // K is free as soon as the last S product of the previous item has retired, V only after its last P V:
+        // the next item's K and first Q tile are fetched while the previous item is still in its softmax.
+        mbar_wait(k_empty, kv_ph ^ 1);
+        mbar_arrive_expect_tx(k_full, Skv * ATT_D * 2);
+        for (int r = 0; r < Skv; r += p.half) tma_load_2d(sK + r * ATT_D * 2, &tmK, k_full, head * ATT_D, kv_row0 + r);
+        for (int t = 0; t < p.tq; ++t, ++qn) {
+          const int slot = qn & 1;
+          const uint32_t ph = (qn >> 1) & 1;
+          mbar_wait(&q_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&q_full[slot], ATT_QBYTES);
+          tma_load_2d(sQ + slot * ATT_QBYTES, &tmQ, &q_full[slot], head * ATT_D, frame * p.Sq + (qt0 + t) * ATT_BM);
+          if (t == 0) {
+            mbar_wait(v_empty, kv_ph ^ 1);
+            mbar_arrive_expect_tx(v_full, Skv * ATT_D * 2);
+            for (int r = 0; r < Skv; r += p.half)
+              tma_load_2d(sV + r * ATT_D * 2, &tmV, v_full, head * ATT_D, kv_row0 + r);
+          }
+        }
+        kv_ph ^= 1;
       }
-      tc_commit(bar_s);
-
-      // ---- O = P V (P in TMEM columns [0, Skv/2), 2 keys per 32-bit column) ----
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
       const uint32_t idesc_o = make_idesc(FMT_BF16, ATT_BM, ATT_D, 0, 1);
-      // V is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom (LBO unused).
-      const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV), 1024, 1024);
-      for (int k = 0; k < Skv / 16; ++k) {
-        // 16 keys per MMA = 8 TMEM columns of P and 2048 B (=128 in >>4 units) of V
-        mma_f16_ts(tmem_base + p.o_col, tmem_base + 8 * k, v_desc + 128 * k, idesc_o, k != 0);
+      const uint32_t idesc_s = make_idesc(FMT_BF16, ATT_BM, p.half, 0, 0);
+      uint32_t kv_ph = 0;
+      int qn = 0;
+      auto issue_s = [&](int n, bool last_of_item) {
+        const int qslot = n & 1;
+        const int slot = p.nbuf == 2 ? (n & 1) : 0;
+        const uint32_t use = p.nbuf == 2 ? (uint32_t)(n >> 1) : (uint32_t)n;  // earlier uses of this TMEM slot
+        mbar_wait(&q_full[qslot], (n >> 1) & 1);
+        mbar_wait(&o_empty[slot], (use & 1) ^ 1);  // previous occupant of the slot fully drained
+        tc_fence_after();
+        const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qslot * ATT_QBYTES), 16, 1024);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t t_s = tmem_base + (slot * 2 + h) * p.region;
+          const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + h * p.half * ATT_D * 2), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) mma_f16_ss(t_s, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          if (h == 1) tc_commit(&q_empty[qslot]);  // Q tile consumed once these MMAs retire
+          tc_commit(&s_full[slot * 2 + h]);
+        }
+        if (last_of_item) tc_commit(k_empty);  // K may be replaced once the last S product of the item has retired
+      };
+      auto issue_pv = [&](int n, bool first_of_item, bool last_of_item) {
+        const int slot = p.nbuf == 2 ? (n & 1) : 0;
+        const uint32_t use = p.nbuf == 2 ? (uint32_t)(n >> 1) : (uint32_t)n;
+        if (first_of_item) mbar_wait(v_full, kv_ph);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[slot * 2 + h], use & 1);
+          tc_fence_after();
+          const uint32_t t_s = tmem_base + (slot * 2 + h) * p.region;
+          // V is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom.
+          const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + h * p.half * ATT_D * 2), 1024, 1024);
+          for (int k = 0; k < p.half / 16; ++k) {
+            // 16 keys per MMA = 8 TMEM columns of P and 2048 B (= 128 in >>4 units) of V
+            mma_f16_ts(t_s + p.o_col, t_s + 8 * k, v_desc + 128 * k, idesc_o, k != 0);
+          }
+          tc_commit(&o_full[slot * 2 + h]);
+        }
+        if (last_of_item) tc_commit(v_empty);  // V may be replaced once every MMA of the item has retired
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(k_full, kv_ph);
+        tc_fence_after();
+        if (p.nbuf == 2) {
+          // S of tile n+1 is issued before P V of tile n: the tensor pipe runs ahead of the softmax warps
+          issue_s(qn, p.tq == 1);
+          for (int t = 0; t < p.tq; ++t) {
+            if (t + 1 < p.tq) issue_s(qn + t + 1, t + 2 == p.tq);
+            issue_pv(qn + t, t == 0, t + 1 == p.tq);
+          }
+        } else {
+          for (int t = 0; t < p.tq; ++t) {
+            issue_s(qn + t, t + 1 == p.tq);
+            issue_pv(qn + t, t == 0, t + 1 == p.tq);
+          }
+        }
+        kv_ph ^= 1;
+        qn += p.tq;
       }
-      tc_commit(bar_o);
     }
   } else {
-    const int q = warp & 3;
+    // ===================== softmax + epilogue (warps 2..9) =====================
+    const int q = warp & 3;              // TMEM lane quarter
+    const int g = (warp - 2) >> 2;       // key half handled by this warp group
     const int row_in_tile = q * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    // sweep 1: row max
-    float mx = -INFINITY;
-    for (int c = 0; c < Skv; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + c, v);
-      tmem_ld_wait();
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int half = p.half;
+    int qn = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int fh = item / p.items_per_head;
+      const int frame = fh / p.heads, head = fh - frame * p.heads;
+      const int qt0 = (item - fh * p.items_per_head) * p.tq;
+      for (int t = 0; t < p.tq; ++t, ++qn) {
+        const int slot = p.nbuf == 2 ? (qn & 1) : 0;
+        const uint32_t use = p.nbuf == 2 ? (uint32_t)(qn >> 1) : (uint32_t)qn;
+        const uint32_t t_mine = tmem_base + (slot * 2 + g) * p.region + lane_off;
+        ATT_STAMP(0);
+        mbar_wait(&s_full[slot * 2 + g], use & 1);
+        tc_fence_after();
+        ATT_STAMP(1);
+        // ---- ONE sweep over this half of S (TMEM -> registers is the scarce resource: 64 B/clk per SM) ----
+        // The shift m of exp2(s*c - m) starts as the exact max of the first 32 columns and is only raised when a later
+        // chunk exceeds it by more than 2^8 (lazy rescale): then the already written P columns and the running sum are
+        // multiplied by the (exact) power-of-two-like factor exp2(m_old - m_new). Any shift gives the same softmax; this
+        // one keeps every term <= 2^8 without a separate max pass.
+        float m_scaled;
+        float sum;
+        {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          uint32_t va[32], vb[32];
+          m_scaled = -INFINITY;
+          auto emit = [&](const uint32_t (&v)[32], int c) {
+            float c0 = __uint_as_float(v[0]), c1 = __uint_as_float(v[1]), c2 = __uint_as_float(v[2]),
+                  c3 = __uint_as_float(v[3]);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    const float m_scaled = mx * p.scale_log2;
-    // sweep 2: probabilities -> bf16 pairs written over consumed S columns
-    float sum = 0.f;
-    for (int c = 0; c < Skv; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + c, v);
-      tmem_ld_wait();
-      uint32_t pk[16];
+            for (int j = 4; j < 32; j += 4) {
+              c0 = fmaxf(c0, __uint_as_float(v[j])); c1 = fmaxf(c1, __uint_as_float(v[j + 1]));
+              c2 = fmaxf(c2, __uint_as_float(v[j + 2])); c3 = fmaxf(c3, __uint_as_float(v[j + 3]));
+            }
+            const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2;
+            const bool raise = cm > m_scaled + 8.0f;
+            if (__any_sync(0xffffffffu, raise)) {
+              const float m_new = raise ? cm : m_scaled;
+              const float f = ex2_approx(m_scaled - m_new);  // 1 for the lanes that keep their shift; 0 at the start
+              for (int pc = 0; pc < (c >> 1); pc += 16) {
+                uint32_t pk[16];
+                tmem_ld16(t_mine + pc, pk);
+                tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled));
-        const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-        sum += __low2float(h) + __high2float(h);
-        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      tmem_st16(t_lane + (c >> 1), pk);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-
-    // normalise and store O
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const float inv = 1.0f / sum;
-    const int64_t row = static_cast<int64_t>(frame) * p.Sq + q_blk * ATT_BM + row_in_tile;
-    const bool row_ok = (q_blk * ATT_BM + row_in_tile) < p.Sq;
-    uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldo + head * ATT_D);
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+                  pk[j] = pack_bf16x2(__low2float(h) * f, __high2float(h) * f);
+                }
+                tmem_st16(t_mine + pc, pk);
+              }
+              s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+              m_scaled = m_new;
+            }
+            uint32_t pk[16];
 #pragma unroll
-    for (int c = 0; c < ATT_D; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + p.o_col + c, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dst[(c >> 3) + j] = make_uint4(
-              pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv),
-              pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
+            for (int j = 0; j < 16; j += 2) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled));
+              const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 2]), p.scale_log2, -m_scaled));
+              const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 3]), p.scale_log2, -m_scaled));
+              s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+              pk[j] = pack_bf16x2(e0, e1);
+              pk[j + 1] = pack_bf16x2(e2, e3);
+            }
+            tmem_st16(t_mine + (c >> 1), pk);  // columns [c/2, c/2+16): below every column still to be read
+          };
+          tmem_ld32(t_mine, va);
+          for (int c = 0; c < half; c += 64) {
+            tmem_ld_wait();
+            if (c + 32 < half) tmem_ld32(t_mine + c + 32, vb);
+            emit(va, c);
+            if (c + 32 < half) {
+              tmem_ld_wait();
+              if (c + 64 < half) tmem_ld32(t_mine + c + 64, va);
+              emit(vb, c + 32);
+            }
+          }
+          sum = (s0 + s1) + (s2 + s3);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[slot * 2 + g]);
+        ATT_STAMP(2);
+
+        // ---- exchange (max, sum) with the other key half ----
+        float* st = s_stat + slot * (2 * 2 * ATT_BM);
+        st[(g * 2 + 0) * ATT_BM + row_in_tile] = m_scaled;
+        st[(g * 2 + 1) * ATT_BM + row_in_tile] = sum;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float m_other = st[((g ^ 1) * 2 + 0) * ATT_BM + row_in_tile];
+        const float l_other = st[((g ^ 1) * 2 + 1) * ATT_BM + row_in_tile];
+        const float m_all = fmaxf(m_scaled, m_other);
+        const float w_mine = ex2_approx(m_scaled - m_all), w_other = ex2_approx(m_other - m_all);
+        const float inv = 1.0f / (w_mine * sum + w_other * l_other);
+        const float a_mine = w_mine * inv, a_other = w_other * inv;
+
+        // ---- O = a_0 O_0 + a_1 O_1 : this group normalises and stores output columns [32 g, 32 g + 32) ----
+        const uint32_t t_o_mine = t_mine + p.o_col + 32 * g;
+        const uint32_t t_o_other = tmem_base + (slot * 2 + (g ^ 1)) * p.region + lane_off + p.o_col + 32 * g;
+        ATT_STAMP(3);
+        mbar_wait(&o_full[slot * 2 + 0], use & 1);
+        mbar_wait(&o_full[slot * 2 + 1], use & 1);
+        tc_fence_after();
+        ATT_STAMP(4);
+        uint32_t o0[32], o1[32];
+        tmem_ld32(t_o_mine, o0);
+        tmem_ld32(t_o_other, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[slot]);  // slot free for the next S as soon as O is in registers
+        const int qrow = (qt0 + t) * ATT_BM + row_in_tile;
+        if (qrow < p.Sq) {
+          const int64_t row = static_cast<int64_t>(frame) * p.Sq + qrow;
+          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldo + head * ATT_D + 32 * g);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float r[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              r[e] = __uint_as_float(o0[8 * j + e]) * a_mine + __uint_as_float(o1[8 * j + e]) * a_other;
+            dst[j] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                                pack_bf16x2(r[6], r[7]));
+          }
+        }
+        ATT_STAMP(5);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
              int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, cudaStream_t stream) {
   RALD_REQUIRE(frames > 0 && heads > 0 && Sq > 0, "attn: bad sizes");
-  RALD_REQUIRE(Skv >= 16 && Skv <= 512 && Skv % 32 == 0, "attn: Skv=%d must be a multiple of 32 in [32, 512]", Skv);
+  RALD_REQUIRE(Skv >= 64 && Skv <= 512 && Skv % 64 == 0, "attn: Skv=%d must be a multiple of 64 in [64, 512]", Skv);
   RALD_REQUIRE(Sq % ATT_BM == 0, "attn: Sq=%d must be a multiple of 128", Sq);
   RALD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "attn: output not 16-byte aligned");
   CUtensorMap tmQ, tmK, tmV;
-  const uint32_t kv_box = Skv < 256 ? Skv : 256;
-  RALD_REQUIRE(Skv % kv_box == 0, "attn: Skv=%d must be <=256 or a multiple of 256", Skv);
+  const uint32_t kv_box = Skv / 2;  // one box per key half (<= 256 rows)
   RALD_TRY(make_tmap_2d_bf16(&tmQ, Q, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldq, ATT_BM));
   RALD_TRY(make_tmap_2d_bf16(&tmK, K, (uint64_t)frames * Skv, (uint64_t)heads * ATT_D, (uint64_t)ldk, kv_box));
   RALD_TRY(make_tmap_2d_bf16(&tmV, V, (uint64_t)frames * Skv, (uint64_t)heads * ATT_D, (uint64_t)ldv, kv_box));
@@ -203,24 +371,50 @@ int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void*
   p.ldo = ldo;
   p.Sq = Sq;
   p.Skv = Skv;
+  p.frames = frames;
+  p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.o_col = (Skv + ATT_D <= 512) ? (uint32_t)Skv : (uint32_t)(Skv / 2);
+  p.half = Skv / 2;
+  // half region: S occupies [0, half), P (bf16 pairs) [0, half/2), O (64 fp32 columns) right after P
+  p.o_col = p.half / 2 < 32 ? 32u : (uint32_t)(p.half / 2);
   uint32_t need = p.o_col + ATT_D;
-  if (need < (uint32_t)Skv) need = Skv;
-  uint32_t cols = 32;
-  while (cols < need) cols <<= 1;
-  p.tmem_cols = cols;
-  const int smem_bytes = (ATT_BM + 2 * Skv) * ATT_D * 2 + 1024 + 128;
+  if (need < (uint32_t)p.half) need = p.half;
+  uint32_t region = 32;
+  while (region < need) region <<= 1;
+  p.region = region;
+  p.nbuf = 4 * region <= 512 ? 2 : 1;
+  p.q_tiles = Sq / ATT_BM;
+  // query tiles per work item: rounds x (K/V load + tq tiles), in units of one tile
+  const int sms = device_sm_count();
+  const double kv_cost = 0.5 * Skv / 512.0;
+  int best_tq = 1;
+  double best = -1.0;
+  for (int tq = 1; tq <= p.q_tiles; ++tq) {
+    if (p.q_tiles % tq != 0) continue;
+    const long items = (long)frames * heads * (p.q_tiles / tq);
+    const double cost = (double)((items + sms - 1) / sms) * (kv_cost + tq);
+    if (best < 0 || cost < best - 1e-9) { best = cost; best_tq = tq; }
+  }
+  p.tq = best_tq;
+  p.items_per_head = p.q_tiles / p.tq;
+  p.num_items = frames * heads * p.items_per_head;
+  p.dbg = g_attn_dbg;
+  const int smem_bytes = 2 * ATT_QBYTES + 2 * Skv * ATT_D * 2 + 2 * 2 * 2 * ATT_BM * 4 + 1024 + 256;
   static int configured_bytes = 0;
   if (smem_bytes > configured_bytes) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured_bytes = smem_bytes;
   }
-  dim3 grid(Sq / ATT_BM, heads, frames);
+  const int grid = p.num_items < sms ? p.num_items : sms;
   ProfScope prof(FAM_ATTN, stream, 4.0 * frames * heads * Sq * Skv * ATT_D);
-  RALD_CHECK_CUDA(launch_pdl(attn_d64_kernel, grid, dim3(ATT_THREADS), smem_bytes, stream, tmQ, tmK, tmV, p));
+  RALD_CHECK_CUDA(launch_pdl(attn_d64_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, tmQ, tmK, tmV, p));
   RALD_LAUNCHED();
   return 0;
 }
 
 }  // namespace rald
+
+extern "C" int rald_attn_debug_buffer(unsigned long long* dev_buf) {
+  rald::g_attn_dbg = dev_buf;
+  return 0;
+}

@@ -59,12 +59,16 @@ def ln(rows, per_frame):
 
 ok = True
 ok &= attn(1, 1, 128, 64)
+ok &= attn(2, 3, 256, 384)
+ok &= attn(5, 8, 512, 256)
 ok &= attn(1, 1, 128, 128)
 ok &= attn(1, 1, 128, 256)
 ok &= attn(1, 1, 128, 512)
 ok &= attn(1, 8, 512, 512)
 ok &= attn(2, 8, 512, 64)
 ok &= attn(3, 8, 512, 512, amp=3.0)
+ok &= attn(2, 8, 512, 512, amp=5.0)
+ok &= attn(2, 8, 512, 64, amp=4.0)
 ok &= attn(64, 8, 512, 512, timing=True)
 ok &= attn(64, 8, 512, 64, timing=True)
 ok &= attn(8, 8, 512, 512, timing=True)
