@@ -137,8 +137,9 @@ def calibrate_occupancy(net, vae, cube, queries, seeds):
     percentile of one decode so that `logit > 0` (engine_generation.py:285) keeps ~5 % of the queries."""
     z = net.sample(cube, batch_seeds=seeds, cond_type="radar")
     lg = vae.decode(z, queries).squeeze(-1)
-    k = max(1, int(0.95 * lg[0].numel()))
-    shift = float(lg[0].flatten().kthvalue(k).values)
+    sub = lg[:, :: max(1, lg.shape[1] // 65536)].flatten()   # a strided subsample of every frame's logits
+    k = max(1, int(0.95 * sub.numel()))
+    shift = float(sub.kthvalue(k).values)
     with torch.no_grad():
         vae.to_outputs.bias -= shift
     return shift
@@ -269,9 +270,9 @@ def run_ours(args, rank, world, local_rank):
         q_d.copy_(q1_d.expand(F, Q, 3))    # the grid is uploaded once and repeated on the device
         pts, cnt = pipeline(cube_d, q_d)
         n = cnt.cpu()                      # device -> host: per-frame point counts ...
-        m = int(n.max()) if n.numel() else 0
-        out = pts[:, :min(m, cap)].cpu()   # ... and the occupied points only
-        d2h[0] = n.numel() * 4 + out.numel() * 4
+        out = [pts[i, :min(int(k), cap)].to("cpu", non_blocking=True) for i, k in enumerate(n.tolist())]
+        torch.cuda.current_stream().synchronize()   # ... and each frame's occupied points only
+        d2h[0] = n.numel() * 4 + sum(o.numel() for o in out) * 4
         return out, n
 
     def barrier():

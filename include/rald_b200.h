@@ -61,6 +61,11 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
                    int bn_hint, void* stream);
 
+/* rald_gemm_bf16 with out_mode 0 whose output columns with (col % f16_period) >= f16_start are written as IEEE fp16
+ * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
+int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                           const float* bias, int M, int N, int K, int f16_start, int f16_period, void* stream);
+
 /* Debug hook: when dev_buf != NULL every GEMM CTA stores %globaltimer stamps of its first tile at dev_buf[cta*8 + i]
  * (0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done, 6 exit). */
 int rald_gemm_debug_buffer(unsigned long long* dev_buf);
@@ -70,8 +75,10 @@ int rald_gemm_debug_buffer(unsigned long long* dev_buf);
  * 4 O ready, 5 stored. */
 int rald_attn_debug_buffer(unsigned long long* dev_buf);
 
-/* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512, scores kept in TMEM.
- * Q: [frames*Sq, >= heads*64] bf16 (ldq), K/V: [frames*Skv, ...] bf16, O: [frames*Sq, ...] bf16; head h uses
+/* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512 (multiple of 64), scores kept in TMEM.
+ * Q: [frames*Sq, >= heads*64] bf16 (ldq), K: [frames*Skv, ...] bf16, V: [frames*Skv, ...] **fp16** (the probabilities
+ * are produced as fp16 by a packed exp2, and tcgen05 kind::f16 needs both operands of P V in one format),
+ * O: [frames*Sq, ...] bf16; head h uses
  * columns [h*64, h*64+64). Replaces the two einsums + softmax of CrossAttention.forward
  * (model/models_radar_generation.py:66-75) and Attention.forward (model/models_ae.py:91-104). */
 int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,

@@ -27,6 +27,8 @@ _SIGNATURES = {
     "rald_prof_collect": [c_int, c_void_p, c_void_p, c_void_p],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_gemm_bf16_f16cols": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_void_p],
     "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,

@@ -137,7 +137,7 @@ extern "C" int rald_ae_stack(const rald_ae_weights* w, const rald_dit_workspace*
       const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w->w_ff2) + (int64_t)n * 4 * dim * dim;
       RALD_TRY(ln_rows(h, dim, w->ln1_w + (int64_t)n * dim, w->ln1_b + (int64_t)n * dim, 0, 0, 0, ws->xn, dim, 0, T,
                        dim, 1e-5f, st));
-      RALD_TRY(gemm_bf16(ws->xn, dim, w_qkv, dim, ws->qkv, 3 * dim, nullptr, nullptr, 0, (int)T, 3 * dim, dim, 0, 0, st));
+      RALD_TRY(gemm_bf16_f16cols(ws->xn, dim, w_qkv, dim, ws->qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
       RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws->att, dim, nf, heads, M, M, scale,
                         st));
       RALD_TRY(gemm_bf16(ws->att, dim, w_o, dim, h, dim, w->b_o + (int64_t)n * dim, h, dim, (int)T, dim, dim, 1, 0, st));

@@ -17,6 +17,12 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                          static_cast<cudaStream_t>(stream));
 }
 
+int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                           const float* bias, int M, int N, int K, int f16_start, int f16_period, void* stream) {
+  return rald::gemm_bf16_f16cols(A, lda, W, ldw, out, ldo, bias, M, N, K, f16_start, f16_period,
+                                 static_cast<cudaStream_t>(stream));
+}
+
 int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                   int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* stream) {
   return rald::attn_d64(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, Skv, scale,

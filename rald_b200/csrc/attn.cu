@@ -149,7 +149,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc_o = make_idesc(FMT_BF16, ATT_BM, ATT_D, 0, 1);
+      const uint32_t idesc_o = make_idesc(FMT_F16, ATT_BM, ATT_D, 0, 1);  // P fp16 (TMEM) x V fp16 (smem)
       const uint32_t idesc_s = make_idesc(FMT_BF16, ATT_BM, p.half, 0, 0);
       uint32_t kv_ph = 0;
       int qn = 0;
@@ -239,10 +239,10 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float m_scaled;
         float sum;
         {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float s0 = 0.f;
           uint32_t va[32], vb[32];
-          m_scaled = -INFINITY;
-          auto emit = [&](const uint32_t (&v)[32], int c) {
+          // first shift: exact max of the first 32 columns (one extra pass over registers, not over TMEM)
+          auto chunk_max = [&](const uint32_t (&v)[32]) {
             float c0 = __uint_as_float(v[0]), c1 = __uint_as_float(v[1]), c2 = __uint_as_float(v[2]),
                   c3 = __uint_as_float(v[3]);
 #pragma unroll
@@ -250,41 +250,55 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               c0 = fmaxf(c0, __uint_as_float(v[j])); c1 = fmaxf(c1, __uint_as_float(v[j + 1]));
               c2 = fmaxf(c2, __uint_as_float(v[j + 2])); c3 = fmaxf(c3, __uint_as_float(v[j + 3]));
             }
-            const float cm = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2;
-            const bool raise = cm > m_scaled + 8.0f;
+            return fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2;
+          };
+          // P is fp16 (11-bit mantissa) and so is V (kind::f16 needs both operands of one MMA in the same format; the
+          // V projection GEMM writes fp16). Per pair of scores: two FFMA (x = s*c - m), one f16x2 pack, ONE packed
+          // MUFU exp2 whose result already is the packed MMA operand, and one packed add into the chunk sum (a 16-leaf
+          // fp16 tree, widened to fp32 once per 32 columns). No per-element max: a shift that is too low shows up as
+          // an fp16 overflow (+inf) of the chunk sum, and only then is the shift raised to the chunk's exact maximum,
+          // the earlier P columns and the running sum rescaled, and the chunk redone.
+          auto chunk_probs = [&](const uint32_t (&v)[32], uint32_t (&ps)[16]) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              ps[j] = ex2_f16x2(pack_f16x2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled),
+                                           fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled)));
+            uint32_t t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = add_f16x2(ps[2 * j], ps[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = add_f16x2(t[2 * j], t[2 * j + 1]);
+            const float2 a = unpack_f16x2(add_f16x2(t[0], t[1])), b = unpack_f16x2(add_f16x2(t[2], t[3]));
+            return (a.x + a.y) + (b.x + b.y);
+          };
+          auto emit = [&](const uint32_t (&v)[32], int c) {
+            uint32_t ps[16];
+            float cs = chunk_probs(v, ps);
+            const bool raise = !(cs < 3.0e38f);  // +inf (or NaN): some probability left the fp16 range
             if (__any_sync(0xffffffffu, raise)) {
-              const float m_new = raise ? cm : m_scaled;
-              const float f = ex2_approx(m_scaled - m_new);  // 1 for the lanes that keep their shift; 0 at the start
+              const float m_new = raise ? chunk_max(v) : m_scaled;
+              const float f = ex2_approx(m_scaled - m_new);  // 1 for the lanes that keep their shift
+              const uint32_t f2 = pack_f16x2(f, f);
               for (int pc = 0; pc < (c >> 1); pc += 16) {
                 uint32_t pk[16];
                 tmem_ld16(t_mine + pc, pk);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
-                  pk[j] = pack_bf16x2(__low2float(h) * f, __high2float(h) * f);
-                }
+                for (int j = 0; j < 16; ++j) pk[j] = mul_f16x2(pk[j], f2);
                 tmem_st16(t_mine + pc, pk);
               }
-              s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+              s0 *= f;
               m_scaled = m_new;
+              cs = chunk_probs(v, ps);
             }
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled));
-              const float e2 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 2]), p.scale_log2, -m_scaled));
-              const float e3 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 3]), p.scale_log2, -m_scaled));
-              s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-              pk[j] = pack_bf16x2(e0, e1);
-              pk[j + 1] = pack_bf16x2(e2, e3);
-            }
-            tmem_st16(t_mine + (c >> 1), pk);  // columns [c/2, c/2+16): below every column still to be read
+            s0 += cs;
+            tmem_st16(t_mine + (c >> 1), ps);  // columns [c/2, c/2+16): below every column still to be read
           };
           tmem_ld32(t_mine, va);
+          tmem_ld_wait();
+          m_scaled = chunk_max(va);
           for (int c = 0; c < half; c += 64) {
-            tmem_ld_wait();
+            if (c != 0) tmem_ld_wait();
             if (c + 32 < half) tmem_ld32(t_mine + c + 32, vb);
             emit(va, c);
             if (c + 32 < half) {
@@ -293,7 +307,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               emit(vb, c + 32);
             }
           }
-          sum = (s0 + s1) + (s2 + s3);
+          sum = s0;
         }
         tmem_st_wait();
         tc_fence_before();

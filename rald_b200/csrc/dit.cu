@@ -38,7 +38,8 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
     const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w.w_ff2) + (int64_t)n * 4 * dim * dim;
     // x += attn1(adaLN1(x))
     RALD_TRY(ln_rows(ws.h, dim, m0, m0 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
-    RALD_TRY(gemm_bf16(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, nullptr, 0, (int)T, 3 * dim, dim, 0, 0, st));
+    // q | k in bf16, v in fp16 (attn_d64 multiplies fp16 probabilities with fp16 values)
+    RALD_TRY(gemm_bf16_f16cols(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
     RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws.att, dim, frames, heads, M, M,
                       scale, st));
     RALD_TRY(gemm_bf16(ws.att, dim, w_o1, dim, ws.h, dim, w.b_o1 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,

@@ -24,7 +24,8 @@ namespace rald {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_EPI_WARPS = 8;
 constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
 
@@ -33,10 +34,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NBUF = BN >= 256 ? 1 : 2;              // staging tiles per epilogue warp
-  static constexpr int STG_TOTAL = 4 * NBUF * STG_BYTES;
+  static constexpr int NBUF = 1;                               // staging tiles per epilogue warp
+  static constexpr int STG_TOTAL = GEMM_EPI_WARPS * NBUF * STG_BYTES;
   static constexpr int BIAS_BYTES = 2 * BN * 4;
-  static constexpr int FIXED = 1024 /*align slack*/ + 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES;
+  // no alignment slack: dynamic shared memory starts 1024-byte aligned (checked at kernel entry)
+  static constexpr int FIXED = 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES;
   static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
@@ -52,6 +54,7 @@ struct GemmParams {
   int64_t resid_mod;   // > 0: residual row = row % resid_mod (a [resid_mod, N] table broadcast over frames)
   int M, N, K;
   int num_m_blks, num_n_blks;
+  int f16_start, f16_period;  // bf16 mode: output columns with (col % f16_period) >= f16_start are written as fp16
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
@@ -133,8 +136,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // accumulator columns consumed per staged 128-byte output row
   constexpr int CHUNK = OUT_MODE == 1 ? 32 : (OUT_MODE == 0 ? 64 : 128);
   static_assert(EPI == EPI_GENERIC || BN % CHUNK == 0, "tile narrower than one staged output row");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128-byte swizzle atoms need 1024-byte aligned tiles
   uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES;                    // 1024-byte aligned (stage sizes are)
   float* s_bias = reinterpret_cast<float*>(stg + Cfg::STG_TOTAL);     // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + Cfg::BIAS_BYTES);
@@ -159,7 +163,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -228,10 +232,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp is allowed to touch
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter: warp pair member `hs` takes the even / odd column chunks of the tile.
+    const int q = warp & 3;          // TMEM lane quarter this warp is allowed to touch
+    const int ew = warp - 2;         // 0..7
+    const int hs = ew >> 2;          // 0: even chunks, 1: odd chunks
     const int row_in_tile = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
     int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -242,11 +249,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* bias_s = s_bias + acc * BN;
       if (EPI != EPI_GENERIC) {
         // bias of this tile -> smem while the MMAs of the tile are still running
-        for (int j = et; j < BN; j += 128) {
+        for (int j = et; j < BN; j += 32 * GEMM_EPI_WARPS) {
           const int col = n_blk * BN + j;
           bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
@@ -256,7 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int64_t row = static_cast<int64_t>(m_blk) * GEMM_BM + row_in_tile;
         const bool row_ok = row < p.M;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hs; c < BN / 32; c += 2) {
           const int col0 = n_blk * BN + c * 32;
           if (col0 >= p.N) break;
           uint32_t v[32];
@@ -270,8 +277,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         constexpr int NCHUNK = BN / CHUNK;
         const int row0 = m_blk * GEMM_BM + q * 32;
+        if (NCHUNK == 1 && hs == 1) {
+          // a single 128-byte output row per tile: the odd warps have no chunk, they only release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
+        for (int c = hs; c < NCHUNK; c += 2) {
           const int acol0 = c * CHUNK;                 // accumulator column inside the tile
           const bool live = n_blk * BN + acol0 < p.N;  // chunks past N are read (uniform TMEM hand-off) but not stored
           uint32_t o[32];                              // one 128-byte output row
@@ -281,15 +294,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + bias_s[acol0 + j]);
           } else if (OUT_MODE == 0) {
+            // 64-column chunks never straddle an fp16 / bf16 boundary (boundaries are multiples of 64 columns)
+            const bool as_f16 = p.f16_period > 0 && ((n_blk * BN + acol0) % p.f16_period) >= p.f16_start;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t v[32];
               tmem_ld32(t_row + acol0 + 32 * h, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                o[16 * h + j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bias_s[acol0 + 32 * h + 2 * j],
-                                            __uint_as_float(v[2 * j + 1]) + bias_s[acol0 + 32 * h + 2 * j + 1]);
+              for (int j = 0; j < 16; ++j) {
+                const float lo = __uint_as_float(v[2 * j]) + bias_s[acol0 + 32 * h + 2 * j];
+                const float hi = __uint_as_float(v[2 * j + 1]) + bias_s[acol0 + 32 * h + 2 * j + 1];
+                o[16 * h + j] = as_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+              }
             }
           } else {
 #pragma unroll
@@ -308,8 +325,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          if (c == NCHUNK - 1) {
-            // every TMEM read of this accumulator has completed -> hand it back to the MMA warp now
+          if (c + 2 >= NCHUNK) {
+            // every TMEM read of this accumulator by this warp has completed -> hand it back to the MMA warp now
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -317,7 +334,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (live) {
             if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the staging tile about to be overwritten was read
             __syncwarp();
-            const uint32_t sdst = smem_u32(stg + (q * NBUF + sbuf) * STG_BYTES) + lane * 128;
+            const uint32_t sdst = smem_u32(stg + (ew * NBUF + sbuf) * STG_BYTES) + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -325,7 +342,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
               const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
-              const void* src = stg + (q * NBUF + sbuf) * STG_BYTES;
+              const void* src = stg + (ew * NBUF + sbuf) * STG_BYTES;
               if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, src, ocol, row0);
               else tma_store_2d(&tmO, src, ocol, row0);
               bulk_commit_group();
@@ -372,9 +389,27 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
   return gemm_bf16_ex(A, lda, W, ldw, out, ldo, bias, resid, ldr, 0, M, N, K, out_mode, bn_hint, stream);
 }
 
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                     const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
+                     int f16_start, int f16_period, cudaStream_t stream);
+
 int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                  const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
                  cudaStream_t stream) {
+  return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, resid_mod, M, N, K, out_mode, bn_hint, 0, 0, stream);
+}
+
+int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                      int M, int N, int K, int f16_start, int f16_period, cudaStream_t stream) {
+  RALD_REQUIRE(f16_period > 0 && f16_period % 64 == 0 && f16_start % 64 == 0 && f16_start < f16_period,
+               "gemm: fp16 column window start=%d period=%d must be multiples of 64", f16_start, f16_period);
+  RALD_REQUIRE(N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
+  return gemm_impl(A, lda, W, ldw, out, ldo, bias, nullptr, 0, 0, M, N, K, 0, 0, f16_start, f16_period, stream);
+}
+
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                     const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
+                     int f16_start, int f16_period, cudaStream_t stream) {
   RALD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RALD_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   RALD_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
@@ -428,6 +463,9 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   p.num_m_blks = m_blks;
   p.num_n_blks = (N + bn - 1) / bn;
   p.dbg = g_gemm_dbg;
+  p.f16_start = f16_start;
+  p.f16_period = f16_period;
+  RALD_REQUIRE(f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));

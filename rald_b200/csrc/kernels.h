@@ -20,6 +20,11 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
                  const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
                  cudaStream_t stream);
 
+// bf16 output in which the columns with (col % f16_period) >= f16_start are written as fp16 instead: the V
+// projections feeding attn_d64 (fp16 probabilities x fp16 values on the tensor cores).
+int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                      int M, int N, int K, int f16_start, int f16_period, cudaStream_t stream);
+
 // attn.cu ------------------------------------------------------------------------------------------
 // O[f, :, h*64:(h+1)*64] = softmax(Q K^T * scale) V per (frame f, head h); head_dim 64; Skv <= 512.
 // Q rows = frames*Sq, K/V rows = frames*Skv; head h lives at columns [h*64, h*64+64) of each operand.

@@ -44,7 +44,7 @@ def geglu_pack_index(inner: int, device) -> torch.Tensor:
 
 
 def default_microbatch() -> int:
-    return int(os.environ.get("RALD_B200_MICROBATCH", "16"))
+    return int(os.environ.get("RALD_B200_MICROBATCH", "32"))
 
 
 def graphs_enabled() -> bool:
@@ -186,8 +186,9 @@ class DitRuntime:
         rows = tokens_bf16.shape[0]
         n = self.depth * 2 * self.dim
         out = torch.empty(rows, n, device=self.device, dtype=torch.bfloat16)
-        _lib.call("rald_gemm_bf16", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim, out.data_ptr(), n,
-                  0, 0, 0, rows, n, self.dim, 0, 0, _lib.cur_stream())
+        # per block the columns are [K (bf16) | V (fp16)]: the attention kernel multiplies fp16 P with fp16 V
+        _lib.call("rald_gemm_bf16_f16cols", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim,
+                  out.data_ptr(), n, 0, rows, n, self.dim, self.dim, 2 * self.dim, _lib.cur_stream())
         return out
 
     # ------------------------------------------------------------------ entry points

@@ -8,7 +8,7 @@ L = _lib.lib()
 for (B, H, Sq, Skv) in [(64, 8, 512, 512), (64, 8, 512, 64), (1, 8, 512, 512)]:
     D = H * 64
     q = torch.randn(B * Sq, D, device=dev).bfloat16(); k = torch.randn(B * Skv, D, device=dev).bfloat16()
-    v = torch.randn(B * Skv, D, device=dev).bfloat16(); o = torch.zeros(B * Sq, D, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(B * Skv, D, device=dev).half(); o = torch.zeros(B * Sq, D, device=dev, dtype=torch.bfloat16)
     dbg = torch.zeros(16 * 2 * 8, dtype=torch.int64, device=dev)
     args = (q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, o.data_ptr(), D, B, H, Sq, Skv, 0.125, _lib.cur_stream())
     _lib.call("rald_attn_d64", *args)

@@ -14,7 +14,7 @@ def attn(B, H, Sq, Skv, amp=1.0, timing=False):
     D = H * 64
     q = (torch.randn(B * Sq, D, device=dev) * amp).bfloat16()
     k = (torch.randn(B * Skv, D, device=dev) * amp).bfloat16()
-    v = torch.randn(B * Skv, D, device=dev).bfloat16()
+    v = torch.randn(B * Skv, D, device=dev).half()   # V is fp16 (see include/rald_b200.h)
     o = torch.zeros(B * Sq, D, device=dev, dtype=torch.bfloat16)
     st = _lib.cur_stream()
     args = (q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, o.data_ptr(), D, B, H, Sq, Skv, 0.125, st)
