@@ -348,6 +348,15 @@ def run_ours(args, rank, world, local_rank):
     step_resident()
     _lib.prof_enable(*fams)
     step_resident()
+    gms, gwork = _lib.prof_dump("gemm")
+    shapes = {}
+    for t, wk in zip(gms.tolist(), gwork.tolist()):
+        a = shapes.setdefault(wk, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+    gemm_shapes = [{"gflop_per_launch": round(wk / 1e9, 3), "launches": n, "ms": round(t, 3),
+                    "tflops": round(wk * n / (t * 1e-3) / 1e12, 1) if t > 0 else None}
+                   for wk, (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:8]
     breakdown = {}
     for f in fams:
         ms, work, n = _lib.prof_collect(f)
@@ -386,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
                         "h2d_bytes_per_step": cube_h.numel() * 4 + q_h.numel() * 4, "d2h_bytes_per_step": d2h[0]},
                 "gpu_launches": int(launches),
                 "latency_b1": lat, "tflops_step": gflop_step / (ms_res / args.steps),
-                "roofline": roofline, "kernel_breakdown": breakdown, "clocks": clock_rec,
+                "roofline": roofline, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes, "clocks": clock_rec,
                 "occupancy_bias_shift": shift}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(Q)

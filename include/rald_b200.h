@@ -50,6 +50,8 @@ void rald_launch_count_add(uint64_t n);
 #define RALD_FAM_XATTN 9
 int rald_prof_enable(unsigned family_mask);
 int rald_prof_collect(int family, double* total_ms, double* total_work, int64_t* launches);
+/* Per-launch records of one family (HOST arrays ms[cap], work[cap]); returns how many were written, -1 on error. */
+int64_t rald_prof_dump(int family, float* ms, double* work, int64_t cap);
 
 /* out = epilogue(A[M,K] @ W[N,K]^T), A and W bf16, fp32 accumulation on tcgen05 tensor cores.
  *   out_mode 0: out bf16 [M,N] (+bias) (+resid f32, added before rounding)

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "rald_launch_count_add": [ctypes.c_uint64],
     "rald_prof_enable": [ctypes.c_uint],
     "rald_prof_collect": [c_int, c_void_p, c_void_p, c_void_p],
+    "rald_prof_dump": [c_int, c_void_p, c_void_p, c_i64],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rald_gemm_bf16_f16cols": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int,
@@ -68,7 +69,7 @@ _SIGNATURES = {
     "rald_occupancy_ws_elems": [c_int, c_i64],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
-             "rald_occupancy_ws_elems": c_i64}
+             "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64}
 
 
 class RaldError(RuntimeError):
@@ -140,3 +141,14 @@ def prof_collect(family: str):
     check(lib().rald_prof_collect(FAMILIES[family], ctypes.addressof(ms), ctypes.addressof(work), ctypes.addressof(n)),
           "rald_prof_collect")
     return ms.value, work.value, n.value
+
+
+def prof_dump(family: str, cap: int = 1 << 16):
+    """[(ms, work)] of every recorded launch of one kernel family since prof_enable()."""
+    import numpy as np
+    ms = np.zeros(cap, dtype=np.float32)
+    work = np.zeros(cap, dtype=np.float64)
+    n = int(lib().rald_prof_dump(FAMILIES[family], ms.ctypes.data, work.ctypes.data, cap))
+    if n < 0:
+        raise RaldError("rald_prof_dump failed")
+    return ms[:n], work[:n]

@@ -180,3 +180,18 @@ extern "C" int rald_prof_collect(int family, double* total_ms, double* total_wor
   if (launches) *launches = n;
   return 0;
 }
+
+// Per-record dump of one family: ms[i], work[i] for up to `cap` launches (returns the number written).
+extern "C" int64_t rald_prof_dump(int family, float* ms, double* work, int64_t cap) {
+  using namespace rald;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int64_t n = 0;
+  for (auto& r : g_prof) {
+    if (r.family != family || n >= cap) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) return -1;
+    ms[n] = t; work[n] = r.work; ++n;
+  }
+  return n;
+}

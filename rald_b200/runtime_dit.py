@@ -44,7 +44,7 @@ def geglu_pack_index(inner: int, device) -> torch.Tensor:
 
 
 def default_microbatch() -> int:
-    return int(os.environ.get("RALD_B200_MICROBATCH", "32"))
+    return int(os.environ.get("RALD_B200_MICROBATCH", "64"))
 
 
 def graphs_enabled() -> bool:
