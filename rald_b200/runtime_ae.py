@@ -176,6 +176,8 @@ class AeRuntime:
         B, Q, _ = queries.shape
         queries = queries.contiguous().float()
         logits = torch.empty(B, Q, device=self.device, dtype=torch.float32)
+        if Q == 0:
+            return logits
         _lib.call("rald_ae_query", queries.data_ptr(), B, Q, self.wpe_bf16.data_ptr(), self.pe_bias.data_ptr(),
                   self.q_ln_w.data_ptr(), self.q_ln_b.data_ptr(), kp.data_ptr(), vp.data_ptr(), c0.data_ptr(),
                   self.freq24.ctypes.data, logits.data_ptr(), self.dim, self.module.num_latents, _lib.cur_stream())
