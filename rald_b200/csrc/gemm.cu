@@ -16,6 +16,8 @@
 // Replaces, for every nn.Linear on the reference hot path, the cuBLAS sgemm + separate elementwise ops:
 //   model/models_radar_generation.py:58-64 (to_q/to_k/to_v), :76 (to_out + residual :166-168),
 //   :91-95 (GEGLU proj + gelu gate), :113 (ff out); model/models_ae.py:60-62, 78-80, 87-105.
+#include <stdlib.h>
+
 #include "host.cuh"
 #include "ptx.cuh"
 #include "kernels.h"
@@ -29,10 +31,13 @@ constexpr int GEMM_EPI_WARPS = 8;
 constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
 
-template <int BN>
+// CG = 1: one CTA computes a 128 x BN tile. CG = 2: a CTA pair (cta_group::2, the two SMs of a TPC) computes a
+// 256 x BN tile with ONE 256-row MMA per K step; each CTA stages its 128 rows of A and only HALF of the W tile, so
+// the shared-memory fill traffic per flop drops by a third and the ring gets deeper.
+template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBUF = 1;                               // staging tiles per epilogue warp
   static constexpr int STG_TOTAL = GEMM_EPI_WARPS * NBUF * STG_BYTES;
@@ -126,11 +131,15 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 }
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE, int EPI>
+template <int BN, int OUT_MODE, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-processing unit (CTA or CTA pair)
+  const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = GEMM_BM * CG;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBUF = Cfg::NBUF;
   // accumulator columns consumed per staged 128-byte output row
@@ -163,16 +172,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();               // A (and an in-place residual) come from the preceding kernel
@@ -184,28 +199,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       GEMM_STAMP(1);
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile / p.num_n_blks;
         const int n_blk = tile - m_blk * p.num_n_blks;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          if (CG == 2) {
+            // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
+            // to the LEADER's full barrier, on which only the leader arrives
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * GEMM_BM);
+            tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_BF16, GEMM_BM, BN, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_BF16, TILE_M, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
@@ -222,12 +245,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
-            mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CG == 2) tc_commit_pair(&empty_bar[s]);
+          else tc_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) tc_commit_pair(&tmem_full_bar[acc]);
+        else tc_commit(&tmem_full_bar[acc]);
         if (it == 0) GEMM_STAMP(3);
       }
     }
@@ -241,12 +269,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
     int sbuf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
       const int m_blk = tile / p.num_n_blks;
       const int n_blk = tile - m_blk * p.num_n_blks;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       float* bias_s = s_bias + acc * BN;
+      // the accumulator is handed back on the LEADER's barrier (its MMA thread waits for both CTAs' epilogues)
+      auto release_acc = [&]() {
+        if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      };
       if (EPI != EPI_GENERIC) {
         // bias of this tile -> smem while the MMAs of the tile are still running
         for (int j = et; j < BN; j += 32 * GEMM_EPI_WARPS) {
@@ -260,7 +293,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (it == 0 && threadIdx.x == 64) GEMM_STAMP(4);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (EPI == EPI_GENERIC) {
-        const int64_t row = static_cast<int64_t>(m_blk) * GEMM_BM + row_in_tile;
+        const int64_t row = static_cast<int64_t>(m_blk) * TILE_M + cta_rank * GEMM_BM + row_in_tile;
         const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int c = hs; c < BN / 32; c += 2) {
@@ -273,15 +306,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) release_acc();
       } else {
         constexpr int NCHUNK = BN / CHUNK;
-        const int row0 = m_blk * GEMM_BM + q * 32;
+        const int row0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
         if (NCHUNK == 1 && hs == 1) {
           // a single 128-byte output row per tile: the odd warps have no chunk, they only release the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc();
         }
 #pragma unroll 1
         for (int c = hs; c < NCHUNK; c += 2) {
@@ -329,7 +362,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // every TMEM read of this accumulator by this warp has completed -> hand it back to the MMA warp now
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc();
           }
           if (live) {
             if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the staging tile about to be overwritten was read
@@ -357,28 +390,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's smem / barriers / TMEM stay valid until both CTAs are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     if (lane == 0) GEMM_STAMP(6);
   }
 }
 
-template <int BN, int OUT_MODE, int EPI>
+template <int BN, int OUT_MODE, int EPI, int CG = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI>;
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int num_tiles = p.num_m_blks * p.num_n_blks;
-  int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  const int num_tiles = p.num_m_blks * p.num_n_blks;       // tiles of (128 * CG) x BN
+  const int max_units = max_ctas / CG;
+  const int units = num_tiles < max_units ? num_tiles : max_units;
   ProfScope prof(FAM_GEMM, stream, 2.0 * p.M * p.N * p.K);
-  RALD_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmO, p));
+  RALD_CHECK_CUDA(launch_pdl_cluster(kern, dim3(units * CG), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, (unsigned)CG,
+                                     tmA, tmB, tmO, p));
   RALD_LAUNCHED();
   return 0;
 }
@@ -450,6 +487,16 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     epi = EPI_TMA_STORE;
   }
 
+  // CTA pairs: 256 x 256 tiles when the problem still fills the machine with them (large-batch regime)
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("RALD_B200_GEMM_PAIR");
+    pair_env = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  const int m_blks2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const bool pair = pair_env == 1 && bn_hint >= 0 && bn == 256 && epi != EPI_GENERIC && N % 256 == 0 &&
+                    (long)m_blks2 * (N / 256) >= sms / 2;
+
   GemmParams p;
   p.out = out;
   p.ldo = ldo;
@@ -460,7 +507,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.M = M;
   p.N = N;
   p.K = K;
-  p.num_m_blks = m_blks;
+  p.num_m_blks = pair ? m_blks2 : m_blks;
   p.num_n_blks = (N + bn - 1) / bn;
   p.dbg = g_gemm_dbg;
   p.f16_start = f16_start;
@@ -469,13 +516,19 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
 
   CUtensorMap tmA, tmB, tmO;
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
-  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
+  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1));
   } else {
     tmO = tmA;
   }
 
+  if (pair) {
+    if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
+    if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
+    if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2>(tmA, tmB, tmO, p, sms, stream);
+    return launch_gemm<256, 1, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
+  }
 #define RALD_GEMM_LAUNCH(BN_, MODE_, EPI_) return launch_gemm<BN_, MODE_, EPI_>(tmA, tmB, tmO, p, sms, stream)
 #define RALD_GEMM_BN(MODE_, EPI_)                   \
   switch (bn) {                                     \
