@@ -27,6 +27,14 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
   const int64_t ld_ctx = (int64_t)depth * 2 * dim;
   const __nv_bfloat16* ctx = reinterpret_cast<const __nv_bfloat16*>(ctxkv);
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws.qkv);
+  // Optional (RALD_B200_WPREFETCH=1): in the latency-bound small-batch regime every weight comes from DRAM (0.33 GB
+  // per evaluation > L2), so each GEMM can prefetch the weights of the GEMM after it into L2. Measured on B200 at
+  // batch 1: 55.6 ms -> 76 ms per frame (prefetch issued at kernel entry: it competes with the kernel's own
+  // latency-critical loads) / 83 ms (issued after the operands landed: it delays the kernel's completion, which the
+  // programmatic-dependent successor waits for). Off by default.
+  static const bool pf_env = [] { const char* e = getenv("RALD_B200_WPREFETCH"); return e != nullptr && e[0] == '1'; }();
+  const bool pf = pf_env && T <= 2048;
+  const size_t wsz = (size_t)dim * dim * 2;  // one dim x dim bf16 matrix
   for (int n = 0; n < depth; ++n) {
     const float* m0 = mod + ((int64_t)n * 3 + 0) * 2 * dim;
     const float* m1 = mod + ((int64_t)n * 3 + 1) * 2 * dim;
@@ -40,22 +48,30 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
     // x += attn1(adaLN1(x))
     RALD_TRY(ln_rows(ws.h, dim, m0, m0 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
     // q | k in bf16, v in fp16 (attn_d64 multiplies fp16 probabilities with fp16 values)
+    if (pf) gemm_prefetch_next(w_o1, wsz);
     RALD_TRY(gemm_bf16_f16cols(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
     RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws.att, dim, frames, heads, M, M,
                       scale, st));
+    if (pf) gemm_prefetch_next(w_q2, wsz);
     RALD_TRY(gemm_bf16(ws.att, dim, w_o1, dim, ws.h, dim, w.b_o1 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
                        0, st));
     // x += attn2(adaLN2(x), context)
     RALD_TRY(ln_rows(ws.h, dim, m1, m1 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
+    if (pf) gemm_prefetch_next(w_o2, wsz);
     RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
     RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx, ws.att,
                       dim, frames, heads, M, L, scale, st));
+    if (pf) gemm_prefetch_next(w_ff1, 8 * wsz);
     RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
                        0, st));
     // x += ff(adaLN3(x))
     RALD_TRY(ln_rows(ws.h, dim, m2, m2 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
+    if (pf) gemm_prefetch_next(w_ff2, 4 * wsz);
     RALD_TRY(gemm_bf16(ws.xn, dim, w_ff1, dim, ws.ff, 4 * dim, w.b_ff1 + (int64_t)n * 8 * dim, nullptr, 0, (int)T,
                        8 * dim, dim, 2, 0, st));
+    if (pf)  // next block's (or, after the last block, the next evaluation's first) QKV weights
+      gemm_prefetch_next(reinterpret_cast<const __nv_bfloat16*>(w.w_qkv) + (int64_t)((n + 1) % depth) * 3 * dim * dim,
+                         3 * wsz);
     RALD_TRY(gemm_bf16(ws.ff, 4 * dim, w_ff2, 4 * dim, ws.h, dim, w.b_ff2 + (int64_t)n * dim, ws.h, dim, (int)T, dim,
                        4 * dim, 1, 0, st));
   }

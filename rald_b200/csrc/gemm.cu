@@ -59,11 +59,15 @@ struct GemmParams {
   int64_t resid_mod;   // > 0: residual row = row % resid_mod (a [resid_mod, N] table broadcast over frames)
   int M, N, K;
   int num_m_blks, num_n_blks;
+  const uint8_t* pf_ptr;      // weights of the NEXT GEMM in the stream, prefetched into L2 by this kernel's idle
+  uint32_t pf_bytes;          // epilogue threads (small-batch regime: hides the DRAM latency of the next launch)
   int f16_start, f16_period;  // bf16 mode: output columns with (col % f16_period) >= f16_start are written as fp16
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
 static unsigned long long* g_gemm_dbg = nullptr;
+static thread_local const void* g_pf_ptr = nullptr;   // consumed by the next GEMM launch of this thread
+static thread_local size_t g_pf_bytes = 0;
 #define GEMM_STAMP(slot)                                                        \
   do {                                                                          \
     if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + (slot)] = global_timer_ns();   \
@@ -291,6 +295,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       if (it == 0 && threadIdx.x == 64) GEMM_STAMP(4);
+      if (it == 0 && p.pf_bytes != 0) {
+        // This CTA's own operands have landed (its first accumulator is complete): now pull the NEXT GEMM's weights
+        // into L2, 16 KB per request, spread over the epilogue threads of all CTAs. Issued here rather than at kernel
+        // entry so that the prefetch does not compete with this kernel's own latency-critical loads.
+        constexpr uint32_t PF_CHUNK = 16384;
+        const uint32_t nreq = (p.pf_bytes + PF_CHUNK - 1) / PF_CHUNK;
+        for (uint32_t r = blockIdx.x * 256u + (uint32_t)et; r < nreq; r += gridDim.x * 256u) {
+          const uint32_t off = r * PF_CHUNK;
+          const uint32_t len = (p.pf_bytes - off) < PF_CHUNK ? (p.pf_bytes - off) & ~15u : PF_CHUNK;
+          if (len != 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + off), "r"(len) : "memory");
+        }
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (EPI == EPI_GENERIC) {
         const int64_t row = static_cast<int64_t>(m_blk) * TILE_M + cta_rank * GEMM_BM + row_in_tile;
@@ -420,6 +437,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
+void gemm_prefetch_next(const void* weights, size_t bytes) {
+  g_pf_ptr = weights;
+  g_pf_bytes = bytes;
+}
+
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
               const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
               cudaStream_t stream) {
@@ -512,6 +534,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.dbg = g_gemm_dbg;
   p.f16_start = f16_start;
   p.f16_period = f16_period;
+  p.pf_ptr = static_cast<const uint8_t*>(g_pf_ptr);
+  p.pf_bytes = (uint32_t)(g_pf_bytes > 0xfffffff0ull ? 0 : g_pf_bytes);
+  g_pf_ptr = nullptr;
+  g_pf_bytes = 0;
   RALD_REQUIRE(f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;

@@ -25,6 +25,10 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
 int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                       int M, int N, int K, int f16_start, int f16_period, cudaStream_t stream);
 
+// Hint for the NEXT gemm launch issued by this thread: while it runs, its idle epilogue threads prefetch `bytes` of
+// `weights` (the operand of the GEMM after it) into L2. Used by the small-batch denoiser loop.
+void gemm_prefetch_next(const void* weights, size_t bytes);
+
 // attn.cu ------------------------------------------------------------------------------------------
 // O[f, :, h*64:(h+1)*64] = softmax(Q K^T * scale) V per (frame f, head h); head_dim 64; Skv <= 512.
 // Q rows = frames*Sq, K/V rows = frames*Skv; head h lives at columns [h*64, h*64+64) of each operand.
