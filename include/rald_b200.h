@@ -362,6 +362,42 @@ int rald_occupancy_compact(const float* logits, const float* queries, int B, int
                            int32_t* counts, int32_t* block_ws, void* stream);
 int64_t rald_occupancy_ws_elems(int B, int64_t Q);
 
+/* ---- the eval loop either side of sampler + decoder ---- */
+
+/* Second-pass ("refine_query") query set of one frame, engine_generation.py:291-297:
+ *   aug_query_helper(pred, aug_num, pc_range, voxel_size, aug_scale)  datasets/utils/query_helper.py:3-43
+ *   norm_points(., pc_range, ...)                                      utils/utils.py:78-104
+ * points f32 [cap, 3] = the first pass's occupied points (inverse-normalised, as written by
+ * rald_occupancy_compact), *count (device int32) of them valid. Rows [0, N) of out f32 [aug_num, 3] are the points
+ * themselves, rows N + g are float32(clip(points[sel[g]] + (u[g]*2-1) * (voxel_size * scales[g]), range)) (fp64
+ * arithmetic as numpy's), all normalised back with (p - offset) / scale in fp32 (norm_scale_offset_host =
+ * {sx, sy, sz, ox, oy, oz}). The three draw arrays (sel i32 [aug_num], scales i32 [aug_num] in [1, aug_scale],
+ * uniforms f64 [aug_num, 3]; indexed by g) are either all given — numpy-parity mode: the host draws them with
+ * np.random in the reference's order — or all NULL: Philox4x32-10 on the device, keyed (seed, g). */
+int rald_refine_queries(const float* points, const int32_t* count, int64_t cap, int64_t aug_num, const int32_t* sel,
+                        const int32_t* scales, const double* uniforms, uint64_t seed, int aug_scale,
+                        const double* voxel_size_host, const double* pc_range_host, const float* norm_scale_offset_host,
+                        float* out, void* stream);
+
+/* cal_metrics / chamfer_distance (utils/utils.py:116-142) for B frames at once: pred f32 [B, pred_cap, 3] with
+ * pred_counts[b] valid rows, gt f32 [B, gt_cap, 3] with gt_counts[b] valid rows (gt_counts NULL: gt_fixed rows in
+ * every frame). out f64 [B, 3] = {0.5*mean_gt(NN dist to pred) + 0.5*mean_pred(NN dist to gt), mean pred->gt,
+ * mean gt->pred}; +inf where a side is empty. Brute-force fp32 nearest-neighbour search, the winning distance is
+ * recomputed in fp64 (the reference's cKDTree works in fp64). ws: f64 scratch of rald_chamfer_ws_elems(). */
+int rald_chamfer(const float* pred, const int32_t* pred_counts, int64_t pred_cap, const float* gt,
+                 const int32_t* gt_counts, int64_t gt_cap, int gt_fixed, int B, double* out, double* ws, void* stream);
+int64_t rald_chamfer_ws_elems(int B, int64_t pred_cap, int64_t gt_cap);
+
+/* Coloradar_dataset.process_radar_data (datasets/aligned_coloradar/Coloradar_dataset.py:432-475): raw f32
+ * [B, R, A, E, C] (C >= 2: intensity dB, doppler, ..., valid mask last) -> out f32 [B, R, A_up, E_up, channels_out]:
+ * channel 0 = clip(I, 0, max_intensity) / max_intensity (zeros if !norm_intensity), channel 1 = doppler * mask
+ * (/ max_dopp if norm_dopp), then bilinear upsampling of the (A, E) plane with align_corners=True (A_up = A and
+ * E_up = E: none). channels_out = 1 writes channel 0 only — the tensor the radar encoder consumes
+ * (model/models_radar_generation.py:378). */
+int rald_radar_cube_prep(const float* raw, int B, int R, int A, int E, int C, int A_up, int E_up, int channels_out,
+                         int norm_intensity, float max_intensity, int norm_dopp, float max_dopp, float* out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,6 +394,93 @@ def occupancy_points(logits: np.ndarray, queries: np.ndarray, pc_range=None, nor
     return pts
 
 
+def norm_constants(pc_range, norm_anisotropy: bool = True, norm_isotropy: bool = False):
+    """(scale[3], offset[3]) python floats shared by norm_points / inverse_norm_points (utils/utils.py:60-65, 88-93)."""
+    r = [float(v) for v in pc_range]
+    off = [(r[3] + r[0]) / 2, (r[4] + r[1]) / 2, (r[5] + r[2]) / 2]
+    sc = [(r[3] - r[0]) / 2, (r[4] - r[1]) / 2, (r[5] - r[2]) / 2]
+    if norm_isotropy:
+        sc = [max(sc)] * 3
+    return sc, off
+
+
+def norm_points(points: np.ndarray, pc_range, norm_anisotropy: bool = True, norm_isotropy: bool = False) -> np.ndarray:
+    """utils/utils.py:78-104: (p - offset) / scale per axis in the array's own dtype (float32 here)."""
+    sc, off = norm_constants(pc_range, norm_anisotropy, norm_isotropy)
+    out = np.zeros_like(points)
+    for a in range(3):
+        out[:, a] = (points[:, a] - off[a]) / sc[a]
+    return out
+
+
+def aug_query_helper(helper_points: np.ndarray, aug_num: int, pc_range, voxel_size, aug_bias_scale: int,
+                     sel: Optional[np.ndarray], scales: Optional[np.ndarray], u: Optional[np.ndarray]) -> np.ndarray:
+    """datasets/utils/query_helper.py:3-43 with the three np.random draws injected (sel = choice(N, G),
+    scales = choice(arange(aug_bias_scale) + 1, G), u = rand(G, 3)): float32 helper points + float64 bias, clipped to
+    the range in float64, stored as float32."""
+    N = helper_points.shape[0]
+    out = np.zeros((aug_num, 3), np.float32)
+    if N >= aug_num:
+        out[:] = helper_points[:aug_num]
+        return out
+    vs = np.asarray(voxel_size, dtype=np.float64)
+    bias = (u * 2 - 1) * (vs * scales[:, None])
+    aug = helper_points[sel] + bias
+    aug = np.clip(aug, np.asarray(pc_range[:3], dtype=np.float64), np.asarray(pc_range[3:], dtype=np.float64))
+    out[:N] = helper_points
+    out[N:] = aug
+    return out
+
+
+def process_radar_data(raw: np.ndarray, norm_intensity: bool, max_intensity: float, norm_dopp: bool, max_dopp: float,
+                       upsample: bool, tgt_a: int, tgt_e: int) -> np.ndarray:
+    """Coloradar_dataset.process_radar_data (datasets/aligned_coloradar/Coloradar_dataset.py:432-475) for one raw
+    cube [R, A, E, C] float32 -> [R, A_up, E_up, 2] float32; the bilinear upsample is written out element by element
+    the way ATen's CPU kernel evaluates it in the torch build of this image (align_corners=True; fp32 source index
+    scale * dst; weights w_ij = w_a[i] * w_e[j] rounded to fp32; out = fma(x00, w00, fma(x01, w01, fma(x11, w11,
+    x10 * w10))) — found by enumeration against F.interpolate, bit-exact on the fixture)."""
+    raw = raw.astype(np.float32)
+    R, A, E, _ = raw.shape
+    out = np.zeros((R, A, E, 2), np.float32)
+    if norm_intensity:
+        out[..., 0] = np.clip(raw[..., 0], 0, max_intensity) / np.float32(max_intensity)
+    out[..., 1] = raw[..., 1] * raw[..., -1]
+    if norm_dopp:
+        out[..., 1] = out[..., 1] / np.float32(max_dopp)
+    if not upsample:
+        return out
+
+    def axis(n_in, n_out):
+        f32 = np.float32
+        if n_out == n_in:
+            i0 = np.arange(n_out)
+            return i0, i0, np.ones(n_out, f32), np.zeros(n_out, f32)
+        scale = f32(n_in - 1) / f32(n_out - 1) if n_out > 1 else f32(0)
+        src = (scale * np.arange(n_out, dtype=f32)).astype(f32)
+        i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1)
+        lam = np.clip((src - i0.astype(f32)).astype(f32), f32(0), f32(1))
+        i1 = i0 + (i0 < n_in - 1)
+        return i0, i1, (f32(1) - lam).astype(f32), lam
+
+    a0, a1, wa0, wa1 = axis(A, tgt_a)
+    e0, e1, we0, we1 = axis(E, tgt_e)
+    def fma(a, b, c):   # fp32 fused multiply-add through fp64 (the product is exact in fp64)
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    res = np.zeros((R, tgt_a, tgt_e, 2), np.float32)
+    w00 = wa0[:, None] * we0[None, :]
+    w01 = wa0[:, None] * we1[None, :]
+    w10 = wa1[:, None] * we0[None, :]
+    w11 = wa1[:, None] * we1[None, :]
+    for ch in range(2):
+        x = out[..., ch]
+        x00, x01 = x[:, a0][:, :, e0], x[:, a0][:, :, e1]
+        x10, x11 = x[:, a1][:, :, e0], x[:, a1][:, :, e1]
+        bc = np.broadcast_to
+        res[..., ch] = fma(x00, bc(w00, x00.shape), fma(x01, bc(w01, x00.shape), fma(x11, bc(w11, x00.shape), x10 * w10)))
+    return res
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()

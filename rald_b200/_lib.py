@@ -67,9 +67,15 @@ _SIGNATURES = {
     "rald_occupancy_compact": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_int, c_i64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p],
     "rald_occupancy_ws_elems": [c_int, c_i64],
+    "rald_refine_queries": [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_int,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rald_chamfer": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "rald_chamfer_ws_elems": [c_int, c_i64, c_i64],
+    "rald_radar_cube_prep": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
+                             c_f32, c_void_p, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
-             "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64}
+             "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64, "rald_chamfer_ws_elems": c_i64}
 
 
 class RaldError(RuntimeError):

@@ -95,8 +95,11 @@ int enc_conv_in(const float* x, const float* w, const float* bias, float* out, i
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x, int64_t V, int C, int groups, int64_t vox_per_block,
                 double* __restrict__ stats) {
-  __shared__ float s_sum[256];
-  __shared__ float s_sq[256];
+  // per-thread partials [voxel lane][channel], reduced in a FIXED order (no floating-point atomics inside the block:
+  // the block's contribution is bit-reproducible; only the fp64 atomics across blocks remain order-dependent, at
+  // 1e-16 relative)
+  __shared__ float s_sum[256 * 4];
+  __shared__ float s_sq[256 * 4];
   const int quads = C >> 2;             // float4 columns per voxel (16 / 32 / 64)
   const int vlanes = blockDim.x / quads;
   const int cq = threadIdx.x % quads;
@@ -104,8 +107,6 @@ gn_stats_kernel(const float* __restrict__ x, int64_t V, int C, int groups, int64
   const int b = blockIdx.y;
   const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
   const int64_t v1 = (v0 + vox_per_block) < V ? (v0 + vox_per_block) : V;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-  __syncthreads();
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
   if (vl < vlanes) {
     const float4* xb = reinterpret_cast<const float4*>(x + (int64_t)b * V * C);
@@ -114,18 +115,18 @@ gn_stats_kernel(const float* __restrict__ x, int64_t V, int C, int groups, int64
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
     }
-    atomicAdd(&s_sum[4 * cq + 0], s.x); atomicAdd(&s_sum[4 * cq + 1], s.y);
-    atomicAdd(&s_sum[4 * cq + 2], s.z); atomicAdd(&s_sum[4 * cq + 3], s.w);
-    atomicAdd(&s_sq[4 * cq + 0], q.x); atomicAdd(&s_sq[4 * cq + 1], q.y);
-    atomicAdd(&s_sq[4 * cq + 2], q.z); atomicAdd(&s_sq[4 * cq + 3], q.w);
+    reinterpret_cast<float4*>(s_sum)[vl * quads + cq] = s;   // s_sum[vl][4*cq .. 4*cq+3]
+    reinterpret_cast<float4*>(s_sq)[vl * quads + cq] = q;
   }
   __syncthreads();
   if (threadIdx.x < groups) {
     const int cpg = C / groups;
     double gs = 0.0, gq = 0.0;
-    for (int j = 0; j < cpg; ++j) {
-      gs += (double)s_sum[threadIdx.x * cpg + j];
-      gq += (double)s_sq[threadIdx.x * cpg + j];
+    for (int l = 0; l < vlanes; ++l) {
+      for (int j = 0; j < cpg; ++j) {
+        gs += (double)s_sum[l * C + threadIdx.x * cpg + j];
+        gq += (double)s_sq[l * C + threadIdx.x * cpg + j];
+      }
     }
     atomicAdd(&stats[((int64_t)b * groups + threadIdx.x) * 2 + 0], gs);
     atomicAdd(&stats[((int64_t)b * groups + threadIdx.x) * 2 + 1], gq);
