@@ -343,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         lat["ms_per_net_eval"] = e0.elapsed_time(e1) / 5 / NET_EVALS
 
     # ---- roofline leg: one more step with CUDA events around every launch of the hot kernel families ----
-    fams = ["gemm", "attn", "ln", "boundary", "conv3d", "gn", "ae_query", "other"]
+    fams = ["gemm", "attn", "xattn", "ln", "boundary", "conv3d", "gn", "ae_query", "other"]
     os.environ["RALD_B200_GRAPH"] = "0"      # per-launch events cannot be recorded inside a graph replay
     step_resident()
     _lib.prof_enable(*fams)
@@ -378,8 +378,12 @@ def run_ours(args, rank, world, local_rank):
                 "launches_timed": g["launches"], "ms_per_launch": g["ms"] / max(1, g["launches"]),
                 "flop_per_launch": g["work"] / max(1, g["launches"])}
     prof_total = sum(v["ms"] for v in breakdown.values())
-    for v in breakdown.values():
+    for k, v in breakdown.items():
         v["share"] = round(v["ms"] / prof_total, 4) if prof_total else None
+        if k in ("gemm", "attn", "xattn", "conv3d", "ae_query") and v["ms"] > 0:   # work = executed flops
+            v["tflops"] = round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)
+        elif k in ("ln", "gn") and v["ms"] > 0:                                   # work = algorithmic bytes
+            v["gb_per_s"] = round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1)
         del v["work"]
 
     frames_total = F * world * args.steps

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RALD_ABI_VERSION 1
+#define RALD_ABI_VERSION 2
 
 int rald_abi_version(void);
 const char* rald_last_error(void);
@@ -155,6 +155,12 @@ typedef struct rald_dit_workspace {
   void* ff;      /* [T][4*dim] bf16 */
   float* x_tmp;  /* [T][channels] */
   float* d_tmp;  /* [T][channels] */
+  /* optional (NULL = unfused attn2 path): context operands of the fused cross-attention, built by rald_xattn_fold
+   * for xattn_frames frames; frame f of a call to rald_dit_forward / rald_dit_sample uses entry f of them */
+  const void* xattn_kp;   /* bf16 [depth][8][xattn_frames][64][dim] */
+  const void* xattn_vt;   /* fp16 [depth][8][dim][xattn_frames*64] */
+  int32_t xattn_frames;
+  int32_t _pad2;
 } rald_dit_workspace;
 
 /* One EDMPrecond.forward (model/models_radar_generation.py:412-430) for `frames` frames given precomputed
@@ -172,6 +178,23 @@ int rald_dit_forward(const rald_dit_weights* w, const rald_dit_workspace* ws, co
 int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspace* ws, const float* latents,
                     const float* sigmas, int num_steps, const float* mod, const void* ctxkv, float* x_out,
                     float* trace, int frames, void* stream);
+
+/* Fused attn2 sub-layer (model/models_radar_generation.py:35-76 called at :167) for 8 heads x 64 and a 64-token
+ * context that is constant over the sampler's network evaluations. rald_xattn_fold (once per sample) folds
+ * attn2.to_q into the keys and attn2.to_out into the values of every block:
+ *   ctxkv_bf16 [frames*64][depth*2*dim] (per block K | V, BOTH bf16), wq_t_scaled bf16 [depth][dim in][dim q] =
+ *   attn2.to_q.weight transposed times log2(e)/sqrt(64), w_o bf16 [depth][dim][dim] = attn2.to_out.0.weight
+ *   -> kp bf16 [depth][8][frames][64][dim], vt fp16 [depth][8][dim][frames*64].
+ * rald_xattn_fused then computes, for ONE block's kp / vt slices, h[T][dim] += softmax_per_head(xn kp^T) vt^T + bias
+ * in a single kernel (xn bf16 [T][dim] = adaLN2(h); T = frames * rows_per_frame; frame f of the call reads entry
+ * frame0 + f of operands built for total_frames frames). */
+int rald_xattn_fold(const void* ctxkv_bf16, const void* wq_t_scaled, const void* w_o, int depth, int frames, void* kp,
+                    void* vt, void* stream);
+int rald_xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
+                     int rows_per_frame, int frame0, int total_frames, void* stream);
+/* Debug hook like rald_gemm_debug_buffer: CTA 0 of the fused kernel stores %globaltimer stamps of its first 4 tiles at
+ * dev_buf[tile*16 + i] (phase list in csrc/xattn.cu). */
+int rald_xattn_debug_buffer(unsigned long long* dev_buf);
 
 /* ---- VecSet autoencoder (model/models_ae.py) ---- */
 typedef struct rald_ae_weights {

@@ -32,6 +32,7 @@ _SIGNATURES = {
                                c_int, c_void_p],
     "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_debug_buffer": [c_void_p],
+    "rald_xattn_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                       c_f32, c_void_p],
     "rald_ln_rows": [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_int,
@@ -46,6 +47,8 @@ _SIGNATURES = {
                          c_void_p],
     "rald_dit_sample": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                         c_void_p],
+    "rald_xattn_fold": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "rald_xattn_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rald_ae_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "rald_linear_smallk": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p],
     "rald_ln_dot_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],

@@ -20,7 +20,7 @@
 namespace rald {
 
 static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, const float* mod,
-                      int64_t mod_frame_stride, const void* ctxkv, int frames, cudaStream_t st) {
+                      int64_t mod_frame_stride, const void* ctxkv, int frames, int frame0, cudaStream_t st) {
   const int dim = w.dim, depth = w.depth, M = w.n_latents, L = w.ctx_len, heads = w.heads;
   const int64_t T = (int64_t)frames * M;
   const float scale = 1.0f / sqrtf((float)(dim / heads));
@@ -35,6 +35,10 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
   static const bool pf_env = [] { const char* e = getenv("RALD_B200_WPREFETCH"); return e != nullptr && e[0] == '1'; }();
   const bool pf = pf_env && T <= 2048;
   const size_t wsz = (size_t)dim * dim * 2;  // one dim x dim bf16 matrix
+  // attn2 as ONE kernel against the folded context operands (xattn.cu) when the caller supplied them
+  const bool fused_x = ws.xattn_kp != nullptr && ws.xattn_vt != nullptr && L == 64 && heads == 8 && dim == 512 &&
+                       xattn_fusion_enabled();
+  const int64_t x_blk = (int64_t)8 * ws.xattn_frames * 64 * dim;  // elements of one block's kp (= vt) slice
   for (int n = 0; n < depth; ++n) {
     const float* m0 = mod + ((int64_t)n * 3 + 0) * 2 * dim;
     const float* m1 = mod + ((int64_t)n * 3 + 1) * 2 * dim;
@@ -57,13 +61,19 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
                        0, st));
     // x += attn2(adaLN2(x), context)
     RALD_TRY(ln_rows(ws.h, dim, m1, m1 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
-    if (pf) gemm_prefetch_next(w_o2, wsz);
-    RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
-    RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx, ws.att,
-                      dim, frames, heads, M, L, scale, st));
-    if (pf) gemm_prefetch_next(w_ff1, 8 * wsz);
-    RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
-                       0, st));
+    if (fused_x) {
+      RALD_TRY(xattn_fused(ws.xn, reinterpret_cast<const __nv_bfloat16*>(ws.xattn_kp) + (int64_t)n * x_blk,
+                           reinterpret_cast<const __nv_bfloat16*>(ws.xattn_vt) + (int64_t)n * x_blk,
+                           w.b_o2 + (int64_t)n * dim, ws.h, frames, M, frame0, ws.xattn_frames, st));
+    } else {
+      if (pf) gemm_prefetch_next(w_o2, wsz);
+      RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
+      RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx, ws.att,
+                        dim, frames, heads, M, L, scale, st));
+      if (pf) gemm_prefetch_next(w_ff1, 8 * wsz);
+      RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
+                         0, st));
+    }
     // x += ff(adaLN3(x))
     RALD_TRY(ln_rows(ws.h, dim, m2, m2 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
     if (pf) gemm_prefetch_next(w_ff2, 4 * wsz);
@@ -119,6 +129,8 @@ static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws,
   RALD_REQUIRE(w->ctx_len % 32 == 0 && w->ctx_len <= 512 && (w->ctx_len <= 256 || w->ctx_len % 256 == 0),
                "dit: context length %d unsupported (multiple of 32, <= 512)", w->ctx_len);
   RALD_REQUIRE(frames > 0 && ws->max_frames > 0, "dit: frames=%d micro-batch=%d", frames, ws->max_frames);
+  RALD_REQUIRE(ws->xattn_kp == nullptr || ws->xattn_frames >= frames,
+               "dit: fused cross-attention operands cover %d frames, %d requested", ws->xattn_frames, frames);
   return 0;
 }
 
@@ -144,7 +156,7 @@ extern "C" int rald_dit_forward(const rald_dit_weights* w, const rald_dit_worksp
                           ws->h, sg, sigma_stride, nullptr, 0, 4, M, C, T, dim, w->sigma_data, st));
     RALD_TRY(run_blocks(*w, *ws, md, mod_frame_stride,
                         reinterpret_cast<const __nv_bfloat16*>(ctxkv) + (int64_t)f0 * ctx_rows * w->depth * 2 * dim, nf,
-                        st));
+                        f0, st));
     RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, xin, nullptr, nullptr,
                           out + (int64_t)f0 * M * C, nullptr, sg, sigma_stride, nullptr, 0, 0, M, C, T, dim,
                           w->sigma_data, st));
@@ -177,13 +189,13 @@ extern "C" int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspa
       const float* t_next = sigmas + i + 1;
       const bool last = (i == num_steps - 1);
       // Euler evaluation at t_cur
-      RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)i * mod_step, 0, ctx, nf, st));
+      RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)i * mod_step, 0, ctx, nf, f0, st));
       RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, x_hat, nullptr, d_cur,
                             last ? x_hat : x_e, last ? nullptr : ws->h, t_cur, 0, t_next, 0, 1, M, C, T, dim,
                             w->sigma_data, st));
       if (!last) {
         // Heun correction at t_next
-        RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)(i + 1) * mod_step, 0, ctx, nf, st));
+        RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)(i + 1) * mod_step, 0, ctx, nf, f0, st));
         RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, x_e, x_hat, d_cur, x_hat, ws->h,
                               t_next, 0, t_cur, 0, 2, M, C, T, dim, w->sigma_data, st));
       }

@@ -35,6 +35,13 @@ void gemm_prefetch_next(const void* weights, size_t bytes);
 int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
              int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, cudaStream_t stream);
 
+// xattn.cu -----------------------------------------------------------------------------------------
+int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
+                int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
+int xattn_fold(const void* ctxkv, const void* wq_t, const void* w_o, int depth, int frames, void* kp, void* vt,
+               cudaStream_t stream);
+bool xattn_fusion_enabled();  // RALD_B200_FUSE_XATTN != 0 (default on)
+
 // norm.cu ------------------------------------------------------------------------------------------
 int ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,
             int rows_per_frame, int gamma_plus_one, void* out, int64_t ldo, int out_f32, int64_t rows, int D,

@@ -30,7 +30,9 @@ class DitWeights(ctypes.Structure):
 class DitWorkspace(ctypes.Structure):
     _fields_ = [("max_frames", ctypes.c_int32), ("_pad", ctypes.c_int32),
                 ("h", c_void_p), ("xn", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("ff", c_void_p),
-                ("x_tmp", c_void_p), ("d_tmp", c_void_p)]
+                ("x_tmp", c_void_p), ("d_tmp", c_void_p),
+                ("xattn_kp", c_void_p), ("xattn_vt", c_void_p), ("xattn_frames", ctypes.c_int32),
+                ("_pad2", ctypes.c_int32)]
 
 
 def geglu_pack_index(inner: int, device) -> torch.Tensor:
@@ -45,6 +47,12 @@ def geglu_pack_index(inner: int, device) -> torch.Tensor:
 
 def default_microbatch() -> int:
     return int(os.environ.get("RALD_B200_MICROBATCH", "64"))
+
+
+def xattn_fusion_enabled() -> bool:
+    """attn2 as one fused kernel against per-sample folded context operands (csrc/xattn.cu); RALD_B200_FUSE_XATTN=0
+    restores the to_q GEMM -> attention -> to_out GEMM sequence."""
+    return os.environ.get("RALD_B200_FUSE_XATTN", "1") != "0"
 
 
 def graphs_enabled() -> bool:
@@ -105,6 +113,9 @@ class DitRuntime:
             self.w_kv2 = torch.cat([torch.cat([b.attn2.to_k.weight, b.attn2.to_v.weight]).detach() for b in blocks]
                                    ).to(bf).contiguous()
             self.w_o2 = stack(lambda b: b.attn2.to_out[0].weight, bf)
+            # fused attn2: to_q transposed ([in][q feature]) with the softmax scale and log2(e) folded in
+            c = (dim // heads) ** -0.5 * 1.4426950408889634
+            self.w_q2t = stack(lambda b: (b.attn2.to_q.weight.float() * c).t(), bf)
             self.b_o2 = stack(lambda b: b.attn2.to_out[0].bias, torch.float32)
             self.w_ff1 = stack(lambda b: b.ff.net[0].proj.weight[idx], bf)
             self.b_ff1 = stack(lambda b: b.ff.net[0].proj.bias[idx], torch.float32)
@@ -191,6 +202,39 @@ class DitRuntime:
                   out.data_ptr(), n, 0, rows, n, self.dim, self.dim, 2 * self.dim, _lib.cur_stream())
         return out
 
+    def _fusable(self, L: int, frames: int) -> bool:
+        """The fused attn2 kernel works on 128-row tiles, one per SM: it needs enough rows to fill the machine (4 tiles
+        per frame; below ~24 frames the three-kernel sequence with its narrower tiles keeps more SMs busy)."""
+        min_frames = int(os.environ.get("RALD_B200_FUSE_XATTN_MIN_FRAMES", "24"))
+        return (xattn_fusion_enabled() and L == 64 and self.heads == 8 and self.dim == 512
+                and min(frames, default_microbatch()) >= min_frames)
+
+    def context_fold(self, tokens_bf16: torch.Tensor, ws: DitWorkspace):
+        """Per-sample operands of the fused attn2 kernel (rald_xattn_fold): K / V projections of the tokens for all
+        blocks (one GEMM, both bf16) folded with attn2.to_q / attn2.to_out. Registers them in the workspace struct and
+        returns the tensors (the caller keeps them alive while launches that read them may be pending)."""
+        rows = tokens_bf16.shape[0]
+        F = rows // 64
+        n = self.depth * 2 * self.dim
+        kv = torch.empty(rows, n, device=self.device, dtype=torch.bfloat16)
+        _lib.call("rald_gemm_bf16", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim, kv.data_ptr(), n,
+                  0, 0, 0, rows, n, self.dim, 0, 0, _lib.cur_stream())
+        kp = torch.empty(self.depth, 8, F, 64, self.dim, device=self.device, dtype=torch.bfloat16)
+        vt = torch.empty(self.depth, 8, self.dim, F * 64, device=self.device, dtype=torch.float16)
+        _lib.call("rald_xattn_fold", kv.data_ptr(), self.w_q2t.data_ptr(), self.w_o2.data_ptr(), self.depth, F,
+                  kp.data_ptr(), vt.data_ptr(), _lib.cur_stream())
+        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames = kp.data_ptr(), vt.data_ptr(), F
+        return kv, kp, vt
+
+    def _conditioning(self, tokens_bf16: torch.Tensor, ws: DitWorkspace, L: int):
+        """(ctxkv pointer or 0, tensors to keep alive) for one call; also (un)registers the fused operands in ws."""
+        if self._fusable(L, tokens_bf16.shape[0] // max(L, 1)):
+            keep = self.context_fold(tokens_bf16, ws)
+            return 0, keep
+        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames = None, None, 0
+        ctxkv = self.context_kv(tokens_bf16)
+        return ctxkv.data_ptr(), (ctxkv,)
+
     # ------------------------------------------------------------------ entry points
     def forward(self, x: torch.Tensor, sigma: torch.Tensor, tokens_bf16: torch.Tensor) -> torch.Tensor:
         self.ensure_packed()
@@ -202,20 +246,22 @@ class DitRuntime:
             raise ValueError(f"sigma must have 1 or {B} elements, got {sigma.numel()}")
         per_frame = sigma.numel() == B and B > 1
         mod = self.mod_table(sigma)
-        ctxkv = self.context_kv(tokens_bf16)
         out = torch.empty_like(x)
         w, ws = self._weights_struct(L), self._workspace(B)
+        ctx_ptr, keep = self._conditioning(tokens_bf16, ws, L)
         _lib.call("rald_dit_forward", ctypes.addressof(w), ctypes.addressof(ws), x.data_ptr(), sigma.data_ptr(),
                   1 if per_frame else 0, mod.data_ptr(), self.depth * 3 * 2 * self.dim if per_frame else 0,
-                  ctxkv.data_ptr(), out.data_ptr(), B, _lib.cur_stream())
+                  ctx_ptr, out.data_ptr(), B, _lib.cur_stream())
+        for t in keep:   # stream-ordered allocator: do not recycle before the launches above have run
+            t.record_stream(torch.cuda.current_stream())
         return out
 
     def _sample_eager(self, latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L):
-        ctxkv = self.context_kv(tokens_bf16)
         w, ws = self._weights_struct(L), self._workspace(B)
+        ctx_ptr, keep = self._conditioning(tokens_bf16, ws, L)
         _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
-                  num_steps, mod.data_ptr(), ctxkv.data_ptr(), out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
-        return ctxkv
+                  num_steps, mod.data_ptr(), ctx_ptr, out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
+        return keep
 
     def sample(self, latents: torch.Tensor, tokens_bf16: torch.Tensor, sigmas: torch.Tensor,
                trace: Optional[torch.Tensor] = None) -> torch.Tensor:
