@@ -148,10 +148,11 @@ def calibrate_occupancy(net, vae, cube, queries, seeds):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's PyTorch modules on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(queries_total: int, sample_queries: int = 16384):
-    """Times ONE network evaluation as the reference executes it (radar encoder + tokens inside every evaluation,
-    models_radar_generation.py:412-430), the decoder latent stack and `sample_queries` decoder queries for one frame,
-    then extrapolates linearly to 35 evaluations + stack + all queries. Returns a dict with frames/s."""
+def cpu_reference_sample(queries_total: int, sample_queries: int = 262144, sample_evals: int = 16):
+    """Times `sample_evals` of the 35 network evaluations as the reference executes them (radar encoder + tokens inside
+    every evaluation, models_radar_generation.py:412-430; the first evaluations of the real Heun schedule), the decoder
+    latent stack and `sample_queries` decoder queries for one frame — about 10 s of CPU work on 16 cores — then
+    extrapolates linearly to 35 evaluations + stack + all queries. Returns a dict with frames/s."""
     from oracle import rald_oracle as orc
     from rald_b200 import synth
     threads = os.cpu_count() or 1
@@ -162,15 +163,19 @@ def cpu_reference_sample(queries_total: int, sample_queries: int = 16384):
     cube = synth.radar_cube(1, seed=SEED)
     lat = synth.unit_latents([0])
     q = synth.query_points(1, sample_queries)
-    sigma = torch.tensor(80.0)
+    sigmas = orc.karras_sigmas()
+    sample_evals = max(1, min(int(sample_evals), NET_EVALS))
 
-    def one_eval():
+    def one_eval(sigma):
         tok = orc.process_radar_cond(sd, cube)
         return orc.edm_precond(sd, lat * sigma, sigma, tok)
 
     with torch.no_grad():
-        one_eval()  # warm-up (oneDNN primitive creation)
-        t0 = time.perf_counter(); d = one_eval(); t_eval = time.perf_counter() - t0
+        one_eval(sigmas[0])  # warm-up (oneDNN primitive creation)
+        t0 = time.perf_counter()
+        for i in range(sample_evals):          # evaluation i of the Heun loop runs at sigma index (i + 1) // 2
+            d = one_eval(sigmas[(i + 1) // 2])
+        t_eval = (time.perf_counter() - t0) / sample_evals
         t0 = time.perf_counter(); tok = orc.process_radar_cond(sd, cube); t_enc = time.perf_counter() - t0
         z = d[:, :, :32]
         orc.ae_latent_stack(sd_ae, z)
@@ -180,8 +185,8 @@ def cpu_reference_sample(queries_total: int, sample_queries: int = 16384):
     t_frame = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
     t_frame_hoisted = NET_EVALS * (t_eval - t_enc) + t_enc + t_stack + t_q * (queries_total / sample_queries)
     return {"value": 1.0 / t_frame, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"1 of {NET_EVALS} network evaluations as the reference runs them (radar encoder inside, "
-                       f"{t_eval:.2f} s) + decoder latent stack ({t_stack:.2f} s) + {sample_queries} of "
+            "sample": (f"{sample_evals} of {NET_EVALS} network evaluations as the reference runs them (radar encoder "
+                       f"inside, {t_eval:.2f} s each) + decoder latent stack ({t_stack:.2f} s) + {sample_queries} of "
                        f"{queries_total} decoder queries ({t_q:.2f} s) for 1 frame, extrapolated linearly; oracle port "
                        f"of the reference's fp32 PyTorch CPU path"),
             "s_per_frame": t_frame, "hoisted_value": 1.0 / t_frame_hoisted, "s_per_net_eval": t_eval}

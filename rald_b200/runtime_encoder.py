@@ -49,7 +49,7 @@ class EncWorkspace(ctypes.Structure):
 
 
 def encoder_microbatch() -> int:
-    return int(os.environ.get("RALD_B200_ENC_MICROBATCH", "4"))
+    return int(os.environ.get("RALD_B200_ENC_MICROBATCH", "32"))
 
 
 def _n_tile(cout: int) -> int:
