@@ -192,6 +192,8 @@ int rald_xattn_fold(const void* ctxkv_bf16, const void* wq_t_scaled, const void*
                     void* vt, void* stream);
 int rald_xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
                      int rows_per_frame, int frame0, int total_frames, void* stream);
+/* Debug hook like rald_gemm_debug_buffer for rald_ae_query (phase list in csrc/ae_query.cu). */
+int rald_ae_query_debug_buffer(unsigned long long* dev_buf);
 /* Debug hook like rald_gemm_debug_buffer: CTA 0 of the fused kernel stores %globaltimer stamps of its first 4 tiles at
  * dev_buf[tile*16 + i] (phase list in csrc/xattn.cu). */
 int rald_xattn_debug_buffer(unsigned long long* dev_buf);

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_debug_buffer": [c_void_p],
     "rald_xattn_debug_buffer": [c_void_p],
+    "rald_ae_query_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                       c_f32, c_void_p],
     "rald_ln_rows": [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_int,
