@@ -115,7 +115,7 @@ struct BoundaryParams {
   float sigma_data;
 };
 
-constexpr int BND_WARPS = 8;
+constexpr int BND_WARPS = 16;  // 16 rows in flight per SM: the kernel is bound by the latency of the row loads
 
 __global__ void __launch_bounds__(BND_WARPS * 32)
 boundary_kernel(const BoundaryParams p) {
