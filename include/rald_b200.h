@@ -86,6 +86,15 @@ int rald_attn_debug_buffer(unsigned long long* dev_buf);
 int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                   int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* stream);
 
+/* rald_attn_d64 for contexts longer than TMEM holds: Skv = chunks * 512 keys per frame (1024 .. 4096), processed as
+ * key chunks with per-chunk softmax statistics and merged exactly (O = sum_c w_c O_c / sum_c w_c, w_c = l_c 2^(m_c - m)).
+ * Serves `use_radar_enc: false` (2048 raw radar-cube tokens as the cross-attention context,
+ * model/models_radar_generation.py:357-361, 378-405). Scratch: o_chunks bf16 [chunks][frames*Sq][heads*64],
+ * stats f32 [chunks][frames*Sq][heads][2]. */
+int rald_attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                       int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* o_chunks, float* stats,
+                       void* stream);
+
 /* out = LN(x) * g + b over rows of 512 fp32 values (eps inside the rsqrt). gamma_plus_one=1 gives the adaLN
  * modulation LN(x)*(1+scale)+shift of AdaLayerNorm.forward (model/models_radar_generation.py:127-131) with
  * gamma/beta = scale/shift of frame f at gamma + f*mod_frame_stride (stride 0 = shared); gamma_plus_one=0 is

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "rald_ae_query_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                       c_f32, c_void_p],
+    "rald_attn_d64_long": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
+                           c_f32, c_void_p, c_void_p, c_void_p],
     "rald_ln_rows": [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_int,
                      c_f32, c_void_p],
     "rald_dit_mod_table": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -42,6 +42,9 @@ struct AttnParams {
   uint32_t o_col;      // O accumulator column inside a half region
   uint32_t region;     // TMEM columns per half region
   int nbuf;            // query tiles in flight in TMEM (1 or 2); a tile uses 2 * region columns
+  int kv_frame_rows;   // rows per frame in the K / V tensors (>= Skv; a key CHUNK of a longer context when larger)
+  float* stats;        // optional [frames*Sq][heads][2] = (shift m in log2 units, sum l): softmax statistics of the
+                       // keys seen by this call, for merging key chunks of a long context (attn_merge_chunks)
   unsigned long long* dbg;  // optional [tile < 16][group 2][8] %globaltimer stamps of CTA 0 (tools/attn_phases.py)
 };
 
@@ -124,7 +127,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int fh = item / p.items_per_head;
         const int frame = fh / p.heads, head = fh - frame * p.heads;
         const int qt0 = (item - fh * p.items_per_head) * p.tq;
-        const int kv_row0 = frame * Skv;
+        const int kv_row0 = frame * p.kv_frame_rows;
         // K is free as soon as the last S product of the previous item has retired, V only after its last P V:
         // the next item's K and first Q tile are fetched while the previous item is still in its softmax.
         mbar_wait(k_empty, kv_ph ^ 1);
@@ -324,8 +327,17 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float l_other = st[((g ^ 1) * 2 + 1) * ATT_BM + row_in_tile];
         const float m_all = fmaxf(m_scaled, m_other);
         const float w_mine = ex2_approx(m_scaled - m_all), w_other = ex2_approx(m_other - m_all);
-        const float inv = 1.0f / (w_mine * sum + w_other * l_other);
+        const float l_all = w_mine * sum + w_other * l_other;
+        const float inv = 1.0f / l_all;
         const float a_mine = w_mine * inv, a_other = w_other * inv;
+        if (p.stats != nullptr && g == 0) {
+          const int qrow_s = (qt0 + t) * ATT_BM + row_in_tile;
+          if (qrow_s < p.Sq) {
+            float* sp = p.stats + ((static_cast<int64_t>(frame) * p.Sq + qrow_s) * p.heads + head) * 2;
+            sp[0] = m_all;
+            sp[1] = l_all;
+          }
+        }
 
         // ---- O = a_0 O_0 + a_1 O_1 : this group normalises and stores output columns [32 g, 32 g + 32) ----
         const uint32_t t_o_mine = t_mine + p.o_col + 32 * g;
@@ -371,15 +383,24 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
              int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, cudaStream_t stream) {
+  return attn_d64_chunk(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, Skv, Skv, nullptr, scale, stream);
+}
+
+int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                   int64_t ldo, int frames, int heads, int Sq, int Skv, int kv_frame_rows, float* stats, float scale,
+                   cudaStream_t stream) {
   RALD_REQUIRE(frames > 0 && heads > 0 && Sq > 0, "attn: bad sizes");
+  RALD_REQUIRE(kv_frame_rows >= Skv, "attn: %d key rows per frame < Skv=%d", kv_frame_rows, Skv);
   RALD_REQUIRE(Skv >= 64 && Skv <= 512 && Skv % 64 == 0, "attn: Skv=%d must be a multiple of 64 in [64, 512]", Skv);
   RALD_REQUIRE(Sq % ATT_BM == 0, "attn: Sq=%d must be a multiple of 128", Sq);
   RALD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "attn: output not 16-byte aligned");
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t kv_box = Skv / 2;  // one box per key half (<= 256 rows)
   RALD_TRY(make_tmap_2d_bf16(&tmQ, Q, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldq, ATT_BM));
-  RALD_TRY(make_tmap_2d_bf16(&tmK, K, (uint64_t)frames * Skv, (uint64_t)heads * ATT_D, (uint64_t)ldk, kv_box));
-  RALD_TRY(make_tmap_2d_bf16(&tmV, V, (uint64_t)frames * Skv, (uint64_t)heads * ATT_D, (uint64_t)ldv, kv_box));
+  // (K / V may point at a key chunk inside each frame's rows: the last frame's chunk ends Skv rows after its start)
+  const uint64_t kv_rows = (uint64_t)(frames - 1) * kv_frame_rows + Skv;
+  RALD_TRY(make_tmap_2d_bf16(&tmK, K, kv_rows, (uint64_t)heads * ATT_D, (uint64_t)ldk, kv_box));
+  RALD_TRY(make_tmap_2d_bf16(&tmV, V, kv_rows, (uint64_t)heads * ATT_D, (uint64_t)ldv, kv_box));
   AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
@@ -388,6 +409,8 @@ int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void*
   p.frames = frames;
   p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.kv_frame_rows = kv_frame_rows;
+  p.stats = stats;
   p.half = Skv / 2;
   // half region: S occupies [0, half), P (bf16 pairs) [0, half/2), O (64 fp32 columns) right after P
   p.o_col = p.half / 2 < 32 ? 32u : (uint32_t)(p.half / 2);
@@ -426,7 +449,94 @@ int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void*
   return 0;
 }
 
+int attn_merge_chunks(const void* o_chunks, int64_t chunk_stride, int64_t ldc, const float* stats,
+                      int64_t stats_chunk_stride, int chunks, int heads, int64_t rows, void* out, int64_t ldo,
+                      cudaStream_t stream);
+
+int attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                  int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* o_chunks, float* stats,
+                  cudaStream_t stream) {
+  RALD_REQUIRE(Skv % 512 == 0 && Skv >= 1024 && Skv <= 4096, "attn_long: Skv=%d must be a multiple of 512 in [1024, 4096]",
+               Skv);
+  RALD_REQUIRE(o_chunks != nullptr && stats != nullptr, "attn_long: scratch buffers missing");
+  const int chunks = Skv / 512;
+  const int64_t rows = (int64_t)frames * Sq;
+  const int64_t wdt = (int64_t)heads * ATT_D;
+  const __nv_bfloat16* Kb = reinterpret_cast<const __nv_bfloat16*>(K);
+  const __nv_bfloat16* Vb = reinterpret_cast<const __nv_bfloat16*>(V);
+  __nv_bfloat16* oc = reinterpret_cast<__nv_bfloat16*>(o_chunks);
+  for (int c = 0; c < chunks; ++c)
+    RALD_TRY(attn_d64_chunk(Q, ldq, Kb + (int64_t)c * 512 * ldk, ldk, Vb + (int64_t)c * 512 * ldv, ldv, oc + c * rows * wdt,
+                            wdt, frames, heads, Sq, 512, Skv, stats + c * rows * heads * 2, scale, stream));
+  return attn_merge_chunks(oc, rows * wdt, wdt, stats, rows * heads * 2, chunks, heads, rows, O, ldo, stream);
+}
+
+// Long contexts (Skv > 512): the keys are processed in chunks of <= 512 by attn_d64_chunk, each chunk yielding its
+// own normalised output O_c (bf16) and statistics (m_c, l_c); the exact softmax over all keys is
+//   O = sum_c w_c O_c / sum_c w_c,   w_c = l_c 2^(m_c - max_c m_c).
+// One thread per (row, head, 8 columns).
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const __nv_bfloat16* __restrict__ o_chunks, int64_t chunk_stride, int64_t ldc,
+                  const float* __restrict__ stats, int64_t stats_chunk_stride, int chunks, int heads, int64_t rows,
+                  __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (row, head, octet)
+  const int64_t total = rows * heads * 8;
+  if (i >= total) return;
+  const int oct = (int)(i & 7);
+  const int head = (int)((i >> 3) % heads);
+  const int64_t row = i / (8 * heads);
+  float m[8], l[8];
+  float mx = -INFINITY;
+  for (int c = 0; c < chunks; ++c) {
+    const float* sp = stats + c * stats_chunk_stride + (row * heads + head) * 2;
+    m[c] = sp[0];
+    l[c] = sp[1];
+    mx = fmaxf(mx, m[c]);
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float w = l[c] * ex2_approx(m[c] - mx);
+    wsum += w;
+    const uint4 v = *reinterpret_cast<const uint4*>(o_chunks + c * chunk_stride + row * ldc + head * ATT_D + oct * 8);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] = fmaf(w, __uint_as_float(u[j] << 16), acc[2 * j]);
+      acc[2 * j + 1] = fmaf(w, __uint_as_float(u[j] & 0xffff0000u), acc[2 * j + 1]);
+    }
+  }
+  const float inv = 1.0f / wsum;
+  *reinterpret_cast<uint4*>(out + row * ldo + head * ATT_D + oct * 8) =
+      make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                 pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+}
+
+int attn_merge_chunks(const void* o_chunks, int64_t chunk_stride, int64_t ldc, const float* stats,
+                      int64_t stats_chunk_stride, int chunks, int heads, int64_t rows, void* out, int64_t ldo,
+                      cudaStream_t stream) {
+  RALD_REQUIRE(chunks >= 1 && chunks <= 8, "attn_merge: %d chunks (1..8)", chunks);
+  RALD_REQUIRE(ldc % 8 == 0 && ldo % 8 == 0 && chunk_stride % 8 == 0, "attn_merge: strides must be 16-byte multiples");
+  const int64_t total = rows * heads * 8;
+  ProfScope prof(FAM_ATTN, stream, 0.0);
+  attn_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o_chunks), chunk_stride, ldc, stats, stats_chunk_stride, chunks, heads, rows,
+      reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  RALD_LAUNCHED();
+  return 0;
+}
+
 }  // namespace rald
+
+// softmax(Q K^T * scale) V over Skv = chunks * 512 keys per frame (K / V rows frame * Skv + key): the chunked form of
+// rald_attn_d64 for contexts longer than TMEM holds. o_chunks: bf16 scratch [chunks][frames*Sq][heads*64];
+// stats: fp32 scratch [chunks][frames*Sq][heads][2].
+extern "C" int rald_attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                  void* O, int64_t ldo, int frames, int heads, int Sq, int Skv, float scale,
+                                  void* o_chunks, float* stats, void* stream) {
+  return rald::attn_d64_long(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, Skv, scale, o_chunks, stats,
+                             static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int rald_attn_debug_buffer(unsigned long long* dev_buf) {
   rald::g_attn_dbg = dev_buf;

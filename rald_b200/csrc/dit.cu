@@ -68,8 +68,17 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
     } else {
       if (pf) gemm_prefetch_next(w_o2, wsz);
       RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
-      RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx, ws.att,
-                        dim, frames, heads, M, L, scale, st));
+      if (L <= 512) {
+        RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx,
+                          ws.att, dim, frames, heads, M, L, scale, st));
+      } else {
+        // long context (use_radar_enc: false -> 2048 raw-cube tokens): key chunks of 512 + exact merge. Scratch: the
+        // GEGLU buffer ws.ff ([T][4 dim] = 4 chunk outputs, idle until the feed-forward) and the unused two thirds
+        // of ws.qkv behind q ([T][dim]) for the statistics (chunks * T * heads * 2 floats <= T * 2 dim bf16).
+        RALD_TRY(attn_d64_long(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx,
+                               ws.att, dim, frames, heads, M, L, scale, ws.ff,
+                               reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(ws.qkv) + T * dim), st));
+      }
       if (pf) gemm_prefetch_next(w_ff1, 8 * wsz);
       RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
                          0, st));
@@ -126,8 +135,9 @@ static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws,
   RALD_REQUIRE(w->heads * 64 == w->dim, "dit: head_dim must be 64 (heads=%d dim=%d)", w->heads, w->dim);
   RALD_REQUIRE(w->n_latents % 128 == 0 && w->n_latents <= 512, "dit: n_latents=%d must be a multiple of 128 <= 512",
                w->n_latents);
-  RALD_REQUIRE(w->ctx_len % 32 == 0 && w->ctx_len <= 512 && (w->ctx_len <= 256 || w->ctx_len % 256 == 0),
-               "dit: context length %d unsupported (multiple of 32, <= 512)", w->ctx_len);
+  RALD_REQUIRE(w->ctx_len % 64 == 0 &&
+                   (w->ctx_len <= 512 || (w->ctx_len % 512 == 0 && w->ctx_len <= 2048)),
+               "dit: context length %d unsupported (multiple of 64 up to 512, or 1024 / 1536 / 2048)", w->ctx_len);
   RALD_REQUIRE(frames > 0 && ws->max_frames > 0, "dit: frames=%d micro-batch=%d", frames, ws->max_frames);
   RALD_REQUIRE(ws->xattn_kp == nullptr || ws->xattn_frames >= frames,
                "dit: fused cross-attention operands cover %d frames, %d requested", ws->xattn_frames, frames);

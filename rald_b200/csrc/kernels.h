@@ -35,6 +35,17 @@ void gemm_prefetch_next(const void* weights, size_t bytes);
 int attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
              int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, cudaStream_t stream);
 
+// one key chunk of a longer context: K / V hold kv_frame_rows >= Skv rows per frame (the pointers address the
+// chunk's first row of frame 0); stats (optional) receives [frames*Sq][heads][2] = (m, l) of this chunk
+int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                   int64_t ldo, int frames, int heads, int Sq, int Skv, int kv_frame_rows, float* stats, float scale,
+                   cudaStream_t stream);
+// Skv = chunks * 512 (1024 .. 4096): chunked attention + exact merge; o_chunks bf16 [chunks][frames*Sq][heads*64],
+// stats fp32 [chunks][frames*Sq][heads][2] are scratch
+int attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                  int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* o_chunks, float* stats,
+                  cudaStream_t stream);
+
 // xattn.cu -----------------------------------------------------------------------------------------
 int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
                 int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
