@@ -35,10 +35,10 @@ constexpr int XA_KEYS = 64;
 constexpr int XA_THREADS = 320;
 constexpr int XA_A_BYTES = XA_BM * 64 * 2;   // 16 KB
 constexpr int XA_A_STAGES = 2;
-constexpr int XA_B_BYTES = 256 * 64 * 2;     // 32 KB: 256 K' rows x 64 k, or 2 x (128 VT rows x 64 k)
-constexpr int XA_B_STAGES = 4;
+constexpr int XA_B_TILE = 256 * 64 * 2;      // 32 KB: 256 K' rows x 64 k, or 2 x (128 VT rows x 64 k)
+constexpr int XA_B_RING = 4 * XA_B_TILE;     // 128 KB of ring per CTA
 constexpr int XA_STG_BYTES = 8 * 2 * 4096;   // two 32 x 32 fp32 staging tiles per epilogue warp
-constexpr int XA_SMEM = XA_A_STAGES * XA_A_BYTES + XA_B_STAGES * XA_B_BYTES + XA_STG_BYTES + XA_DIM * 4 + 256;
+constexpr int XA_SMEM = XA_A_STAGES * XA_A_BYTES + XA_B_RING + XA_STG_BYTES + XA_DIM * 4 + 256;
 
 struct XattnParams {
   const float* bias;   // [512] to_out bias
@@ -55,29 +55,41 @@ static unsigned long long* g_xattn_dbg = nullptr;
     if (p.dbg != nullptr && blockIdx.x == 0 && it < 4) p.dbg[it * 16 + (slot_)] = global_timer_ns(); \
   } while (0)
 
+// CG = 1: one CTA per 128-row tile. CG = 2: a CTA pair (cta_group::2) works on two neighbouring tiles of ONE frame with
+// 256-row MMAs: each CTA stages its own xn rows but only HALF of every K' / VT tile (the pair's tensor cores share the
+// halves), which halves the shared-memory fill + operand-read traffic per flop — the resource that paces the
+// single-CTA form (fill + reads of a B tile that is used by one MMA group only run at the 128 B/clk crossbar limit).
+// The leader (rank 0) issues all MMAs; softmax / epilogue warps of both CTAs work on their own 128 TMEM lanes.
+template <int CG>
 __global__ void __launch_bounds__(XA_THREADS, 1)
 xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                    const XattnParams p) {
+  constexpr int B_BYTES = XA_B_TILE / CG;          // this CTA's share of a B tile
+  constexpr int B_STAGES = XA_B_RING / B_BYTES;    // 4 (CG = 1) or 8 (CG = 2)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ringA = smem;
   uint8_t* ringB = ringA + XA_A_STAGES * XA_A_BYTES;
-  uint8_t* stg = ringB + XA_B_STAGES * XA_B_BYTES;
+  uint8_t* stg = ringB + XA_B_RING;
   float* s_bias = reinterpret_cast<float*>(stg + XA_STG_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + XA_DIM);
-  uint64_t* a_full = bars;                     // [3]
-  uint64_t* a_empty = a_full + XA_A_STAGES;    // [3]
-  uint64_t* b_full = a_empty + XA_A_STAGES;    // [4]
-  uint64_t* b_empty = b_full + XA_B_STAGES;    // [4]
-  uint64_t* s_full = b_empty + XA_B_STAGES;    // [2] S of head set 0 / 1 complete
-  uint64_t* p_full = s_full + 2;               // [2] P of head set 0 / 1 written by its 4 softmax warps
+  uint64_t* a_full = bars;                     // [2]   (leader's copy is the one waited on when CG = 2)
+  uint64_t* a_empty = a_full + XA_A_STAGES;    // [2]
+  uint64_t* b_full = a_empty + XA_A_STAGES;    // [8]
+  uint64_t* b_empty = b_full + 8;              // [8]
+  uint64_t* s_full = b_empty + 8;              // [2] S complete (one per head set)
+  uint64_t* p_full = s_full + 2;               // [2] P of head set 0 / 1 written by its softmax warps (of both CTAs)
   uint64_t* o_full = p_full + 2;               // [2] O quarter accumulated
-  uint64_t* o_empty = o_full + 2;              // [2] O quarter drained by the 8 epilogue warps
+  uint64_t* o_empty = o_full + 2;              // [2] O quarter drained by the epilogue warps (of both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit_tiles = p.num_tiles / CG;     // tile pairs when CG = 2 (tiles 2u, 2u + 1: same frame)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -85,22 +97,23 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < XA_A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < XA_B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 4 * CG);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 8);
+      mbar_init(&o_empty[i], 8 * CG);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < XA_DIM; i += XA_THREADS) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // (Prefetching the context boxes of this CTA's tiles into L2 here, before the grid dependency resolves, was measured
@@ -110,57 +123,87 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA: its xn rows, its share of the B tiles) =====================
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int ut = unit; ut < unit_tiles; ut += num_units) {
+        const int tile = ut * CG + (int)rank;
         const int f = p.frame0 + tile / p.tiles_per_frame;
         // S phase: per k-step one xn tile and the two 256-column halves of K' (4 heads x 64 keys each). (Running the
         // two head sets one after the other, so that the first softmax overlaps the second set's MMAs, was measured
-        // SLOWER: 60.5 vs 56.2 us per launch at 64 frames — the phase is bound by operand delivery from L2, and that
-        // order streams xn twice.)
+        // SLOWER: 60.5 vs 56.2 us per launch at 64 frames, and that order streams xn twice.)
         for (int kb = 0; kb < XA_DIM / 64; ++kb) {
           mbar_wait(&a_empty[sa], pha ^ 1);
-          mbar_arrive_expect_tx(&a_full[sa], XA_A_BYTES);
-          tma_load_2d(ringA + sa * XA_A_BYTES, &tmX, &a_full[sa], kb * 64, tile * XA_BM);
+          if (CG == 2) {
+            // every byte of the pair is credited to the LEADER's full barrier, on which only the leader arrives
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * XA_A_BYTES);
+            tma_load_2d_pair(ringA + sa * XA_A_BYTES, &tmX, &a_full[sa], kb * 64, tile * XA_BM);
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], XA_A_BYTES);
+            tma_load_2d(ringA + sa * XA_A_BYTES, &tmX, &a_full[sa], kb * 64, tile * XA_BM);
+          }
           if (++sa == XA_A_STAGES) { sa = 0; pha ^= 1; }
           for (int j = 0; j < 2; ++j) {
             mbar_wait(&b_empty[sb], phb ^ 1);
-            mbar_arrive_expect_tx(&b_full[sb], XA_B_BYTES);
-            for (int i = 0; i < 4; ++i)
-              tma_load_2d(ringB + sb * XA_B_BYTES + i * (XA_KEYS * 128), &tmK, &b_full[sb], kb * 64,
-                          ((4 * j + i) * p.total_frames + f) * XA_KEYS);
-            if (++sb == XA_B_STAGES) { sb = 0; phb ^= 1; }
+            if (CG == 2) {
+              // rows [128 rank, 128 rank + 128) of the 256-row K' tile = heads 4 j + 2 rank + {0, 1}
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], XA_B_TILE);
+              for (int i = 0; i < 2; ++i)
+                tma_load_2d_pair(ringB + sb * B_BYTES + i * (XA_KEYS * 128), &tmK, &b_full[sb], kb * 64,
+                                 ((4 * j + 2 * (int)rank + i) * p.total_frames + f) * XA_KEYS);
+            } else {
+              mbar_arrive_expect_tx(&b_full[sb], XA_B_TILE);
+              for (int i = 0; i < 4; ++i)
+                tma_load_2d(ringB + sb * B_BYTES + i * (XA_KEYS * 128), &tmK, &b_full[sb], kb * 64,
+                            ((4 * j + i) * p.total_frames + f) * XA_KEYS);
+            }
+            if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
         }
-        // O phase: per output quarter, four slots of two VT k-blocks (= two heads) each
+        // O phase: per output quarter, four slots of two VT k-blocks (= two heads) each; with CG = 2 this CTA stages
+        // output rows [64 rank, 64 rank + 64) of each 128-row quarter tile
         for (int q = 0; q < 4; ++q) {
           for (int kp = 0; kp < 4; ++kp) {
             mbar_wait(&b_empty[sb], phb ^ 1);
-            mbar_arrive_expect_tx(&b_full[sb], XA_B_BYTES);
-            for (int sub = 0; sub < 2; ++sub)
-              tma_load_2d(ringB + sb * XA_B_BYTES + sub * (XA_B_BYTES / 2), &tmV, &b_full[sb], f * XA_KEYS,
-                          (2 * kp + sub) * XA_DIM + q * 128);
-            if (++sb == XA_B_STAGES) { sb = 0; phb ^= 1; }
+            if (CG == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], XA_B_TILE);
+              for (int sub = 0; sub < 2; ++sub)
+                tma_load_2d_pair(ringB + sb * B_BYTES + sub * (B_BYTES / 2), &tmV, &b_full[sb], f * XA_KEYS,
+                                 (2 * kp + sub) * XA_DIM + q * 128 + (int)rank * 64);
+            } else {
+              mbar_arrive_expect_tx(&b_full[sb], XA_B_TILE);
+              for (int sub = 0; sub < 2; ++sub)
+                tma_load_2d(ringB + sb * B_BYTES + sub * (B_BYTES / 2), &tmV, &b_full[sb], f * XA_KEYS,
+                            (2 * kp + sub) * XA_DIM + q * 128);
+            }
+            if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(FMT_BF16, XA_BM, 256, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc(FMT_F16, XA_BM, 128, 0, 0);   // P fp16 (TMEM) x VT fp16 (smem)
+    // ===================== MMA issuer (the leader CTA only when CG = 2) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc_s = make_idesc(FMT_BF16, XA_BM * CG, 256, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc(FMT_F16, XA_BM * CG, 128, 0, 0);   // P fp16 (TMEM) x VT fp16 (smem)
+      auto commit = [&](uint64_t* bar) {
+        if (CG == 2) tc_commit_pair(bar);
+        else tc_commit(bar);
+      };
+      auto wait_peer = [&](uint64_t* bar, uint32_t parity) {   // barriers the peer's warps arrive on remotely
+        if (CG == 2) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+      };
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int ut = unit; ut < unit_tiles; ut += num_units, ++it) {
         // the previous tile's last two O quarters (one per buffer) have been drained; since those were committed after
         // every earlier MMA, all reads of the previous P have retired too: S may overwrite the whole TMEM
         const uint32_t u0 = 2u * (uint32_t)it;   // use index of each O buffer at this tile's first quarter
-        mbar_wait(&o_empty[0], (u0 & 1u) ^ 1u);
-        mbar_wait(&o_empty[1], (u0 & 1u) ^ 1u);
+        wait_peer(&o_empty[0], (u0 & 1u) ^ 1u);
+        wait_peer(&o_empty[1], (u0 & 1u) ^ 1u);
         tc_fence_after();
         XA_STAMP(0);
         for (int kb = 0; kb < XA_DIM / 64; ++kb) {
@@ -169,29 +212,31 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           for (int j = 0; j < 2; ++j) {
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
-            const uint64_t b_desc = make_sdesc_sw128(smem_u32(ringB + sb * XA_B_BYTES), 16, 1024);
+            const uint64_t b_desc = make_sdesc_sw128(smem_u32(ringB + sb * B_BYTES), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss(tmem_base + 256 * j, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
-            tc_commit(&b_empty[sb]);
-            if (++sb == XA_B_STAGES) { sb = 0; phb ^= 1; }
+            for (int k = 0; k < 4; ++k) {
+              if (CG == 2) mma_f16_ss_pair(tmem_base + 256 * j, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+              else mma_f16_ss(tmem_base + 256 * j, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+            }
+            commit(&b_empty[sb]);
+            if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
-          tc_commit(&a_empty[sa]);
+          commit(&a_empty[sa]);
           if (++sa == XA_A_STAGES) { sa = 0; pha ^= 1; }
         }
-        tc_commit(&s_full[0]);
-        tc_commit(&s_full[1]);
+        commit(&s_full[0]);
+        commit(&s_full[1]);
         XA_STAMP(1);
         for (int q = 0; q < 4; ++q) {
           const int buf = q & 1;
           const uint32_t u = u0 + (uint32_t)(q >> 1);
-          mbar_wait(&o_empty[buf], (u & 1u) ^ 1u);
+          wait_peer(&o_empty[buf], (u & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (buf ? 384u : 128u);
           for (int kp = 0; kp < 4; ++kp) {
             // heads 0..3 read P of set 0, heads 4..7 of set 1 (written while the first MMAs of this quarter run)
             if (q == 0 && (kp == 0 || kp == 2)) {
-              mbar_wait(&p_full[kp >> 1], (uint32_t)it & 1u);
+              wait_peer(&p_full[kp >> 1], (uint32_t)it & 1u);
               XA_STAMP(2 + (kp >> 1));
             }
             mbar_wait(&b_full[sb], phb);
@@ -200,28 +245,34 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             for (int sub = 0; sub < 2; ++sub) {
               const int kb = 2 * kp + sub;   // = head
               const uint32_t p_col = tmem_base + (kb < 4 ? 32u * kb : 256u + 32u * (kb - 4));
-              const uint64_t b_desc =
-                  make_sdesc_sw128(smem_u32(ringB + sb * XA_B_BYTES + sub * (XA_B_BYTES / 2)), 16, 1024);
+              const uint64_t b_desc = make_sdesc_sw128(smem_u32(ringB + sb * B_BYTES + sub * (B_BYTES / 2)), 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma_f16_ts(d_tmem, p_col + 8 * k, b_desc + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (CG == 2) mma_f16_ts_pair(d_tmem, p_col + 8 * k, b_desc + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
+                else mma_f16_ts(d_tmem, p_col + 8 * k, b_desc + 2 * k, idesc_o, (kb | k) != 0 ? 1u : 0u);
+              }
             }
-            tc_commit(&b_empty[sb]);
-            if (++sb == XA_B_STAGES) { sb = 0; phb ^= 1; }
+            commit(&b_empty[sb]);
+            if (++sb == B_STAGES) { sb = 0; phb ^= 1; }
           }
-          tc_commit(&o_full[buf]);
+          commit(&o_full[buf]);
           XA_STAMP(4 + q);
         }
       }
     }
   } else {
-    // ===================== softmax + epilogue (warps 2..9) =====================
+    // ===================== softmax + epilogue (warps 2..9 of every CTA, on its own tile) =====================
     const int qd = warp & 3;             // TMEM lane quarter
     const int ew = warp - 2;             // 0..7
     const int hs = ew >> 2;              // head set: 0 -> heads 0..3, 1 -> heads 4..7
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    auto arrive_mma = [&](uint64_t* bar) {   // barriers the (leader's) MMA thread waits on
+      if (CG == 2) mbar_arrive_leader(bar);
+      else mbar_arrive(bar);
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int ut = unit; ut < unit_tiles; ut += num_units, ++it) {
+      const int tile = ut * CG + (int)rank;
       mbar_wait(&s_full[hs], (uint32_t)it & 1u);
       tc_fence_after();
       if (warp == 2 && lane == 0) XA_STAMP(8);
@@ -277,7 +328,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[hs]);
+      if (lane == 0) arrive_mma(&p_full[hs]);
       if (warp == 2 && lane == 0) XA_STAMP(9);
 
       // ---- epilogue: four output quarters, this warp stores 32-column chunks hs and hs + 2 of each ----
@@ -300,13 +351,13 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (c + 2 >= 4) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[buf]);
+            if (lane == 0) arrive_mma(&o_empty[buf]);
           }
           const float* bs = s_bias + q * 128 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + bs[j]);
           uint8_t* my_stg = my_stg0 + sbuf * 4096;
-          if (lane == 0) bulk_wait_group_read<1>();   // the store issued two chunks ago (same tile) has been read
+          if (lane == 0) bulk_wait_group_read<1>();   // the store issued two chunks ago has been read
           __syncwarp();
           const uint32_t sdst = smem_u32(my_stg) + lane * 128;
 #pragma unroll
@@ -315,6 +366,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
+            // (reading the residual chunk into registers ahead of the accumulator and issuing a plain TMA store was
+            // measured slower than the L2-side reduction: 69 vs 56 us per launch)
             tma_reduce_add_2d(&tmO, my_stg, q * 128 + c * 32, row0);
             bulk_commit_group();
           }
@@ -327,11 +380,21 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's smem / barriers / TMEM stay valid until both CTAs are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
+}
+
+// CTA pairs are OFF by default: parity-green, but measured slower at 64 frames (62.5 vs 56.3 us per launch): the O phase
+// is paced by the residual read-modify-write of all CTAs at once and the S phase by L2 -> SM delivery, and the pair
+// form shortens neither enough to pay for its longer softmax / epilogue tail. RALD_B200_XATTN_PAIR=1 enables it.
+static bool xattn_pair_enabled() {
+  const char* e = getenv("RALD_B200_XATTN_PAIR");
+  return e != nullptr && e[0] == '1';
 }
 
 // h[T][512] += fused cross-attention of xn[T][512] against the folded context operands of one block.
@@ -344,8 +407,11 @@ int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bia
   CUtensorMap tmX, tmK, tmV, tmO;
   RALD_TRY(make_tmap_2d_bf16(&tmX, xn, (uint64_t)T, XA_DIM, XA_DIM, XA_BM));
   RALD_TRY(make_tmap_2d_bf16(&tmK, kp, (uint64_t)8 * total_frames * XA_KEYS, XA_DIM, XA_DIM, XA_KEYS));
+  // CTA pairs when the row tiles pair up inside a frame and there are enough of them to fill the machine
+  const int sms = device_sm_count();
+  const bool pair = xattn_pair_enabled() && (rows_per_frame / XA_BM) % 2 == 0 && T / XA_BM >= sms;
   RALD_TRY(make_tmap_2d_bf16(&tmV, vt, (uint64_t)8 * XA_DIM, (uint64_t)total_frames * XA_KEYS,
-                             (uint64_t)total_frames * XA_KEYS, 128));
+                             (uint64_t)total_frames * XA_KEYS, pair ? 64 : 128));
   RALD_TRY(make_tmap_out(&tmO, h, (uint64_t)T, XA_DIM, XA_DIM, true));
   XattnParams p;
   p.bias = bias;
@@ -356,14 +422,20 @@ int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bia
   p.dbg = g_xattn_dbg;
   static bool configured = false;
   if (!configured) {
-    RALD_CHECK_CUDA(cudaFuncSetAttribute(xattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(xattn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(xattn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM));
     configured = true;
   }
-  const int sms = device_sm_count();
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   // executed flops: S and O products, 2 x (2 * 128 * 512 * 512) per tile
   ProfScope prof(FAM_XATTN, stream, 4.0 * (double)T * XA_DIM * XA_HK);
-  RALD_CHECK_CUDA(launch_pdl(xattn_fused_kernel, dim3(grid), dim3(XA_THREADS), XA_SMEM, stream, tmX, tmK, tmV, tmO, p));
+  if (pair) {
+    const int units = p.num_tiles / 2 < sms / 2 ? p.num_tiles / 2 : sms / 2;
+    RALD_CHECK_CUDA(launch_pdl_cluster(xattn_fused_kernel<2>, dim3(2 * units), dim3(XA_THREADS), XA_SMEM, stream, 2u, tmX,
+                                       tmK, tmV, tmO, p));
+  } else {
+    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    RALD_CHECK_CUDA(launch_pdl(xattn_fused_kernel<1>, dim3(grid), dim3(XA_THREADS), XA_SMEM, stream, tmX, tmK, tmV, tmO, p));
+  }
   RALD_LAUNCHED();
   return 0;
 }

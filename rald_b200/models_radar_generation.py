@@ -170,15 +170,30 @@ def edm_sampler(net, latents, class_labels=None, cond_type=None, randn_like=torc
 
 
 class EDMLoss:
-    """Training loss of the reference (:277-295). Training is outside this round's hot path:
-    the network forward here is inference-only, so calling the loss raises."""
+    """EDM denoising loss of the reference (:277-295): per-sample log-normal sigma, weight (s^2 + sd^2) / (s sd)^2,
+    mean of weight * (D(y + n; sigma) - y)^2. The network forward of this package is inference-only, so the loss can
+    be EVALUATED (validation loss: call it under ``torch.no_grad()`` or with an ``.eval()`` network; the per-sample
+    sigma path of ``rald_dit_forward`` is used) but not differentiated — training is SURVEY.md §8f #3. The RNG calls
+    (``randn([B,1,1])``, then ``randn_like(y)``, both on the input's device) are the reference's, in its order."""
 
     def __init__(self, P_mean=-1.2, P_std=1.2, sigma_data=1):
         self.P_mean, self.P_std, self.sigma_data = P_mean, P_std, sigma_data
 
     def __call__(self, net, inputs, labels=None, cond_type=None, augment_pipe=None):
-        raise NotImplementedError("rald_b200: EDMLoss needs the training forward/backward (SURVEY.md §8f #3), "
-                                  "which is not part of the generation hot path")
+        if torch.is_grad_enabled() and getattr(net, "training", False) and any(
+                p.requires_grad for p in net.parameters()):
+            raise NotImplementedError("rald_b200: EDMLoss can be evaluated but not differentiated — the training "
+                                      "forward/backward is not built (SURVEY.md §8f #3); call it under "
+                                      "torch.no_grad() or with net.eval()")
+        with torch.no_grad():
+            rnd_normal = torch.randn([inputs.shape[0], 1, 1], device=inputs.device)
+            sigma = (rnd_normal * self.P_std + self.P_mean).exp()
+            weight = (sigma ** 2 + self.sigma_data ** 2) / (sigma * self.sigma_data) ** 2
+            y, _ = augment_pipe(inputs) if augment_pipe is not None else (inputs, None)
+            n = torch.randn_like(y) * sigma
+            D_yn = net(y + n, sigma, labels, cond_type)
+            loss = weight * ((D_yn - y) ** 2)
+            return loss.mean()
 
 
 # --------------------------------------------------------------------------------------------------

@@ -61,3 +61,32 @@ def test_batch_equals_single_frames(net, golden):
     for i in range(3):
         xi = net.sample_from_latents(lat[i:i + 1], tokens[i:i + 1], num_steps=4)
         assert torch.equal(xb[i], xi[0])
+
+
+@torch.no_grad()
+def test_edm_loss_evaluation_matches_oracle(net, golden):
+    """EDMLoss.__call__ (reference :277-295) evaluated without gradients: the CUDA generator's draws are replayed
+    (same seed -> same randn calls in the reference's order) and the loss recomputed through the CPU oracle."""
+    from oracle import rald_oracle as orc
+    from rald_b200.models_radar_generation import EDMLoss
+    tok = golden("denoiser_eval")["tokens2"].cuda()
+    y = (synth.unit_latents([3, 4]) * 0.7).cuda()
+    crit = EDMLoss()
+    torch.cuda.manual_seed(11)
+    loss = crit(net, y, tok, "radar")
+    torch.cuda.manual_seed(11)
+    rnd = torch.randn([2, 1, 1], device="cuda")
+    noise = torch.randn_like(y)
+    sigma = (rnd * crit.P_std + crit.P_mean).exp()
+    sd = cpu_state_dict(net)
+    d = orc.edm_precond(sd, (y + noise * sigma).cpu(), sigma.cpu(), tok.cpu().float())
+    weight = (sigma.cpu() ** 2 + 1.0) / sigma.cpu() ** 2
+    want = (weight * (d - y.cpu()) ** 2).mean()
+    assert loss.dim() == 0 and abs(float(loss) - float(want)) <= 2e-2 * float(want)
+    # differentiating it is not available: a training-mode network with gradients enabled raises
+    net.train()
+    try:
+        with torch.enable_grad(), pytest.raises(NotImplementedError):
+            crit(net, y, tok, "radar")
+    finally:
+        net.eval()

@@ -29,8 +29,10 @@ def _reference(xn, kv, wq, wo, bias, h0, depth_idx, frames_slice, heads=8):
 
 
 @torch.no_grad()
-@pytest.mark.parametrize("frames,frame0,total", [(1, 0, 1), (2, 1, 4), (5, 0, 5)])
-def test_fused_cross_attention_kernel(frames, frame0, total):
+@pytest.mark.parametrize("frames,frame0,total", [(1, 0, 1), (2, 1, 4), (5, 0, 5), (38, 2, 41)])  # 38 frames: CTA pairs
+def test_fused_cross_attention_kernel(frames, frame0, total, monkeypatch):
+    if frames >= 37:
+        monkeypatch.setenv("RALD_B200_XATTN_PAIR", "1")   # the optional cta_group::2 form (off by default)
     torch.manual_seed(5 + frames)
     depth, dim, M = 2, 512, 512
     bf = torch.bfloat16
