@@ -30,20 +30,36 @@ constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
+// staging tiles per epilogue warp: 2 was measured no faster for the K = 512 GEMMs and slower for K = 2048 (one ring
+// stage less): FF1 127.6 vs 128.5, QKV 49.2 vs 49.4, FF2 66.1 vs 64.2 us at M = 32768
+#ifndef RALD_GEMM_NBUF
+#define RALD_GEMM_NBUF 1
+#endif
 
 // CG = 1: one CTA computes a 128 x BN tile. CG = 2: a CTA pair (cta_group::2, the two SMs of a TPC) computes a
 // 256 x BN tile with ONE 256-row MMA per K step; each CTA stages its 128 rows of A and only HALF of the W tile, so
 // the shared-memory fill traffic per flop drops by a third and the ring gets deeper.
-template <int BN, int CG = 1>
+//
+// ARES (A-resident, K = 512): the 128 x 512 A block of a row block (128 KB) is loaded ONCE and stays in shared memory
+// while the W tiles of all the column tiles this unit owns of that row block stream through the ring. Each unit walks a
+// contiguous, balanced range of the row-block-major tile order. The L2 -> SM operand traffic of a wide GEMM drops by
+// almost half (FF1: 8 MB -> 4.25 MB per 256-row block). MEASURED on B200 at M = 32768: parity-green but NOT faster
+// (FF1 124.3 vs 122.8 us, QKV 47.3 vs 47.8 us, N = 512: 34.5 vs 31.1 us) — operand delivery is not what holds these
+// kernels at ~2x the tcgen05 issue floor (every shape runs at 2.0x: FF1 4.64 us per 256 x 256 x 512 tile against
+// 2.35 us, FF2 18.5 against 9.4). Off by default; RALD_B200_GEMM_ARES=1 enables it for N >= 1024, =2 for all N.
+constexpr int ARES_K = 512;
+constexpr int ARES_BYTES = GEMM_BM * ARES_K * 2;
+template <int BN, int CG = 1, bool ARES = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NBUF = 1;                               // staging tiles per epilogue warp
+  static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
+  static constexpr int A_RES_BYTES = ARES ? ARES_BYTES : 0;
+  static constexpr int NBUF = ARES ? 1 : RALD_GEMM_NBUF;       // staging tiles per epilogue warp
   static constexpr int STG_TOTAL = GEMM_EPI_WARPS * NBUF * STG_BYTES;
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   // no alignment slack: dynamic shared memory starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int FIXED = 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES;
+  static constexpr int FIXED = 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES + A_RES_BYTES;
   static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
@@ -135,11 +151,11 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 }
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE, int EPI, int CG>
+template <int BN, int OUT_MODE, int EPI, int CG, bool ARES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, ARES>;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-processing unit (CTA or CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -152,18 +168,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128-byte swizzle atoms need 1024-byte aligned tiles
-  uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES;                    // 1024-byte aligned (stage sizes are)
+  uint8_t* a_res = smem + STAGES * Cfg::STAGE_BYTES;                  // ARES: the resident A block (1024-aligned)
+  uint8_t* stg = a_res + Cfg::A_RES_BYTES;                            // 1024-byte aligned (stage sizes are)
   float* s_bias = reinterpret_cast<float*>(stg + Cfg::STG_TOTAL);     // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* a_full_bar = tmem_empty_bar + 2;    // ARES: resident A block landed (both CTAs' rows when CG = 2)
+  uint64_t* a_empty_bar = a_full_bar + 1;       // ARES: every MMA reading the resident A block has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blks * p.num_n_blks;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  // Tile walk of this unit. Default: tiles unit, unit + num_units, ... ARES: the contiguous, balanced range
+  // [unit * T / U, (unit + 1) * T / U) of the row-block-major order (consecutive tiles share the resident A block).
+  const int t_begin = ARES ? (int)(((long long)unit * num_tiles) / num_units) : unit;
+  const int t_end = ARES ? (int)(((long long)(unit + 1) * num_tiles) / num_units) : num_tiles;
+  const int t_step = ARES ? 1 : num_units;
 
   if (threadIdx.x == 0) {
     GEMM_STAMP(0);
@@ -178,6 +202,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(a_full_bar, 1);
+    mbar_init(a_empty_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -203,22 +229,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       GEMM_STAMP(1);
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
+      int seg = -1, seg_m = -1;   // ARES: index / row block of the resident A block
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         const int m_blk = tile / p.num_n_blks;
         const int n_blk = tile - m_blk * p.num_n_blks;
+        if (ARES && m_blk != seg_m) {
+          // new row block: the resident A buffer is free once every MMA of the previous one has completed
+          ++seg;
+          seg_m = m_blk;
+          mbar_wait(a_empty_bar, ((uint32_t)seg & 1u) ^ 1u);
+          if (CG == 2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(a_full_bar, 2 * ARES_BYTES);
+            for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
+              tma_load_2d_pair(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK,
+                               m_blk * TILE_M + (int)cta_rank * GEMM_BM);
+          } else {
+            mbar_arrive_expect_tx(a_full_bar, ARES_BYTES);
+            for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
+              tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK, m_blk * GEMM_BM);
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
           if (CG == 2) {
             // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
             // to the LEADER's full barrier, on which only the leader arrives
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * GEMM_BM);
+            if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * GEMM_BM);
             tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+            if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
             tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -232,9 +275,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      int seg = -1, seg_m = -1;
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
+        if (ARES) {
+          const int m_blk = tile / p.num_n_blks;
+          if (m_blk != seg_m) {
+            // every MMA of the previous row block has been issued: its A block is free once they complete
+            if (seg >= 0) {
+              if (CG == 2) tc_commit_pair(a_empty_bar);
+              else tc_commit(a_empty_bar);
+            }
+            ++seg;
+            seg_m = m_blk;
+            mbar_wait(a_full_bar, (uint32_t)seg & 1u);
+            tc_fence_after();
+          }
+        }
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -242,8 +300,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (it == 0 && kb == 0) GEMM_STAMP(2);
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sst = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sa = ARES ? smem_u32(a_res) + (uint32_t)kb * Cfg::A_BYTES : sst;
+          const uint32_t sb = ARES ? sst : sst + Cfg::A_BYTES;
           const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
           const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
@@ -273,7 +332,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
     int sbuf = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       const int m_blk = tile / p.num_n_blks;
       const int n_blk = tile - m_blk * p.num_n_blks;
       const int acc = it & 1;
@@ -417,11 +476,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int OUT_MODE, int EPI, int CG = 1>
+template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG>;
+  using Cfg = GemmCfg<BN, CG, ARES>;
+  static_assert(Cfg::STAGES >= 3, "ring too shallow");
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -549,6 +609,17 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     tmO = tmA;
   }
 
+  // A-resident form for the K = 512 pair GEMMs (off by default, see GemmCfg)
+  static int ares_env = -1;
+  if (ares_env < 0) {
+    const char* e = getenv("RALD_B200_GEMM_ARES");
+    ares_env = e == nullptr ? 0 : (e[0] - '0');
+  }
+  if (pair && K == ARES_K && ares_env >= 1 && (N >= 1024 || ares_env >= 2)) {
+    if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2, true>(tmA, tmB, tmO, p, sms, stream);
+    if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2, true>(tmA, tmB, tmO, p, sms, stream);
+    if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2, true>(tmA, tmB, tmO, p, sms, stream);
+  }
   if (pair) {
     if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);

@@ -55,7 +55,11 @@ def run(M, N, K, mode, bn, reps=20):
           f" | last-exit={acc[7] / 1000:.2f} us | warm back-to-back {warm:.2f} us")
 
 
-for (M, N, K, mode) in [(512, 1536, 512, 0), (512, 512, 512, 1), (512, 4096, 512, 2), (512, 512, 2048, 1),
+if __name__ != "__main__":
+    SHAPES = []
+else:
+    SHAPES = None
+for (M, N, K, mode) in SHAPES if SHAPES is not None else [(512, 1536, 512, 0), (512, 512, 512, 1), (512, 4096, 512, 2), (512, 512, 2048, 1),
                         (4096, 1536, 512, 0), (4096, 512, 2048, 1)]:
     for bn in ((32, 64, 128) if M == 512 else (128, 256)):
         if mode == 2 and bn < 64:
