@@ -32,6 +32,13 @@ constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
 // staging tiles per epilogue warp: 2 was measured no faster for the K = 512 GEMMs and slower for K = 2048 (one ring
 // stage less): FF1 127.6 vs 128.5, QKV 49.2 vs 49.4, FF2 66.1 vs 64.2 us at M = 32768
+// 1: one 128-row TMA store per column chunk (four warps share a staging tile, two named barriers per chunk) instead
+// of four 32-row stores. Parity-green, measured NOT faster (QKV 50.9 vs 49.4, O1 28.8 vs 26.9 us at M = 32768): the
+// ~11 us the store path adds to every large GEMM is not the TMA issue rate of small boxes.
+#ifndef RALD_GEMM_WIDE_STORE
+#define RALD_GEMM_WIDE_STORE 0
+#endif
+constexpr bool GEMM_WIDE_STORE = RALD_GEMM_WIDE_STORE != 0;
 #ifndef RALD_GEMM_NBUF
 #define RALD_GEMM_NBUF 1
 #endif
@@ -78,6 +85,8 @@ struct GemmParams {
   const uint8_t* pf_ptr;      // weights of the NEXT GEMM in the stream, prefetched into L2 by this kernel's idle
   uint32_t pf_bytes;          // epilogue threads (small-batch regime: hides the DRAM latency of the next launch)
   int f16_start, f16_period;  // bf16 mode: output columns with (col % f16_period) >= f16_start are written as fp16
+  int skip_epilogue;          // DEBUG (RALD_B200_GEMM_SKIP_EPI=1): accumulators are released unread, nothing is stored —
+                              // isolates the TMA + MMA main loop for timing (tools/gemm_phases_big.py); results are garbage
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
@@ -354,6 +363,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       if (it == 0 && threadIdx.x == 64) GEMM_STAMP(4);
+      if (p.skip_epilogue == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_acc();
+        continue;
+      }
       if (it == 0 && p.pf_bytes != 0) {
         // This CTA's own operands have landed (its first accumulator is complete): now pull the NEXT GEMM's weights
         // into L2, 16 KB per request, spread over the epilogue threads of all CTAs. Issued here rather than at kernel
@@ -440,7 +455,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) release_acc();
           }
-          if (live) {
+          if (p.skip_epilogue == 2) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x ^= o[j];
+            if (x == 0x12345678u) p.dbg[0] = x;   // keeps the arithmetic alive
+          } else if (live && GEMM_WIDE_STORE) {
+            // One 128-row TMA store per column chunk instead of four 32-row ones: the four warps owning the four TMEM
+            // lane quarters of this chunk parity share a 16 KB staging tile (small boxes made the TMA store rate the
+            // pace of the K = 512 GEMMs' epilogue). Two 128-thread named barriers per chunk: staging free / rows written.
+            uint8_t* gstg = stg + hs * (4 * STG_BYTES);
+            if (q == 0 && lane == 0) bulk_wait_group_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + hs) : "memory");
+            const uint32_t sdst = smem_u32(gstg) + (uint32_t)(q * 32 + lane) * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + hs) : "memory");
+            if (q == 0 && lane == 0) {
+              const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
+              const int orow = m_blk * TILE_M + (int)cta_rank * GEMM_BM;
+              if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, gstg, ocol, orow);
+              else tma_store_2d(&tmO, gstg, ocol, orow);
+              bulk_commit_group();
+            }
+          } else if (live) {
             if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the staging tile about to be overwritten was read
             __syncwarp();
             const uint32_t sdst = smem_u32(stg + (ew * NBUF + sbuf) * STG_BYTES) + lane * 128;
@@ -594,6 +634,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.dbg = g_gemm_dbg;
   p.f16_start = f16_start;
   p.f16_period = f16_period;
+  {
+    const char* e = getenv("RALD_B200_GEMM_SKIP_EPI");
+    p.skip_epilogue = e != nullptr ? (e[0] - '0') : 0;   // 1: no epilogue at all; 2: TMEM reads + arithmetic, no stores
+  }
   p.pf_ptr = static_cast<const uint8_t*>(g_pf_ptr);
   p.pf_bytes = (uint32_t)(g_pf_bytes > 0xfffffff0ull ? 0 : g_pf_bytes);
   g_pf_ptr = nullptr;
@@ -604,7 +648,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
   RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
   if (epi != EPI_GENERIC) {
-    RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1));
+    RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1,
+                           GEMM_WIDE_STORE ? 128u : 32u));
   } else {
     tmO = tmA;
   }

@@ -81,10 +81,11 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box, nullptr);
 }
 
-int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32) {
+int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32,
+                  uint32_t box_rows) {
   uint64_t dims[2] = {cols, rows};
   uint64_t strides[1] = {ld * (f32 ? 4u : 2u)};
-  uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+  uint32_t box[2] = {f32 ? 32u : 64u, box_rows};
   return encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 2, dims, strides,
                 box, nullptr);
 }

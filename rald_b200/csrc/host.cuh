@@ -43,8 +43,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // same for 32-bit elements (tf32 operands): box = box_rows x 32 columns (128 bytes)
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows);
-// Output tiles for TMA stores: box = 32 rows x 128 bytes (32 fp32 or 64 bf16 columns), 128-byte swizzle.
-int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32);
+// Output tiles for TMA stores: box = box_rows (32 or 128) rows x 128 bytes (32 fp32 or 64 bf16 columns), 128-byte swizzle.
+int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool f32,
+                  uint32_t box_rows = 32);
 // General tiled map over 16-bit elements: dims/strides innermost first (strides in BYTES for dims 1..rank-1).
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
