@@ -98,7 +98,7 @@ def main():
     # ---- radar cube prep: process_radar_data on raw cubes [128, 8, 2, 3] ----
     stand_in = types.SimpleNamespace(config=types.SimpleNamespace(radar=radar))
     raws, refs = [], []
-    for k in range(2):
+    for k in range(1):
         raw = np.zeros((radar.input_r_dim, radar.input_a_dim, radar.input_e_dim, 3), np.float32)
         raw[..., 0] = rs.uniform(-5.0, 60.0, raw.shape[:3])            # dB, beyond the clip on both sides
         raw[..., 1] = rs.uniform(-2.5, 2.5, raw.shape[:3])

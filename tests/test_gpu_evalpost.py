@@ -118,13 +118,13 @@ def test_radar_cube_prep_fixture_bit_exact():
                tgt_r_dim=128, tgt_a_dim=int(ta), tgt_e_dim=int(te))
     raw = torch.from_numpy(g["radar_raw"]).to(DEV)
     out = radar_prep.process_radar_data(raw, cfg)
-    assert out.shape == (2, 128, 64, 32, 2)
+    assert out.shape == (1, 128, 64, 32, 2)
     assert np.array_equal(out.cpu().numpy(), g["radar_processed"])
     # single un-batched cube, intensity channel only (the encoder's input), early return (no upsample, raw doppler)
     one = radar_prep.process_radar_data(raw[0], cfg, channels_out=1)
     assert np.array_equal(one.cpu().numpy()[..., 0], g["radar_processed"][0][..., 0])
-    early = radar_prep.process_radar_data(raw[1], cfg, early_return=True)
-    want = orc.process_radar_data(g["radar_raw"][1], bool(ni), mi, False, 1.0, False, 0, 0)
+    early = radar_prep.process_radar_data(raw[0], cfg, early_return=True)
+    want = orc.process_radar_data(g["radar_raw"][0], bool(ni), mi, False, 1.0, False, 0, 0)
     assert np.array_equal(early.cpu().numpy(), want)
     # other target sizes, seeded, against the oracle
     rs = np.random.RandomState(5)
@@ -147,7 +147,7 @@ def test_prepared_cube_feeds_the_denoiser_conditioning():
     cube = radar_prep.process_radar_data(torch.from_numpy(g["radar_raw"]).to(DEV), cfg)
     a = net.process_radar_cond(cube)
     b = net.process_radar_cond(torch.from_numpy(g["radar_processed"]).to(DEV))
-    assert a.shape == (2, 64, 512) and rel_l2(a, b) < 1e-3
+    assert a.shape == (1, 64, 512) and rel_l2(a, b) < 1e-3
 
 
 @torch.no_grad()
