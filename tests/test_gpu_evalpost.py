@@ -175,3 +175,40 @@ def test_refine_pass_end_to_end():
         assert np.allclose(pts2[b, :len(want)].cpu().numpy(), want, rtol=0, atol=2e-5)
     cd = postproc.chamfer_distance(pts2, cnt2, postproc.polar_to_cartesian(pts[:, :4000]), cnt.clamp(max=4000))
     assert torch.isfinite(cd).all() and float(cd.min()) >= 0.0
+
+
+@torch.no_grad()
+def test_generate_point_clouds_pipeline():
+    """evaluate()'s per-batch body chained on the device equals the same chain assembled by hand from the
+    parity-tested pieces; the host query grid replays the reference's np.random.uniform draws."""
+    from helpers import build_ae, build_denoiser
+    from rald_b200 import evaluate, synth
+    rng = [0, -90, -20, 15.8, 90, 20]
+    np.random.seed(5)
+    g = evaluate.generate_query_points(1000, rng)
+    np.random.seed(5)
+    want = np.stack([np.random.uniform(-1, 1, 1000) for _ in range(3)], axis=1)
+    assert g.dtype == np.float64 and np.array_equal(g, want)
+    net, ae = build_denoiser(device=DEV), build_ae(device=DEV)
+    cube = synth.radar_cube(2, seed=21).to(DEV)
+    grid = synth.query_points(1, 16384, seed=4)[0].to(DEV)
+    z = net.sample(cond=cube, batch_seeds=None, cond_type="radar")
+    lg = ae.decode(z, grid[None].expand(2, -1, -1).contiguous()).squeeze(-1)
+    thr = float(torch.quantile(lg, 0.9, dim=1).min())
+    gt = synth.query_points(2, 3000, seed=8).to(DEV)
+    out = evaluate.generate_point_clouds(net, ae, cube, 16384, rng, threshold=thr, ground_truth=gt, grid=grid)
+    assert torch.equal(out["latents"], z)
+    pts, cnt, _ = postproc.occupied_points(lg, grid[None].expand(2, -1, -1).contiguous(), thr, rng, view_cone=True)
+    assert torch.equal(out["counts"], cnt) and int(cnt.min()) > 0
+    n = int(cnt.max())
+    assert torch.equal(out["points"][:, :n], pts[:, :n]) or all(
+        torch.equal(out["points"][b, :int(cnt[b])], pts[b, :int(cnt[b])]) for b in range(2))
+    for b in range(2):
+        pred = orc.occupancy_points(lg[b].cpu().numpy(), grid.cpu().numpy(), pc_range=rng, view_cone=True, threshold=thr)
+        ref_gt = orc.occupancy_points(np.ones(3000, np.float32), gt[b].cpu().numpy(), pc_range=rng, view_cone=True)
+        want_cd = orc.chamfer_distance(pred, ref_gt)
+        assert abs(float(out["cd"][b]) - want_cd) <= 2e-5 * want_cd
+    # with the refine pass: shapes / ranges / finite metric
+    out2 = evaluate.generate_point_clouds(net, ae, cube, 16384, rng, threshold=thr, ground_truth=gt, grid=grid,
+                                          refine=dict(aug_num=30000, voxel_size=[0.05, 0.25, 0.5], scale=10, seed=3))
+    assert out2["points"].shape[0] == 2 and torch.isfinite(out2["cd"]).all()
