@@ -63,14 +63,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Skv = p.Skv;
   uint8_t* sQ = smem;                       // [2][128 x 64]
   uint8_t* sK = sQ + 2 * ATT_QBYTES;        // [Skv x 64]
   uint8_t* sV = sK + Skv * ATT_D * 2;       // [Skv x 64]
-  float* s_stat = reinterpret_cast<float*>(sV + Skv * ATT_D * 2);  // [nbuf 2][half 2][m, l][128]
+  uint8_t* sO = sV + Skv * ATT_D * 2;       // [128 x 64] bf16 output staging tile (128-byte swizzled rows) for the TMA store
+  float* s_stat = reinterpret_cast<float*>(sO + ATT_QBYTES);  // [nbuf 2][half 2][m, l][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 2 * 2 * ATT_BM);
   uint64_t* k_full = bars + 0;
   uint64_t* k_empty = bars + 1;
@@ -91,6 +92,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     mbar_init(k_full, 1);
     mbar_init(k_empty, 1);
     mbar_init(v_full, 1);
@@ -322,6 +324,9 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float* st = s_stat + slot * (2 * 2 * ATT_BM);
         st[(g * 2 + 0) * ATT_BM + row_in_tile] = m_scaled;
         st[(g * 2 + 1) * ATT_BM + row_in_tile] = sum;
+        // (the thread that issues the output TMA stores first makes sure the previous tile's store has read the staging
+        // tile: everybody may overwrite it after the barrier)
+        if (threadIdx.x == 64) bulk_wait_group_read<0>();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const float m_other = st[((g ^ 1) * 2 + 0) * ATT_BM + row_in_tile];
         const float l_other = st[((g ^ 1) * 2 + 1) * ATT_BM + row_in_tile];
@@ -354,18 +359,25 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[slot]);  // slot free for the next S as soon as O is in registers
-        const int qrow = (qt0 + t) * ATT_BM + row_in_tile;
-        if (qrow < p.Sq) {
-          const int64_t row = static_cast<int64_t>(frame) * p.Sq + qrow;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldo + head * ATT_D + 32 * g);
+        // O tile -> swizzled staging -> ONE asynchronous TMA store per tile (direct global stores kept these warps, which
+        // also are the softmax warps of the next tile, busy for ~0.9 us per tile). Group g owns bytes [64 g, 64 g + 64)
+        // of every 128-byte row = 16-byte chunks 4 g .. 4 g + 3.
+        {
+          const uint32_t srow = smem_u32(sO) + (uint32_t)row_in_tile * 128u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float r[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               r[e] = __uint_as_float(o0[8 * j + e]) * a_mine + __uint_as_float(o1[8 * j + e]) * a_other;
-            dst[j] = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                                pack_bf16x2(r[6], r[7]));
+            st_shared_v4(srow + ((uint32_t)((4 * g + j) ^ (row_in_tile & 7)) << 4), pack_bf16x2(r[0], r[1]),
+                         pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (threadIdx.x == 64) {
+            tma_store_2d(&tmO, sO, head * ATT_D, frame * p.Sq + (qt0 + t) * ATT_BM);
+            bulk_commit_group();
           }
         }
         ATT_STAMP(5);
@@ -373,6 +385,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
 
+  if (threadIdx.x == 64) bulk_wait_group<0>();   // the staging tile must outlive the last store
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -394,7 +407,9 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
   RALD_REQUIRE(Skv >= 64 && Skv <= 512 && Skv % 64 == 0, "attn: Skv=%d must be a multiple of 64 in [64, 512]", Skv);
   RALD_REQUIRE(Sq % ATT_BM == 0, "attn: Sq=%d must be a multiple of 128", Sq);
   RALD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "attn: output not 16-byte aligned");
-  CUtensorMap tmQ, tmK, tmV;
+  RALD_REQUIRE((uint64_t)ldo * 2 % 16 == 0, "attn: output row pitch must be a multiple of 16 bytes");
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  RALD_TRY(make_tmap_out(&tmO, O, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldo, false, ATT_BM));
   const uint32_t kv_box = Skv / 2;  // one box per key half (<= 256 rows)
   RALD_TRY(make_tmap_2d_bf16(&tmQ, Q, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldq, ATT_BM));
   // (K / V may point at a key chunk inside each frame's rows: the last frame's chunk ends Skv rows after its start)
@@ -436,7 +451,7 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
   p.items_per_head = p.q_tiles / p.tq;
   p.num_items = frames * heads * p.items_per_head;
   p.dbg = g_attn_dbg;
-  const int smem_bytes = 2 * ATT_QBYTES + 2 * Skv * ATT_D * 2 + 2 * 2 * 2 * ATT_BM * 4 + 1024 + 256;
+  const int smem_bytes = 3 * ATT_QBYTES + 2 * Skv * ATT_D * 2 + 2 * 2 * 2 * ATT_BM * 4 + 1024 + 256;
   static int configured_bytes = 0;
   if (smem_bytes > configured_bytes) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -444,7 +459,7 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
   }
   const int grid = p.num_items < sms ? p.num_items : sms;
   ProfScope prof(FAM_ATTN, stream, 4.0 * frames * heads * Sq * Skv * ATT_D);
-  RALD_CHECK_CUDA(launch_pdl(attn_d64_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, tmQ, tmK, tmV, p));
+  RALD_CHECK_CUDA(launch_pdl(attn_d64_kernel, dim3(grid), dim3(ATT_THREADS), smem_bytes, stream, tmQ, tmK, tmV, tmO, p));
   RALD_LAUNCHED();
   return 0;
 }
