@@ -38,7 +38,9 @@ struct AttnParams {
   int items_per_head;  // q_tiles / tq
   int num_items;
   float scale_log2;    // scale * log2(e)
-  int half;            // keys per half = Skv / 2
+  int half;            // keys per part = Skv / parts
+  int parts;           // 2: the two softmax groups each take one key half. 4 (Skv = 512): key quarters, two passes —
+                       // the P V products of the first two quarters run while the groups are in their second pass
   uint32_t o_col;      // O accumulator column inside a half region
   uint32_t region;     // TMEM columns per half region
   int nbuf;            // query tiles in flight in TMEM (1 or 2); a tile uses 2 * region columns
@@ -166,14 +168,13 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&o_empty[slot], (use & 1) ^ 1);  // previous occupant of the slot fully drained
         tc_fence_after();
         const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qslot * ATT_QBYTES), 16, 1024);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t t_s = tmem_base + (slot * 2 + h) * p.region;
+        for (int h = 0; h < p.parts; ++h) {
+          const uint32_t t_s = tmem_base + (slot * p.parts + h) * p.region;
           const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + h * p.half * ATT_D * 2), 16, 1024);
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k) mma_f16_ss(t_s, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-          if (h == 1) tc_commit(&q_empty[qslot]);  // Q tile consumed once these MMAs retire
-          tc_commit(&s_full[slot * 2 + h]);
+          if (h == p.parts - 1) tc_commit(&q_empty[qslot]);  // Q tile consumed once these MMAs retire
+          tc_commit(&s_full[slot * p.parts + h]);
         }
         if (last_of_item) tc_commit(k_empty);  // K may be replaced once the last S product of the item has retired
       };
@@ -181,18 +182,17 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int slot = p.nbuf == 2 ? (n & 1) : 0;
         const uint32_t use = p.nbuf == 2 ? (uint32_t)(n >> 1) : (uint32_t)n;
         if (first_of_item) mbar_wait(v_full, kv_ph);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&p_full[slot * 2 + h], use & 1);
+        for (int h = 0; h < p.parts; ++h) {
+          mbar_wait(&p_full[slot * p.parts + h], use & 1);
           tc_fence_after();
-          const uint32_t t_s = tmem_base + (slot * 2 + h) * p.region;
+          const uint32_t t_s = tmem_base + (slot * p.parts + h) * p.region;
           // V is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom.
           const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + h * p.half * ATT_D * 2), 1024, 1024);
           for (int k = 0; k < p.half / 16; ++k) {
             // 16 keys per MMA = 8 TMEM columns of P and 2048 B (= 128 in >>4 units) of V
             mma_f16_ts(t_s + p.o_col, t_s + 8 * k, v_desc + 128 * k, idesc_o, k != 0);
           }
-          tc_commit(&o_full[slot * 2 + h]);
+          tc_commit(&o_full[slot * p.parts + h]);
         }
         if (last_of_item) tc_commit(v_empty);  // V may be replaced once every MMA of the item has retired
       };
@@ -231,11 +231,17 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int t = 0; t < p.tq; ++t, ++qn) {
         const int slot = p.nbuf == 2 ? (qn & 1) : 0;
         const uint32_t use = p.nbuf == 2 ? (uint32_t)(qn >> 1) : (uint32_t)qn;
-        const uint32_t t_mine = tmem_base + (slot * 2 + g) * p.region + lane_off;
+        const int passes = p.parts >> 1;
+        float m_part[2], l_part[2];
         ATT_STAMP(0);
-        mbar_wait(&s_full[slot * 2 + g], use & 1);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+        if (pass >= passes) break;
+        const int part = 2 * pass + g;
+        const uint32_t t_mine = tmem_base + (slot * p.parts + part) * p.region + lane_off;
+        mbar_wait(&s_full[slot * p.parts + part], use & 1);
         tc_fence_after();
-        ATT_STAMP(1);
+        if (pass == 0) ATT_STAMP(1);
         // ---- ONE sweep over this half of S (TMEM -> registers is the scarce resource: 64 B/clk per SM) ----
         // The shift m of exp2(s*c - m) starts as the exact max of the first 32 columns and is only raised when a later
         // chunk exceeds it by more than 2^8 (lazy rescale): then the already written P columns and the running sum are
@@ -317,24 +323,39 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[slot * 2 + g]);
+        if (lane == 0) mbar_arrive(&p_full[slot * p.parts + part]);
+        m_part[pass] = m_scaled;
+        l_part[pass] = sum;
+        }  // pass
         ATT_STAMP(2);
 
-        // ---- exchange (max, sum) with the other key half ----
-        float* st = s_stat + slot * (2 * 2 * ATT_BM);
-        st[(g * 2 + 0) * ATT_BM + row_in_tile] = m_scaled;
-        st[(g * 2 + 1) * ATT_BM + row_in_tile] = sum;
+        // ---- exchange (max, sum) of every key part ----
+        float* st = s_stat + slot * (2 * 2 * ATT_BM);   // [part][m, l][128]; parts = 4 only occurs with one slot
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass < passes) {
+            st[((2 * pass + g) * 2 + 0) * ATT_BM + row_in_tile] = m_part[pass];
+            st[((2 * pass + g) * 2 + 1) * ATT_BM + row_in_tile] = l_part[pass];
+          }
+        }
         // (the thread that issues the output TMA stores first makes sure the previous tile's store has read the staging
         // tile: everybody may overwrite it after the barrier)
         if (threadIdx.x == 64) bulk_wait_group_read<0>();
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float m_other = st[((g ^ 1) * 2 + 0) * ATT_BM + row_in_tile];
-        const float l_other = st[((g ^ 1) * 2 + 1) * ATT_BM + row_in_tile];
-        const float m_all = fmaxf(m_scaled, m_other);
-        const float w_mine = ex2_approx(m_scaled - m_all), w_other = ex2_approx(m_other - m_all);
-        const float l_all = w_mine * sum + w_other * l_other;
+        float m_all = -INFINITY;
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt)
+          if (pt < p.parts) m_all = fmaxf(m_all, st[(pt * 2 + 0) * ATT_BM + row_in_tile]);
+        float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+        float l_all = 0.f;
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) {
+          if (pt < p.parts) {
+            wgt[pt] = ex2_approx(st[(pt * 2 + 0) * ATT_BM + row_in_tile] - m_all);
+            l_all = fmaf(wgt[pt], st[(pt * 2 + 1) * ATT_BM + row_in_tile], l_all);
+          }
+        }
         const float inv = 1.0f / l_all;
-        const float a_mine = w_mine * inv, a_other = w_other * inv;
         if (p.stats != nullptr && g == 0) {
           const int qrow_s = (qt0 + t) * ATT_BM + row_in_tile;
           if (qrow_s < p.Sq) {
@@ -344,18 +365,24 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
 
-        // ---- O = a_0 O_0 + a_1 O_1 : this group normalises and stores output columns [32 g, 32 g + 32) ----
-        const uint32_t t_o_mine = t_mine + p.o_col + 32 * g;
-        const uint32_t t_o_other = tmem_base + (slot * 2 + (g ^ 1)) * p.region + lane_off + p.o_col + 32 * g;
+        // ---- O = sum_part a_part O_part : this group normalises and stores output columns [32 g, 32 g + 32) ----
         ATT_STAMP(3);
-        mbar_wait(&o_full[slot * 2 + 0], use & 1);
-        mbar_wait(&o_full[slot * 2 + 1], use & 1);
-        tc_fence_after();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int pt = 0; pt < 4; ++pt) {
+          if (pt >= p.parts) break;
+          mbar_wait(&o_full[slot * p.parts + pt], use & 1);
+          tc_fence_after();
+          uint32_t ov[32];
+          tmem_ld32(tmem_base + (slot * p.parts + pt) * p.region + lane_off + p.o_col + 32 * g, ov);
+          tmem_ld_wait();
+          const float a = wgt[pt] * inv;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, __uint_as_float(ov[j]), acc[j]);
+        }
         ATT_STAMP(4);
-        uint32_t o0[32], o1[32];
-        tmem_ld32(t_o_mine, o0);
-        tmem_ld32(t_o_other, o1);
-        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[slot]);  // slot free for the next S as soon as O is in registers
@@ -366,10 +393,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t srow = smem_u32(sO) + (uint32_t)row_in_tile * 128u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float r[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              r[e] = __uint_as_float(o0[8 * j + e]) * a_mine + __uint_as_float(o1[8 * j + e]) * a_other;
+            const float* r = acc + 8 * j;
             st_shared_v4(srow + ((uint32_t)((4 * g + j) ^ (row_in_tile & 7)) << 4), pack_bf16x2(r[0], r[1]),
                          pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
           }
@@ -410,7 +434,8 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
   RALD_REQUIRE((uint64_t)ldo * 2 % 16 == 0, "attn: output row pitch must be a multiple of 16 bytes");
   CUtensorMap tmQ, tmK, tmV, tmO;
   RALD_TRY(make_tmap_out(&tmO, O, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldo, false, ATT_BM));
-  const uint32_t kv_box = Skv / 2;  // one box per key half (<= 256 rows)
+  const int parts = Skv == 512 ? 4 : 2;
+  const uint32_t kv_box = Skv / parts;  // one box per key part (<= 256 rows)
   RALD_TRY(make_tmap_2d_bf16(&tmQ, Q, (uint64_t)frames * Sq, (uint64_t)heads * ATT_D, (uint64_t)ldq, ATT_BM));
   // (K / V may point at a key chunk inside each frame's rows: the last frame's chunk ends Skv rows after its start)
   const uint64_t kv_rows = (uint64_t)(frames - 1) * kv_frame_rows + Skv;
@@ -426,15 +451,16 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
   p.scale_log2 = scale * 1.4426950408889634f;
   p.kv_frame_rows = kv_frame_rows;
   p.stats = stats;
-  p.half = Skv / 2;
-  // half region: S occupies [0, half), P (bf16 pairs) [0, half/2), O (64 fp32 columns) right after P
+  p.parts = parts;
+  p.half = Skv / parts;
+  // part region: S occupies [0, half), P (fp16 pairs) [0, half/2), O (64 fp32 columns) right after P
   p.o_col = p.half / 2 < 32 ? 32u : (uint32_t)(p.half / 2);
   uint32_t need = p.o_col + ATT_D;
   if (need < (uint32_t)p.half) need = p.half;
   uint32_t region = 32;
   while (region < need) region <<= 1;
   p.region = region;
-  p.nbuf = 4 * region <= 512 ? 2 : 1;
+  p.nbuf = 2 * parts * region <= 512 ? 2 : 1;
   p.q_tiles = Sq / ATT_BM;
   // query tiles per work item: rounds x (K/V load + tq tiles), in units of one tile
   const int sms = device_sm_count();
