@@ -147,7 +147,7 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
     // of the same 16 output features (reference: x, gate = proj(x).chunk(2); x * gelu(gate)).
     float o[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_erf(__uint_as_float(v[16 + j]));
+    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_act(__uint_as_float(v[16 + j]));
     if (row_ok) {
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col0 >> 1));
 #pragma unroll
@@ -442,9 +442,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float a0 = (__uint_as_float(v[2 * j]) + bs[2 * j]) *
-                                 gelu_erf(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
+                                 gelu_act(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
                 const float a1 = (__uint_as_float(v[2 * j + 1]) + bs[2 * j + 1]) *
-                                 gelu_erf(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
+                                 gelu_act(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
                 o[8 * h + j] = pack_bf16x2(a0, a1);
               }
             }
