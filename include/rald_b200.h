@@ -56,7 +56,9 @@ int64_t rald_prof_dump(int family, float* ms, double* work, int64_t cap);
 /* out = epilogue(A[M,K] @ W[N,K]^T), A and W bf16, fp32 accumulation on tcgen05 tensor cores.
  *   out_mode 0: out bf16 [M,N] (+bias) (+resid f32, added before rounding)
  *   out_mode 1: out f32  [M,N] = acc (+bias) (+resid f32 [M,ldr]); out may alias resid
- *   out_mode 2: GEGLU, out bf16 [M,N/2]; W rows / bias packed in groups of 32 = 16 value + 16 gate rows
+ *   out_mode 2: GEGLU, out bf16 [M,N/2] = value * gelu(gate); W rows / bias packed in groups of 32 = 16 value + 16
+ *               gate rows. gelu is the erf GELU of F.gelu evaluated in logistic form x * sigmoid(x * P(x^2)) with
+ *               |error| <= 2.5e-5 (build with -DRALD_GELU_LOGISTIC=0 for the A&S 7.1.26 erf polynomial, 1.5e-7)
  * Replaces nn.Linear (+ residual add / GEGLU) at model/models_radar_generation.py:58-64, 76, 91-95, 113,
  * 166-168 and model/models_ae.py:60-62, 87-89, 105. bn_hint: 0 = auto, else 32/64/128/256 (tile N). */
 int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
