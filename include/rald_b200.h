@@ -434,6 +434,25 @@ int rald_radar_cube_prep(const float* raw, int B, int R, int A, int E, int C, in
                          int norm_intensity, float max_intensity, int norm_dopp, float max_dopp, float* out,
                          void* stream);
 
+/* ---- training-loop helpers that need no autograd ---- */
+
+/* update_ema (engine_generation.py:29-39) over a whole parameter list in ONE launch:
+ *   target[i] = fma(source[i], one_minus_rate, rn(target[i] * rate))   -- ATen's mul_(rate).add_(src, alpha=1-rate)
+ * table_dev: device int64 [4 * n_tensors + 1] = { target pointers [n] | source pointers [n] | element counts [n] |
+ * first chunk of each tensor [n + 1] (exclusive prefix sum of ceil(count / rald_ema_chunk_elems()), last entry =
+ * total_chunks) }. All tensors fp32, contiguous; target and source of a pair must not overlap. total_elems is used
+ * for launch accounting only (12 B of HBM traffic per element). */
+int rald_ema_update(const int64_t* table_dev, int n_tensors, int64_t total_chunks, int64_t total_elems, float rate,
+                    float one_minus_rate, void* stream);
+int rald_ema_chunk_elems(void);
+
+/* Occupancy accuracy / IoU of the AE evaluation loops (engine_generation.py:376-385 in cache_latents; engine_ae.py's
+ * evaluate has the same lines): pred = logits >= threshold. logits, labels f32 [B, Q] (labels 0 / 1);
+ * out f32 [B, 2] = { mean(pred == labels), sum(pred * labels) / count(pred + labels > 0) + 1e-5 } per frame (the
+ * reference then averages over the batch); ws: int32 [3 * B] scratch. */
+int rald_occupancy_iou(const float* logits, const float* labels, int B, int64_t Q, float threshold, float* out,
+                       int32_t* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -481,6 +481,34 @@ def process_radar_data(raw: np.ndarray, norm_intensity: bool, max_intensity: flo
     return res
 
 
+# ----------------------------------------------------------------------------------------------
+# training / AE-evaluation loop helpers
+# ----------------------------------------------------------------------------------------------
+def update_ema(target_params, source_params, rate: float = 0.99) -> None:
+    """engine_generation.py:29-39, in numpy with the fp32 roundings spelled out: t1 = rn32(targ * rn32(rate));
+    targ = rn32(t1 + src * rn32(1 - rate)) with the product unrounded (ATen contracts ``a + alpha * b`` into one fma —
+    the fp64 product of two fp32 values is exact, so one fp64 add followed by the fp32 rounding is that fma up to
+    double rounding). In place on numpy arrays or torch CPU tensors."""
+    r32, a32 = np.float32(rate), np.float32(1 - rate)
+    for targ, src in zip(target_params, source_params):
+        t = targ.detach().numpy() if isinstance(targ, torch.Tensor) else targ
+        s = src.detach().numpy() if isinstance(src, torch.Tensor) else src
+        t1 = (t * r32).astype(np.float32)
+        t[...] = (t1.astype(np.float64) + s.astype(np.float64) * np.float64(a32)).astype(np.float32)
+
+
+def occupancy_iou(logits: torch.Tensor, labels: torch.Tensor, threshold: float = 0.0):
+    """engine_generation.py:376-385 (cache_latents; engine_ae.py's evaluate has the same lines), per frame (the
+    reference takes the batch mean of each): logits, labels [B, Q] -> (accuracy [B], iou [B])."""
+    pred = torch.zeros_like(logits)
+    pred[logits >= threshold] = 1
+    accuracy = (pred == labels).float().sum(dim=1) / labels.shape[1]
+    intersection = (pred * labels).sum(dim=1)
+    union = (pred + labels).gt(0).sum(dim=1)
+    iou = intersection * 1.0 / union + 1e-5
+    return accuracy, iou
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()

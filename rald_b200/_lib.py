@@ -79,6 +79,9 @@ _SIGNATURES = {
     "rald_chamfer_ws_elems": [c_int, c_i64, c_i64],
     "rald_radar_cube_prep": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int,
                              c_f32, c_void_p, c_void_p],
+    "rald_ema_update": [c_void_p, c_int, c_i64, c_i64, c_f32, c_f32, c_void_p],
+    "rald_ema_chunk_elems": [],
+    "rald_occupancy_iou": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
              "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64, "rald_chamfer_ws_elems": c_i64}

@@ -176,3 +176,24 @@ def refine_pass(vae, latents: torch.Tensor, points: torch.Tensor, counts: torch.
                                   norm_anisotropy=norm_anisotropy, norm_isotropy=norm_isotropy, view_cone=view_cone,
                                   capacity=capacity)
     return pts, cnt, queries
+
+
+@torch.no_grad()
+def occupancy_iou(logits: torch.Tensor, labels: torch.Tensor, threshold: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Accuracy and IoU of decoded occupancy against 0 / 1 labels, per frame (engine_generation.py:376-385 in
+    ``cache_latents``; engine_ae.py's ``evaluate`` has the same lines): logits, labels [B, Q] on the device ->
+    (accuracy [B], iou [B]) fp32 with ``pred = logits >= threshold``; the reference logs their batch means."""
+    if logits.device.type != "cuda":
+        raise _lib.RaldError("rald_b200 runs on CUDA devices only (no CPU fallback)")
+    if logits.dim() == 3:
+        logits = logits.squeeze(-1)
+    if labels.shape != logits.shape:
+        raise _lib.RaldError(f"occupancy_iou: logits {tuple(logits.shape)} vs labels {tuple(labels.shape)}")
+    B, Q = logits.shape
+    logits = logits.contiguous().float()
+    labels = labels.to(logits.device).contiguous().float()
+    out = torch.empty(B, 2, device=logits.device, dtype=torch.float32)
+    ws = torch.empty(3 * B, device=logits.device, dtype=torch.int32)
+    _lib.call("rald_occupancy_iou", logits.data_ptr(), labels.data_ptr(), B, Q, float(threshold), out.data_ptr(),
+              ws.data_ptr(), _lib.cur_stream())
+    return out[:, 0], out[:, 1]
