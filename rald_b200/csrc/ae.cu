@@ -124,6 +124,7 @@ extern "C" int rald_ae_stack(const rald_ae_weights* w, const rald_dit_workspace*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dim = w->dim, M = w->n_latents, heads = w->heads;
   const float scale = 1.0f / sqrtf((float)(dim / heads));
+  GemmStaticWeights static_w;  // every GEMM below multiplies activations with packed model weights
   for (int f0 = 0; f0 < frames; f0 += ws->max_frames) {
     const int nf = (frames - f0) < ws->max_frames ? (frames - f0) : ws->max_frames;
     const int64_t T = (int64_t)nf * M;

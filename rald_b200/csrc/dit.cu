@@ -22,6 +22,7 @@ namespace rald {
 static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, const float* mod,
                       int64_t mod_frame_stride, const void* ctxkv, int frames, int frame0, cudaStream_t st) {
   const int dim = w.dim, depth = w.depth, M = w.n_latents, L = w.ctx_len, heads = w.heads;
+  GemmStaticWeights static_w;  // every GEMM below multiplies activations with packed model weights
   const int64_t T = (int64_t)frames * M;
   const float scale = 1.0f / sqrtf((float)(dim / heads));
   const int64_t ld_ctx = (int64_t)depth * 2 * dim;

@@ -85,6 +85,9 @@ struct GemmParams {
   const uint8_t* pf_ptr;      // weights of the NEXT GEMM in the stream, prefetched into L2 by this kernel's idle
   uint32_t pf_bytes;          // epilogue threads (small-batch regime: hides the DRAM latency of the next launch)
   int f16_start, f16_period;  // bf16 mode: output columns with (col % f16_period) >= f16_start are written as fp16
+  int w_static;               // W does not depend on the preceding kernel: its first ring stages are loaded BEFORE the
+                              // programmatic-dependency wait (hides the DRAM latency of the weights behind the
+                              // predecessor's tail in the latency-bound small-batch regime); CG = 1, !ARES only
   int skip_epilogue;          // DEBUG (RALD_B200_GEMM_SKIP_EPI=1): accumulators are released unread, nothing is stored —
                               // isolates the TMA + MMA main loop for timing (tools/gemm_phases_big.py); results are garbage
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
@@ -93,6 +96,7 @@ struct GemmParams {
 static unsigned long long* g_gemm_dbg = nullptr;
 static thread_local const void* g_pf_ptr = nullptr;   // consumed by the next GEMM launch of this thread
 static thread_local size_t g_pf_bytes = 0;
+static thread_local int g_w_static = 0;               // GemmStaticWeights scopes alive on this thread
 #define GEMM_STAMP(slot)                                                        \
   do {                                                                          \
     if (p.dbg != nullptr) p.dbg[blockIdx.x * 8 + (slot)] = global_timer_ns();   \
@@ -229,6 +233,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int w_pre = 0;            // ring stages whose W tile is already in flight (producer thread only)
+  if (CG == 1 && !ARES && p.w_static != 0 && threadIdx.x == 0) {
+    // static weights: the W tiles of this CTA's first STAGES k-blocks do not depend on the preceding kernel
+    int tile = t_begin, kb = 0;
+    while (w_pre < STAGES && tile < t_end) {
+      const int n_blk = tile % p.num_n_blks;
+      mbar_arrive_expect_tx(&full_bar[w_pre], Cfg::STAGE_BYTES);
+      tma_load_2d(smem + w_pre * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[w_pre], kb * GEMM_BK, n_blk * BN);
+      ++w_pre;
+      if (++kb == num_kb) { kb = 0; tile += t_step; }
+    }
+  }
   pdl_wait();               // A (and an in-place residual) come from the preceding kernel
   pdl_launch_dependents();  // the next kernel may set itself up on idle SMs while this one runs
 
@@ -268,6 +284,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
             if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * GEMM_BM);
             tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+          } else if (w_pre > 0) {
+            // transaction bytes announced and W tile issued before the dependency wait: only A is left
+            --w_pre;
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
@@ -537,6 +557,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return 0;
 }
 
+GemmStaticWeights::GemmStaticWeights() { ++g_w_static; }
+GemmStaticWeights::~GemmStaticWeights() { --g_w_static; }
+
 void gemm_prefetch_next(const void* weights, size_t bytes) {
   g_pf_ptr = weights;
   g_pf_bytes = bytes;
@@ -637,6 +660,11 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   {
     const char* e = getenv("RALD_B200_GEMM_SKIP_EPI");
     p.skip_epilogue = e != nullptr ? (e[0] - '0') : 0;   // 1: no epilogue at all; 2: TMEM reads + arithmetic, no stores
+  }
+  {
+    // RALD_B200_GEMM_WPRE=0 disables the early weight loads
+    static const bool wpre_env = [] { const char* e = getenv("RALD_B200_GEMM_WPRE"); return e == nullptr || e[0] != '0'; }();
+    p.w_static = (wpre_env && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
   }
   p.pf_ptr = static_cast<const uint8_t*>(g_pf_ptr);
   p.pf_bytes = (uint32_t)(g_pf_bytes > 0xfffffff0ull ? 0 : g_pf_bytes);

@@ -28,6 +28,14 @@ int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, vo
 // Hint for the NEXT gemm launch issued by this thread: while it runs, its idle epilogue threads prefetch `bytes` of
 // `weights` (the operand of the GEMM after it) into L2. Used by the small-batch denoiser loop.
 void gemm_prefetch_next(const void* weights, size_t bytes);
+// While alive on this thread, every GEMM launched treats its W operand as STATIC (model weights: not written by any
+// kernel in flight), which lets the kernel start streaming W before its programmatic-dependency wait.
+struct GemmStaticWeights {
+  GemmStaticWeights();
+  ~GemmStaticWeights();
+  GemmStaticWeights(const GemmStaticWeights&) = delete;
+  GemmStaticWeights& operator=(const GemmStaticWeights&) = delete;
+};
 
 // attn.cu ------------------------------------------------------------------------------------------
 // O[f, :, h*64:(h+1)*64] = softmax(Q K^T * scale) V per (frame f, head h); head_dim 64; Skv <= 512.
