@@ -9,7 +9,8 @@ import os
 from pathlib import Path
 
 _LIB = None
-LIB_PATH = Path(__file__).resolve().parent / "_C" / "librald_b200.so"
+# RALD_B200_LIB: an alternative build of the same sources (kernel-variant experiments)
+LIB_PATH = Path(os.environ.get("RALD_B200_LIB") or Path(__file__).resolve().parent / "_C" / "librald_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

@@ -26,7 +26,14 @@ namespace rald {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+// RALD_GEMM_PRODUCERS = 2: a second TMA producer warp (warp 10) issues the W tiles while warp 0 issues the A tiles.
+// One thread issues a cp.async.bulk.tensor every ~125 ns (measured: "ring-issued" stamp of tools/gemm_phases.py — the
+// 16 loads of a K = 512 tile take 2.0 us to ISSUE, whatever the box sizes, tile shape, CTA count or ring depth), which
+// is what paces the main loop of the latency-bound batch-1 GEMMs (0.25 us per k-block).
+#ifndef RALD_GEMM_PRODUCERS
+#define RALD_GEMM_PRODUCERS 1
+#endif
+constexpr int GEMM_THREADS = 320 + 32 * (RALD_GEMM_PRODUCERS - 1);  // TMA warp, MMA warp, 8 epilogue warps (, W producer)
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
@@ -56,9 +63,13 @@ constexpr bool GEMM_WIDE_STORE = RALD_GEMM_WIDE_STORE != 0;
 // 2.35 us, FF2 18.5 against 9.4). Off by default; RALD_B200_GEMM_ARES=1 enables it for N >= 1024, =2 for all N.
 constexpr int ARES_K = 512;
 constexpr int ARES_BYTES = GEMM_BM * ARES_K * 2;
-template <int BN, int CG = 1, bool ARES = false>
+// BM = 64 (CG = 1, generic epilogue only): half-height tiles for the latency-bound batch-1 regime (twice the CTAs,
+// 40 % fewer operand bytes per CTA). The K order is unchanged: results are bit-identical to the 128-row tiles
+// (tools/gpu_check_bm64.py). Measured not faster, off by default — see the selection in gemm_impl. Accumulator layout of an M = 64 MMA: row 16 j + i -> TMEM lane 32 j + i (the lower half of every
+// lane quarter), so epilogue warp q owns rows [16 q, 16 q + 16) and its lanes 16..31 read nothing useful.
+template <int BN, int CG = 1, bool ARES = false, int BM = GEMM_BM>
 struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int A_BYTES = BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
   static constexpr int A_RES_BYTES = ARES ? ARES_BYTES : 0;
@@ -66,9 +77,13 @@ struct GemmCfg {
   static constexpr int STG_TOTAL = GEMM_EPI_WARPS * NBUF * STG_BYTES;
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   // no alignment slack: dynamic shared memory starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int FIXED = 256 /*barriers*/ + STG_TOTAL + BIAS_BYTES + A_RES_BYTES;
+  static constexpr int FIXED = 512 /*barriers*/ + STG_TOTAL + BIAS_BYTES + A_RES_BYTES;
   static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+#ifndef RALD_GEMM_MAX_STAGES
+#define RALD_GEMM_MAX_STAGES 8
+#endif
+  static constexpr int STAGES = STAGES_RAW > RALD_GEMM_MAX_STAGES ? RALD_GEMM_MAX_STAGES : STAGES_RAW;
+  static_assert(2 * STAGES + 7 <= 64, "barrier block too small");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
 };
@@ -164,15 +179,16 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 }
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE, int EPI, int CG, bool ARES>
+template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, ARES>;
+  using Cfg = GemmCfg<BN, CG, ARES, BM>;
+  static_assert(BM == 128 || (BM == 64 && CG == 1 && !ARES && EPI == EPI_GENERIC), "64-row tiles: CG = 1, generic epilogue");
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-processing unit (CTA or CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int TILE_M = GEMM_BM * CG;
+  constexpr int TILE_M = BM * CG;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBUF = Cfg::NBUF;
   // accumulator columns consumed per staged 128-byte output row
@@ -233,8 +249,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr bool SPLIT = RALD_GEMM_PRODUCERS == 2 && !ARES;   // W tiles come from warp 10
   int w_pre = 0;            // ring stages whose W tile is already in flight (producer thread only)
-  if (CG == 1 && !ARES && p.w_static != 0 && threadIdx.x == 0) {
+  if (!SPLIT && CG == 1 && !ARES && p.w_static != 0 && threadIdx.x == 0) {
     // static weights: the W tiles of this CTA's first STAGES k-blocks do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
     while (w_pre < STAGES && tile < t_end) {
@@ -245,7 +262,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++kb == num_kb) { kb = 0; tile += t_step; }
     }
   }
-  pdl_wait();               // A (and an in-place residual) come from the preceding kernel
+  // A (and an in-place residual) come from the preceding kernel; static weights do not, so a dedicated W producer
+  // starts streaming them right away
+  if (!(SPLIT && warp == 10 && p.w_static != 0)) pdl_wait();
   pdl_launch_dependents();  // the next kernel may set itself up on idle SMs while this one runs
 
   if (warp == 0) {
@@ -267,11 +286,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (cta_rank == 0) mbar_arrive_expect_tx(a_full_bar, 2 * ARES_BYTES);
             for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
               tma_load_2d_pair(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK,
-                               m_blk * TILE_M + (int)cta_rank * GEMM_BM);
+                               m_blk * TILE_M + (int)cta_rank * BM);
           } else {
             mbar_arrive_expect_tx(a_full_bar, ARES_BYTES);
             for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
-              tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK, m_blk * GEMM_BM);
+              tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK, m_blk * BM);
           }
         }
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -282,17 +301,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
             // to the LEADER's full barrier, on which only the leader arrives
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-            if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * GEMM_BM);
-            tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+            if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * BM);
+            if (!SPLIT) tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
           } else if (w_pre > 0) {
             // transaction bytes announced and W tile issued before the dependency wait: only A is left
             --w_pre;
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * BM);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * GEMM_BM);
-            tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+            if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * BM);
+            if (!SPLIT) tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           }
+          if (++s == STAGES) {
+            s = 0;
+            if (ph == 0) GEMM_STAMP(7);   // first pass over the ring issued (tools/gemm_phases.py: "ring-issued")
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (SPLIT && warp == 10) {
+    // ===================== second TMA producer: W tiles =====================
+    // (their transaction bytes are announced by warp 0's arrive.expect_tx on the same barrier; a complete_tx that
+    // lands first only makes the pending count transiently negative, the phase cannot flip before that arrive)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        const int n_blk = tile % p.num_n_blks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sb = smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+          if (CG == 2) tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+          else tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -351,13 +392,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (it == 0) GEMM_STAMP(3);
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue (warps 2..9) =====================
     // Two warps per TMEM lane quarter: warp pair member `hs` takes the even / odd column chunks of the tile.
     const int q = warp & 3;          // TMEM lane quarter this warp is allowed to touch
     const int ew = warp - 2;         // 0..7
     const int hs = ew >> 2;          // 0: even chunks, 1: odd chunks
-    const int row_in_tile = q * 32 + lane;
+    const int row_in_tile = BM == 64 ? q * 16 + lane : q * 32 + lane;
+    const bool lane_ok = BM == 128 || lane < 16;   // M = 64 accumulators live in the lower half of each lane quarter
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
     int sbuf = 0;
@@ -404,8 +446,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (EPI == EPI_GENERIC) {
-        const int64_t row = static_cast<int64_t>(m_blk) * TILE_M + cta_rank * GEMM_BM + row_in_tile;
-        const bool row_ok = row < p.M;
+        const int64_t row = static_cast<int64_t>(m_blk) * TILE_M + cta_rank * BM + row_in_tile;
+        const bool row_ok = lane_ok && row < p.M;
 #pragma unroll 1
         for (int c = hs; c < BN / 32; c += 2) {
           const int col0 = n_blk * BN + c * 32;
@@ -420,7 +462,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) release_acc();
       } else {
         constexpr int NCHUNK = BN / CHUNK;
-        const int row0 = m_blk * TILE_M + (int)cta_rank * GEMM_BM + q * 32;
+        const int row0 = m_blk * TILE_M + (int)cta_rank * BM + q * 32;
         if (NCHUNK == 1 && hs == 1) {
           // a single 128-byte output row per tile: the odd warps have no chunk, they only release the accumulator
           tc_fence_before();
@@ -495,7 +537,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             asm volatile("bar.sync %0, 128;" ::"r"(2 + hs) : "memory");
             if (q == 0 && lane == 0) {
               const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
-              const int orow = m_blk * TILE_M + (int)cta_rank * GEMM_BM;
+              const int orow = m_blk * TILE_M + (int)cta_rank * BM;
               if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, gstg, ocol, orow);
               else tma_store_2d(&tmO, gstg, ocol, orow);
               bulk_commit_group();
@@ -536,12 +578,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false>
+template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false, int BM = GEMM_BM>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, ARES>;
+  using Cfg = GemmCfg<BN, CG, ARES, BM>;
   static_assert(Cfg::STAGES >= 3, "ring too shallow");
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES, BM>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -632,6 +674,27 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     epi = EPI_TMA_STORE;
   }
 
+  // 64-row tiles (see GemmCfg): latency-bound small problems whose 64 x bn tiling still fits one wave. Same cost
+  // model with the per-CTA operand height halved.
+  bool bm64 = false;
+  {
+    // MEASURED on B200 at batch 1: parity bit-exact, but 58.2 vs 55.8 ms per frame — the batch-1 main loop takes
+    // ~0.25 us per k-block whatever the tile shape, CTA count (16..128), ring depth (8 / 16 stages) or number of
+    // producer threads, so halving the rows per CTA buys nothing and the direct-store epilogue costs 1.2 us more than
+    // the TMA one. Off by default; RALD_B200_GEMM_BM64=1 enables it.
+    static const bool bm64_env = [] { const char* e = getenv("RALD_B200_GEMM_BM64"); return e != nullptr && e[0] == '1'; }();
+    if (bm64_env && bn_hint == 0 && out_mode != 2 && f16_period == 0) {
+      const long m_blks64 = (M + 63) / 64;
+      long best = (((long)m_blks * (N / bn) + sms - 1) / sms) * (64 + bn);
+      for (int cand = 64; cand >= 32; cand >>= 1) {
+        if (N % cand != 0 || m_blks64 * (N / cand) > sms) continue;
+        const long cost = 32 + cand;
+        if (cost < best) { best = cost; bn = cand; bm64 = true; }
+      }
+      if (bm64) epi = EPI_GENERIC;
+    }
+  }
+
   // CTA pairs: 256 x 256 tiles when the problem still fills the machine with them (large-batch regime)
   static int pair_env = -1;
   if (pair_env < 0) {
@@ -652,7 +715,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.M = M;
   p.N = N;
   p.K = K;
-  p.num_m_blks = pair ? m_blks2 : m_blks;
+  p.num_m_blks = pair ? m_blks2 : (bm64 ? (M + 63) / 64 : m_blks);
   p.num_n_blks = (N + bn - 1) / bn;
   p.dbg = g_gemm_dbg;
   p.f16_start = f16_start;
@@ -673,7 +736,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;
-  RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM));
+  RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, bm64 ? 64u : (uint32_t)GEMM_BM));
   RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1,
@@ -698,6 +761,14 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2>(tmA, tmB, tmO, p, sms, stream);
     return launch_gemm<256, 1, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
+  }
+  if (bm64) {
+    if (out_mode == 1) {
+      if (bn == 32) return launch_gemm<32, 1, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
+      return launch_gemm<64, 1, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
+    }
+    if (bn == 32) return launch_gemm<32, 0, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
+    return launch_gemm<64, 0, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
   }
 #define RALD_GEMM_LAUNCH(BN_, MODE_, EPI_) return launch_gemm<BN_, MODE_, EPI_>(tmA, tmB, tmO, p, sms, stream)
 #define RALD_GEMM_BN(MODE_, EPI_)                   \

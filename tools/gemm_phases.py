@@ -34,11 +34,14 @@ def run(M, N, K, mode, bn, reps=20):
         dbg.zero_()
         call()
         torch.cuda.synchronize()
-        d = dbg.view(148, 8)[:, :7].cpu()
+        d8 = dbg.view(148, 8).cpu()
+        ring = d8[d8[:, 0] > 0]
+        ring_issued = (ring[:, 7] - ring[:, 0].min()).float().mean() if (ring[:, 7] > 0).all() else torch.tensor(float("nan"))
+        d = d8[:, :7]
         d = d[d[:, 0] > 0]
         t0 = d[:, 0].min()
         rel = (d - t0).float()
-        row = torch.cat([rel.mean(0), rel[:, 6].max()[None], torch.tensor([float(d.shape[0])])])
+        row = torch.cat([rel.mean(0), rel[:, 6].max()[None], torch.tensor([float(d.shape[0])]), ring_issued[None]])
         acc = row if acc is None else acc + row
     _lib.lib().rald_gemm_debug_buffer(0)
     acc /= reps
@@ -52,7 +55,7 @@ def run(M, N, K, mode, bn, reps=20):
     names = ["entry", "setup", "1st-ops", "mma-issued", "acc-ready", "epi-done", "exit"]
     print(f"M={M} N={N} K={K} mode={mode} bn={bn} ctas={int(acc[8])}: " +
           " ".join(f"{n}={acc[i] / 1000:.2f}" for i, n in enumerate(names)) +
-          f" | last-exit={acc[7] / 1000:.2f} us | warm back-to-back {warm:.2f} us")
+          f" | last-exit={acc[7] / 1000:.2f} us | ring-issued={acc[9] / 1000:.2f} | warm back-to-back {warm:.2f} us")
 
 
 if __name__ != "__main__":

@@ -1,5 +1,5 @@
 // Microbenchmark: issue rate of tcgen05.mma (kind::f16, bf16, M=128, SS operands resident in shared memory, no TMA,
-// no epilogue) for N in {64,128,256}, one or two accumulators. Prints cycles per MMA per SM.
+// no epilogue) for N in {32,64,128,256}, one or two accumulators. Prints cycles per MMA per SM.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I rald_b200/csrc tools/micro/mma_rate.cu -o tools/micro/_bin/mma_rate
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -66,6 +66,9 @@ int main() {
   run<128, 1, false>("SS N=128 1 acc", d);
   run<128, 2, false>("SS N=128 2 acc", d);
   run<64, 2, false>("SS N=64 2 acc", d);
+  run<64, 1, false>("SS N=64 1 acc", d);
+  run<32, 1, false>("SS N=32 1 acc", d);
+  run<32, 2, false>("SS N=32 2 acc", d);
   run<128, 1, true>("TS N=128 1 acc", d);
   run<128, 2, true>("TS N=128 2 acc", d);
   run<256, 1, true>("TS N=256 1 acc", d);
