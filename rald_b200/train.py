@@ -18,7 +18,7 @@ _MAX_TABLES = 8
 
 
 def _table(targets: List[torch.Tensor], sources: List[torch.Tensor]):
-    key = (tuple(t.data_ptr() for t in targets), tuple(s.data_ptr() for s in sources),
+    key = (targets[0].device.index, tuple(t.data_ptr() for t in targets), tuple(s.data_ptr() for s in sources),
            tuple(t.numel() for t in targets))
     hit = _TABLES.get(key)
     if hit is not None:
