@@ -61,3 +61,47 @@ def test_decode_cache_and_ragged_queries(ae):
     assert torch.equal(a, c)
     single = ae.decode(z[1:2].contiguous(), q[1:2].contiguous())
     assert torch.allclose(a[1], single[0], atol=1e-6, rtol=0)
+
+
+def test_dense_query_sweep_full_size_properties(ae):
+    """BASELINE configs[3] at its largest size (2^20 query points of one frame against the latent set): the oracle
+    cannot decode a million queries in seconds, so the full-size run is checked through properties of the path —
+    every query is decoded independently of its neighbours (row <-> TMEM lane), so any subset decoded alone and any
+    permutation of the set give bit-identical logits — and against the oracle on a 2048-query sample."""
+    from oracle import rald_oracle as orc
+    Q = 1 << 20
+    z = synth.posterior_noise(1, seed=5).cuda()
+    gen = torch.Generator().manual_seed(17)
+    q = (torch.rand(1, Q, 3, generator=gen) * 2 - 1).cuda()
+    full = ae.decode(z, q)[0, :, 0]
+    assert full.shape == (Q,) and bool(torch.isfinite(full).all())
+    # a contiguous slice that is not tile aligned, decoded alone
+    lo, n = 123457, 8191
+    part = ae.decode(z, q[:, lo:lo + n].contiguous())[0, :, 0]
+    assert torch.equal(part, full[lo:lo + n])
+    # a random permutation of the whole set
+    perm = torch.randperm(Q, generator=gen).cuda()
+    shuffled = ae.decode(z, q[:, perm].contiguous())[0, :, 0]
+    assert torch.equal(shuffled, full[perm])
+    # oracle on a sample (same bars as test_decode_logits)
+    idx = torch.randperm(Q, generator=gen)[:2048]
+    ref = orc.ae_decode(cpu_state_dict(ae), z.cpu(), q[:, idx.cuda()].cpu())[0, :, 0]
+    got = full[idx.cuda()].cpu()
+    offset = float((got - ref).mean())
+    resid = float(((got - ref) - offset).std())
+    print(f"2^20 queries: common-mode {offset:.3e}, spatial residual {resid / float(ref.std()):.2%} of the field")
+    assert abs(offset) < 2e-2 * abs(float(ref.mean())) + 1e-3
+    assert resid < 0.05 * float(ref.std())
+
+
+def test_batched_decode_equals_single_frames_at_sweep_size(ae):
+    """64 frames x 2^16 queries (micro-batched latent stack, one query launch): each frame's logits are those of the
+    frame decoded alone."""
+    B, Q = 64, 1 << 16
+    z = synth.posterior_noise(B, seed=9).cuda()
+    gen = torch.Generator().manual_seed(23)
+    q = (torch.rand(B, Q, 3, generator=gen) * 2 - 1).cuda()
+    full = ae.decode(z, q)
+    for f in (0, 31, 63):
+        single = ae.decode(z[f:f + 1].contiguous(), q[f:f + 1].contiguous())
+        assert torch.equal(full[f], single[0]), f
