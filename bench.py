@@ -192,7 +192,7 @@ def cpu_reference_sample(queries_total: int, sample_queries: int = 262144, sampl
             "s_per_frame": t_frame, "hoisted_value": 1.0 / t_frame_hoisted, "s_per_net_eval": t_eval}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world=1):
     if rank != 0:
         return
     t_all = time.perf_counter()
@@ -207,7 +207,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, world),
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
@@ -427,7 +427,7 @@ def main():
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
 
