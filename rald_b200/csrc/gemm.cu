@@ -179,12 +179,20 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 }
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM>
+template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM, int G>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG, ARES, BM>;
   static_assert(BM == 128 || (BM == 64 && CG == 1 && !ARES && EPI == EPI_GENERIC), "64-row tiles: CG = 1, generic epilogue");
+  // G k-blocks share one ring slot = ONE full / empty barrier pair: the MMA thread then probes an mbarrier once per
+  // 4 G MMAs instead of once per 4. Measured (tools/micro/mma_rate.cu): a try_wait on an ALREADY COMPLETE mbarrier
+  // between groups of 4 MMAs costs the issuing thread ~260 cycles (490 cycles per 64-wide k-block in all, whatever
+  // N) — more than the 180 cycles of tensor work of a k-block at N = 32 and barely less than the 512 at N = 256.
+  static_assert(G == 1 || !ARES, "grouped ring slots are not combined with the A-resident form");
+  static_assert(Cfg::STAGES % G == 0 || G == 1, "ring depth must be a multiple of the group");
+  constexpr int SLOTS = Cfg::STAGES / G;
+  constexpr int SLOT_BYTES = G * Cfg::STAGE_BYTES;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-processing unit (CTA or CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -252,14 +260,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool SPLIT = RALD_GEMM_PRODUCERS == 2 && !ARES;   // W tiles come from warp 10
   int w_pre = 0;            // ring stages whose W tile is already in flight (producer thread only)
   if (!SPLIT && CG == 1 && !ARES && p.w_static != 0 && threadIdx.x == 0) {
-    // static weights: the W tiles of this CTA's first STAGES k-blocks do not depend on the preceding kernel
+    // static weights: the W tiles of this CTA's first SLOTS ring slots do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
-    while (w_pre < STAGES && tile < t_end) {
+    while (w_pre < SLOTS && tile < t_end) {
       const int n_blk = tile % p.num_n_blks;
-      mbar_arrive_expect_tx(&full_bar[w_pre], Cfg::STAGE_BYTES);
-      tma_load_2d(smem + w_pre * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[w_pre], kb * GEMM_BK, n_blk * BN);
+      mbar_arrive_expect_tx(&full_bar[w_pre], SLOT_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        tma_load_2d(smem + w_pre * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[w_pre],
+                    (kb + g) * GEMM_BK, n_blk * BN);
       ++w_pre;
-      if (++kb == num_kb) { kb = 0; tile += t_step; }
+      kb += G;
+      if (kb == num_kb) { kb = 0; tile += t_step; }
     }
   }
   // A (and an in-place residual) come from the preceding kernel; static weights do not, so a dedicated W producer
@@ -293,26 +305,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK, m_blk * BM);
           }
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += G) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
+          uint8_t* slot = smem + s * SLOT_BYTES;
           if (CG == 2) {
             // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
             // to the LEADER's full barrier, on which only the leader arrives
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-            if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * TILE_M + (int)cta_rank * BM);
-            if (!SPLIT) tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * SLOT_BYTES);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
+              uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
+              if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * TILE_M + (int)cta_rank * BM);
+              if (!SPLIT) tma_load_2d_pair(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+            }
           } else if (w_pre > 0) {
-            // transaction bytes announced and W tile issued before the dependency wait: only A is left
+            // transaction bytes announced and W tiles issued before the dependency wait: only A is left
             --w_pre;
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * BM);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              tma_load_2d(slot + g * Cfg::STAGE_BYTES, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * BM);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m_blk * BM);
-            if (!SPLIT) tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
+            mbar_arrive_expect_tx(&full_bar[s], SLOT_BYTES);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
+              uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
+              if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * BM);
+              if (!SPLIT) tma_load_2d(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
+            }
           }
-          if (++s == STAGES) {
+          if (++s == SLOTS) {
             s = 0;
             if (ph == 0) GEMM_STAMP(7);   // first pass over the ring issued (tools/gemm_phases.py: "ring-issued")
             ph ^= 1;
@@ -329,12 +352,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       for (int tile = t_begin; tile < t_end; tile += t_step) {
         const int n_blk = tile % p.num_n_blks;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += G) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sb = smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-          if (CG == 2) tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
-          else tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n_blk * BN);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            uint8_t* sb = smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+            if (CG == 2) tma_load_2d_pair(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+            else tma_load_2d(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
+          }
+          if (++s == SLOTS) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -366,25 +392,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += G) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (it == 0 && kb == 0) GEMM_STAMP(2);
-          const uint32_t sst = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sa = ARES ? smem_u32(a_res) + (uint32_t)kb * Cfg::A_BYTES : sst;
-          const uint32_t sb = ARES ? sst : sst + Cfg::A_BYTES;
-          const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
-            if (CG == 2) mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < G; ++g) {
+            const uint32_t sst = smem_u32(smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES);
+            const uint32_t sa = ARES ? smem_u32(a_res) + (uint32_t)(kb + g) * Cfg::A_BYTES : sst;
+            const uint32_t sb = ARES ? sst : sst + Cfg::A_BYTES;
+            const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
+            const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
+              const uint32_t accum = ((kb + g) | k) != 0 ? 1u : 0u;
+              if (CG == 2) mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+              else mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+            }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          // frees this ring slot (in both CTAs of a pair) once the MMAs above have read it
           if (CG == 2) tc_commit_pair(&empty_bar[s]);
           else tc_commit(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == SLOTS) { s = 0; ph ^= 1; }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
         if (CG == 2) tc_commit_pair(&tmem_full_bar[acc]);
@@ -578,12 +608,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false, int BM = GEMM_BM>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM, int G>
+static int launch_gemm_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG, ARES, BM>;
   static_assert(Cfg::STAGES >= 3, "ring too shallow");
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES, BM>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES, BM, G>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -597,6 +627,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                                      tmA, tmB, tmO, p));
   RALD_LAUNCHED();
   return 0;
+}
+
+// Picks the ring-slot group (k-blocks per full / empty barrier pair, see the kernel): the largest the ring depth
+// allows when K is a multiple of it. RALD_B200_GEMM_GROUP=0 forces one k-block per slot.
+template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false, int BM = GEMM_BM>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+                       int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG, ARES, BM>;
+  constexpr int GMAX = (ARES || EPI == EPI_GENERIC) ? 1
+                       : (Cfg::STAGES >= 8 && Cfg::STAGES % 4 == 0) ? 4
+                       : (Cfg::STAGES >= 4 && Cfg::STAGES % 2 == 0) ? 2 : 1;
+  static const bool group_env = [] { const char* e = getenv("RALD_B200_GEMM_GROUP"); return e == nullptr || e[0] != '0'; }();
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  if (GMAX > 1 && group_env && num_kb % GMAX == 0)
+    return launch_gemm_g<BN, OUT_MODE, EPI, CG, ARES, BM, GMAX>(tmA, tmB, tmO, p, max_ctas, stream);
+  return launch_gemm_g<BN, OUT_MODE, EPI, CG, ARES, BM, 1>(tmA, tmB, tmO, p, max_ctas, stream);
 }
 
 GemmStaticWeights::GemmStaticWeights() { ++g_w_static; }
