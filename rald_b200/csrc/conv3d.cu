@@ -41,10 +41,18 @@ struct ConvCfg {
   static constexpr int A_BYTES = CV_BM * 64 * 2;
   static constexpr int B_BYTES = BN * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // CV_G k-blocks (tap x 64 input channels) share one ring slot = one full / empty barrier pair: an mbarrier probe
+  // between groups of 4 MMAs costs the issuing thread ~260 cycles (tools/micro/mma_rate.cu), more than the 192 cycles
+  // of tensor work of a k-block at N = 64 — with one probe per k-block the level-0 convolutions ran at ~500 cycles
+  // per k-block. 27 taps x Cin / 64 chunks is always a multiple of 3.
+  static constexpr int G = 3;
+  static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (STAGES_RAW > 9 ? 9 : STAGES_RAW) / G * G;
+  static constexpr int SLOTS = STAGES / G;
+  static constexpr int SLOT_BYTES = G * STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SLOTS >= 2, "ring too shallow");
 };
 
 template <int BN>
@@ -100,24 +108,27 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUt
         const int td = mt % p.tiles_d; mt /= p.tiles_d;
         const int tn = mt;
         const int w0 = tw * p.bw, h0 = th * p.bh, d0 = td * p.bd, n0 = tn * p.bn;
-        for (int tap = 0; tap < 27; ++tap) {
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          int mi, od, oh, ow;
-          if (p.stride == 1) {
-            mi = 0; od = kd - 1; oh = kh - 1; ow = kw - 1;
-          } else {
-            mi = (kd & 1) * 4 + (kh & 1) * 2 + (kw & 1);
-            od = kd >> 1; oh = kh >> 1; ow = kw >> 1;
-          }
-          for (int cc = 0; cc < c_chunks; ++cc) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::G) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::SLOT_BYTES);
+#pragma unroll
+          for (int g = 0; g < Cfg::G; ++g) {
+            const int kb = kb0 + g;
+            const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            int mi, od, oh, ow;
+            if (p.stride == 1) {
+              mi = 0; od = kd - 1; oh = kh - 1; ow = kw - 1;
+            } else {
+              mi = (kd & 1) * 4 + (kh & 1) * 2 + (kw & 1);
+              od = kd >> 1; oh = kh >> 1; ow = kw >> 1;
+            }
+            uint8_t* sa = smem + s * Cfg::SLOT_BYTES + g * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_5d(sa, &maps.a[mi], &full_bar[s], cc * 64, w0 + ow, h0 + oh, d0 + od, n0);
             tma_load_2d(sb, &tmW, &full_bar[s], tap * p.Cin + cc * 64, n_blk * BN);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
+          if (++s == Cfg::SLOTS) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -133,16 +144,20 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUt
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::G) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < Cfg::G; ++g) {
+            const uint32_t sa = smem_u32(smem + s * Cfg::SLOT_BYTES + g * Cfg::STAGE_BYTES);
+            const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
+            const uint64_t b_desc = make_sdesc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb0 + g) | k) != 0 ? 1u : 0u);
+          }
           tc_commit(&empty_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == Cfg::SLOTS) { s = 0; ph ^= 1; }
         }
         tc_commit(&tmem_full_bar[acc]);
       }
