@@ -4,6 +4,8 @@
 //   boundary_kernel  final LayerNorm + proj_out + EDM preconditioning + Euler/Heun update + next proj_in
 //                                                                        :230-232, :422-429, :265-273, :221
 //   radar_tokens_kernel  token projection + r/a/e embeddings            :390-405
+#include <stdlib.h>
+
 #include "host.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -115,14 +117,17 @@ struct BoundaryParams {
   float sigma_data;
 };
 
-constexpr int BND_WARPS = 16;  // 16 rows in flight per SM: the kernel is bound by the latency of the row loads
-
-__global__ void __launch_bounds__(BND_WARPS * 32)
+// R rows per warp iteration. R = 1 (16 warps): 16 rows in flight per SM, the latency-bound small-batch form. R = 4
+// (8 warps, 32 rows in flight): every weight value fetched from shared memory serves four rows — with one row per warp
+// the two projections read 128 KB of shared memory per row and the kernel ran at the shared-memory bandwidth
+// (194 us per 32 768 rows). The per-row arithmetic and its order are the same for both forms (bit-identical results).
+template <int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 boundary_kernel(const BoundaryParams p) {
   extern __shared__ float sm[];
   float* s_wout = sm;                    // [512][32]
   float* s_win = s_wout + 512 * 32;      // [C][512] (allocated for 32 channels)
-  float* s_row = s_win + 32 * 512;       // [BND_WARPS][512]
+  float* s_row = s_win + 32 * 512;       // [WARPS][R][512]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool need_net = p.mode < 3;
   const bool need_next = p.h_next != nullptr;
@@ -137,100 +142,153 @@ boundary_kernel(const BoundaryParams p) {
   pdl_wait();  // the weights staged above are constants; h / x / d come from the preceding kernels
   pdl_launch_dependents();
   __syncthreads();
-  float* my_row = s_row + warp * 512;
+  float* my_rows = s_row + warp * (R * 512);
   const float sd = p.sigma_data;
 
-  for (int64_t row = (int64_t)blockIdx.x * BND_WARPS + warp; row < p.T; row += (int64_t)gridDim.x * BND_WARPS) {
-    const int64_t f = row / p.rows_per_frame;
+  for (int64_t row0 = ((int64_t)blockIdx.x * WARPS + warp) * R; row0 < p.T; row0 += (int64_t)gridDim.x * WARPS * R) {
+    // the R rows of an iteration belong to one frame (R divides rows_per_frame, checked on the host)
+    const int64_t f = row0 / p.rows_per_frame;
     const float sig = p.sigma[f * p.sigma_stride];
     const float sig_o = p.sigma_other ? p.sigma_other[f * p.sigma_other_stride] : 0.f;
-    float F = 0.f;
+    float F[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) F[r] = 0.f;
     if (need_net) {
-      const float4* hr = reinterpret_cast<const float4*>(p.h + row * 512);
-      float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = hr[j * 32 + lane];
-      float s = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r;
+        float4 v[4];
+        if (row < p.T) {
+          const float4* hr = reinterpret_cast<const float4*>(p.h + row * 512);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-      const float mean = warp_sum(s) * (1.0f / 512);
-      float ss = 0.f;
+          for (int j = 0; j < 4; ++j) v[j] = hr[j * 32 + lane];
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-        ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
-      }
-      const float rstd = rsqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+          for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + j * 32 + lane);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_b) + j * 32 + lane);
-        reinterpret_cast<float4*>(my_row)[j * 32 + lane] =
-            make_float4(v[j].x * rstd * g.x + b.x, v[j].y * rstd * g.y + b.y, v[j].z * rstd * g.z + b.z,
-                        v[j].w * rstd * g.w + b.w);
+        for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        const float mean = warp_sum(s) * (1.0f / 512);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+          ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + j * 32 + lane);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_b) + j * 32 + lane);
+          reinterpret_cast<float4*>(my_rows + r * 512)[j * 32 + lane] =
+              make_float4(v[j].x * rstd * g.x + b.x, v[j].y * rstd * g.y + b.y, v[j].z * rstd * g.z + b.z,
+                          v[j].w * rstd * g.w + b.w);
+        }
       }
       __syncwarp();
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+      float a[R][4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.f;
+#pragma unroll 2
       for (int k = 0; k < 512; k += 4) {
-        const float4 r = *reinterpret_cast<const float4*>(my_row + k);  // broadcast
-        a0 = fmaf(r.x, s_wout[(k + 0) * 32 + lane], a0);
-        a1 = fmaf(r.y, s_wout[(k + 1) * 32 + lane], a1);
-        a2 = fmaf(r.z, s_wout[(k + 2) * 32 + lane], a2);
-        a3 = fmaf(r.w, s_wout[(k + 3) * 32 + lane], a3);
+        const float w0 = s_wout[(k + 0) * 32 + lane], w1 = s_wout[(k + 1) * 32 + lane];
+        const float w2 = s_wout[(k + 2) * 32 + lane], w3 = s_wout[(k + 3) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 rv = *reinterpret_cast<const float4*>(my_rows + r * 512 + k);  // broadcast
+          a[r][0] = fmaf(rv.x, w0, a[r][0]);
+          a[r][1] = fmaf(rv.y, w1, a[r][1]);
+          a[r][2] = fmaf(rv.z, w2, a[r][2]);
+          a[r][3] = fmaf(rv.w, w3, a[r][3]);
+        }
       }
-      F = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int r = 0; r < R; ++r) F[r] = (a[r][0] + a[r][1]) + (a[r][2] + a[r][3]);
       __syncwarp();
     }
     const bool ch_ok = lane < p.C;
-    const float x = ch_ok ? p.x_in[row * p.C + lane] : 0.f;
-    float xo;
-    float sig_next = sig;  // sigma at which the NEXT evaluation runs
-    if (p.mode == 3) {
-      xo = x * sig;   // x_0 = latents * t_0
-    } else if (p.mode == 4) {
-      xo = x;         // plain forward(): only the next projection h = proj_in(c_in x) is wanted
-    } else {
-      const float c_skip = sd * sd / (sig * sig + sd * sd);
-      const float c_out = sig * sd / sqrtf(sig * sig + sd * sd);
-      const float D = c_skip * x + c_out * F;
-      if (p.mode == 0) {
-        xo = D;
-      } else if (p.mode == 1) {
-        const float d = (x - D) / sig;
-        xo = x + (sig_o - sig) * d;
-        if (ch_ok) p.d_buf[row * p.C + lane] = d;
-        sig_next = sig_o;
-      } else {
-        const float dp = (x - D) / sig;
-        const float dc = ch_ok ? p.d_buf[row * p.C + lane] : 0.f;
-        const float xb = ch_ok ? p.x_base[row * p.C + lane] : 0.f;
-        xo = xb + (sig - sig_o) * (0.5f * dc + 0.5f * dp);
-      }
-    }
-    if (ch_ok && p.x_out != nullptr) p.x_out[row * p.C + lane] = xo;
-    if (need_next) {
-      const float c_in = 1.0f / sqrtf(sd * sd + sig_next * sig_next);
-      const float xs = ch_ok ? c_in * xo : 0.f;
-      float4 acc[4];
+    float xs[R];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      const bool ok = ch_ok && row < p.T;
+      const float x = ok ? p.x_in[row * p.C + lane] : 0.f;
+      float xo;
+      float sig_next = sig;  // sigma at which the NEXT evaluation runs
+      if (p.mode == 3) {
+        xo = x * sig;   // x_0 = latents * t_0
+      } else if (p.mode == 4) {
+        xo = x;         // plain forward(): only the next projection h = proj_in(c_in x) is wanted
+      } else {
+        const float c_skip = sd * sd / (sig * sig + sd * sd);
+        const float c_out = sig * sd / sqrtf(sig * sig + sd * sd);
+        const float D = c_skip * x + c_out * F[r];
+        if (p.mode == 0) {
+          xo = D;
+        } else if (p.mode == 1) {
+          const float d = (x - D) / sig;
+          xo = x + (sig_o - sig) * d;
+          if (ok) p.d_buf[row * p.C + lane] = d;
+          sig_next = sig_o;
+        } else {
+          const float dp = (x - D) / sig;
+          const float dc = ok ? p.d_buf[row * p.C + lane] : 0.f;
+          const float xb = ok ? p.x_base[row * p.C + lane] : 0.f;
+          xo = xb + (sig - sig_o) * (0.5f * dc + 0.5f * dp);
+        }
+      }
+      if (ok && p.x_out != nullptr) p.x_out[row * p.C + lane] = xo;
+      const float c_in = 1.0f / sqrtf(sd * sd + sig_next * sig_next);
+      xs[r] = ok ? c_in * xo : 0.f;
+    }
+    if (need_next) {
+      float4 acc[R][4];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int c = 0; c < p.C; ++c) {
-        const float xc = __shfl_sync(0xffffffffu, xs, c);
+        float xc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xc[r] = __shfl_sync(0xffffffffu, xs[r], c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 w = reinterpret_cast<const float4*>(s_win + c * 512)[j * 32 + lane];
-          acc[j].x = fmaf(xc, w.x, acc[j].x);
-          acc[j].y = fmaf(xc, w.y, acc[j].y);
-          acc[j].z = fmaf(xc, w.z, acc[j].z);
-          acc[j].w = fmaf(xc, w.w, acc[j].w);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][j].x = fmaf(xc[r], w.x, acc[r][j].x);
+            acc[r][j].y = fmaf(xc[r], w.y, acc[r][j].y);
+            acc[r][j].z = fmaf(xc[r], w.z, acc[r][j].z);
+            acc[r][j].w = fmaf(xc[r], w.w, acc[r][j].w);
+          }
         }
       }
-      float4* hn = reinterpret_cast<float4*>(p.h_next + row * 512);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) hn[j * 32 + lane] = acc[j];
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < p.T) {
+          float4* hn = reinterpret_cast<float4*>(p.h_next + (row0 + r) * 512);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hn[j * 32 + lane] = acc[r][j];
+        }
+      }
     }
   }
+}
+
+template <int R, int WARPS>
+static int launch_boundary(const BoundaryParams& p, int64_t T, cudaStream_t stream) {
+  const int smem = (512 * 32 + 32 * 512 + WARPS * R * 512) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(boundary_kernel<R, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int64_t blocks = (T + WARPS * R - 1) / (WARPS * R);
+  const int64_t cap = device_sm_count();
+  if (blocks > cap) blocks = cap;
+  RALD_CHECK_CUDA(launch_pdl(boundary_kernel<R, WARPS>, dim3((unsigned)blocks), dim3(WARPS * 32), smem, stream, p));
+  return 0;
 }
 
 int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t,
@@ -246,18 +304,12 @@ int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const flo
   p.d_buf = d_buf; p.x_out = x_out; p.h_next = h_next; p.sigma = sigma; p.sigma_other = sigma_other;
   p.sigma_stride = sigma_stride; p.sigma_other_stride = sigma_other_stride; p.mode = mode;
   p.rows_per_frame = rows_per_frame; p.C = C; p.T = T; p.sigma_data = sigma_data;
-  const int smem = (512 * 32 + 32 * 512 + BND_WARPS * 512) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    RALD_CHECK_CUDA(cudaFuncSetAttribute(boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  int64_t blocks = (T + BND_WARPS - 1) / BND_WARPS;
-  const int64_t cap = device_sm_count();
-  if (blocks > cap) blocks = cap;
   ProfScope prof(FAM_BOUNDARY, stream, (double)T * (mode < 3 ? 2048.0 : 0.0) + (h_next ? (double)T * 2048.0 : 0.0) +
                                           (double)T * C * 16.0);
-  RALD_CHECK_CUDA(launch_pdl(boundary_kernel, dim3((unsigned)blocks), dim3(BND_WARPS * 32), smem, stream, p));
+  // four rows per warp once the batch fills the machine with them (RALD_B200_BOUNDARY_R4=0: always one row per warp)
+  static const bool r4_env = [] { const char* e = getenv("RALD_B200_BOUNDARY_R4"); return e == nullptr || e[0] != '0'; }();
+  if (r4_env && rows_per_frame % 4 == 0 && T >= (int64_t)device_sm_count() * 8 * 4) RALD_TRY((launch_boundary<4, 8>(p, T, stream)));
+  else RALD_TRY((launch_boundary<1, 16>(p, T, stream)));
   RALD_LAUNCHED();
   return 0;
 }
