@@ -225,7 +225,8 @@ typedef struct rald_ae_weights {
   const float* ln1_b;
   const float* ln2_w;  /* [depth][dim] layers.N.1.norm */
   const float* ln2_b;
-  const float* proj_wt; /* [latent_dim][dim] proj.weight transposed */
+  const float* proj_wt; /* [latent_dim][dim] proj.weight transposed; NULL (with latent_dim == dim): deterministic
+                         * AutoEncoder.decode (models_ae.py:260-264), the latents are the residual stream */
   const float* proj_b;  /* [dim] */
 } rald_ae_weights;
 
@@ -292,7 +293,8 @@ typedef struct rald_ae_enc_weights {
   const void* ca_wq; const void* ca_wkv; const void* ca_wo; const float* ca_bo;
   const float* ff_ln_w; const float* ff_ln_b;      /* cross_attend_blocks.1 */
   const void* ff_w1; const float* ff_b1; const void* ff_w2; const float* ff_b2;   /* GEGLU-packed w1/b1 */
-  const void* w_stats;           /* bf16 [stats_rows][dim]: mean_fc rows, logvar_fc rows, zero rows */
+  const void* w_stats;           /* bf16 [stats_rows][dim]: mean_fc rows, logvar_fc rows, zero rows; NULL: deterministic
+                                  * AutoEncoder.encode (models_ae.py:226-257), ml_out receives x itself [B*n_latents][dim] */
   const float* b_stats;
 } rald_ae_enc_weights;
 

@@ -318,6 +318,8 @@ def ae_encode_stats(sd: SD, pc: torch.Tensor, query_type: str, num_latents: int 
         raise NotImplementedError(query_type)
     x = _ae_attention(sd, "cross_attend_blocks.0", x, pe, heads=1) + x
     x = _ae_ff(sd, "cross_attend_blocks.1", x) + x
+    if "mean_fc.weight" not in sd:
+        return x          # deterministic AutoEncoder.encode, models_ae.py:226-257: the latents are x itself
     mean = _lin(sd, "mean_fc", x)
     logvar = torch.clamp(_lin(sd, "logvar_fc", x), -30.0, 20.0)
     return mean, logvar
@@ -339,7 +341,7 @@ def ae_depth(sd: SD) -> int:
 
 def ae_latent_stack(sd: SD, z: torch.Tensor) -> torch.Tensor:
     """proj + 24 x (self-attn, FF) of KLAutoEncoder.decode, models_ae.py:410-414."""
-    x = _lin(sd, "proj", z)
+    x = _lin(sd, "proj", z) if "proj.weight" in sd else z   # deterministic AutoEncoder.decode (:260-264) has no proj
     for n in range(ae_depth(sd)):
         x = _ae_attention(sd, f"layers.{n}.0", x, None, heads=8) + x
         x = _ae_ff(sd, f"layers.{n}.1", x) + x

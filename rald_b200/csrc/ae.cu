@@ -129,7 +129,13 @@ extern "C" int rald_ae_stack(const rald_ae_weights* w, const rald_dit_workspace*
     const int nf = (frames - f0) < ws->max_frames ? (frames - f0) : ws->max_frames;
     const int64_t T = (int64_t)nf * M;
     float* h = x_out + (int64_t)f0 * M * dim;  // the residual stream lives directly in the output buffer
-    RALD_TRY(linear_smallk(z + (int64_t)f0 * M * w->latent_dim, w->latent_dim, w->proj_wt, w->proj_b, h, T, dim, st));
+    if (w->proj_wt != nullptr) {
+      RALD_TRY(linear_smallk(z + (int64_t)f0 * M * w->latent_dim, w->latent_dim, w->proj_wt, w->proj_b, h, T, dim, st));
+    } else {
+      // deterministic AutoEncoder.decode (models_ae.py:260-264): the latents ARE the residual stream, no projection
+      RALD_REQUIRE(w->latent_dim == dim, "ae_stack: latents of width %d need a projection to %d", w->latent_dim, dim);
+      RALD_CHECK_CUDA(cudaMemcpyAsync(h, z + (int64_t)f0 * M * dim, sizeof(float) * T * dim, cudaMemcpyDeviceToDevice, st));
+    }
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws->qkv);
     for (int n = 0; n < w->depth; ++n) {
       const __nv_bfloat16* w_qkv = reinterpret_cast<const __nv_bfloat16*>(w->w_qkv) + (int64_t)n * 3 * dim * dim;

@@ -163,7 +163,8 @@ int fps(const float* pts, int B, int N, int M, int64_t* out_idx, cudaStream_t st
   RALD_REQUIRE(M <= N, "fps: cannot sample %d of %d points", M, N);
   const int smem = 3 * N * sizeof(float);
   RALD_REQUIRE(smem <= 200 * 1024, "fps: cloud of %d points does not fit in shared memory", N);
-  static int configured = 48 * 1024;
+  // the kernel also has static shared memory, so even a request of exactly 48 KB needs the opt-in
+  static int configured = 32 * 1024;
   if (smem > configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
@@ -365,6 +366,11 @@ extern "C" int rald_ae_encode_stats(const rald_ae_enc_weights* w, const rald_ae_
     RALD_TRY(ln_rows(x, dim, w->ff_ln_w, w->ff_ln_b, 0, 0, 0, xn, dim, 0, M, dim, 1e-5f, st));
     RALD_TRY(gemm_bf16(xn, dim, w->ff_w1, dim, ff, 4 * dim, w->ff_b1, nullptr, 0, M, 8 * dim, dim, 2, 0, st));
     RALD_TRY(gemm_bf16(ff, 4 * dim, w->ff_w2, 4 * dim, x, dim, w->ff_b2, x, dim, M, dim, 4 * dim, 1, 0, st));
+    if (w->w_stats == nullptr) {
+      // deterministic AutoEncoder.encode (:226-257): the latents are the fp32 residual stream itself, [M][dim]
+      RALD_CHECK_CUDA(cudaMemcpyAsync(ml_out + (int64_t)b * M * dim, x, sizeof(float) * M * dim, cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     // ---- (mean | logvar) = x [W_mean; W_logvar]^T + b (:398-399), x taken in fp32 -> bf16 without a norm ----
     RALD_TRY(gn_apply(x, nullptr, nullptr, nullptr, xn, 1, (int64_t)M * dim / 256, 256, 0, 0.f, 2, st));
     RALD_TRY(gemm_bf16(xn, dim, w->w_stats, dim, ml_out + (int64_t)b * M * n_stats, n_stats, w->b_stats, nullptr, 0, M,

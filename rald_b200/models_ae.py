@@ -212,17 +212,42 @@ class KLAutoEncoder(nn.Module):
 
 
 class AutoEncoder(nn.Module):
-    """Deterministic variant ("not actually used" in the reference, :181-282): parameter container only."""
+    """Deterministic variant ("not actually used" in the reference, :181-282): FPS queries, no posterior head, the
+    latents are the 512-wide residual stream itself. Served by the same kernels as KLAutoEncoder (encode without the
+    (mean | logvar) projection, decode without ``proj``); like there, dim 512 = 8 x 64 heads and 512 latents only
+    (``ae_d512_m512``) — the other ``ae_d*_m*`` factories construct (state_dict contract) and raise on use."""
 
     def __init__(self, *, depth=24, dim=512, queries_dim=512, output_dim=1, num_inputs=2048, num_latents=512, heads=8,
                  dim_head=64, weight_tie_layers=False, decoder_ff=False):
         super().__init__()
         self.depth, self.num_inputs, self.num_latents = depth, num_inputs, num_latents
+        self.dim, self.latent_dim, self.heads = dim, dim, heads
         _build_trunk(self, depth, dim, queries_dim, output_dim, heads, dim_head, weight_tie_layers, decoder_ff,
                      "point", num_latents)
+        self.__dict__["_rt"] = None
+
+    def _runtime(self):
+        if self.__dict__.get("_rt") is None:
+            from .runtime_ae import AeRuntime
+            self.__dict__["_rt"] = AeRuntime(self)
+        return self.__dict__["_rt"]
+
+    def encode(self, pc):
+        """pc [B, N, 3] -> latents [B, M, dim] (reference :226-257)."""
+        B, N, D = pc.shape
+        assert N == self.num_inputs
+        with torch.no_grad():
+            return self._runtime().encode_deterministic(pc)
+
+    def decode(self, x, queries):
+        """latents [B, M, dim], queries [B, Q, 3] -> occupancy logits [B, Q, 1] (reference :260-274)."""
+        with torch.no_grad():
+            return self._runtime().decode(x, queries)
 
     def forward(self, pc, queries):
-        raise NotImplementedError("rald_b200: the deterministic AutoEncoder is a next-tier component (SURVEY.md §2 #3)")
+        x = self.encode(pc)
+        o = self.decode(x, queries).squeeze(-1)
+        return {"logits": o}
 
 
 def create_autoencoder(dim=512, M=512, latent_dim=64, N=2048, determinisitc=False, query_type="point"):

@@ -44,6 +44,7 @@ class AeRuntime:
         if dev.type != "cuda":
             raise _lib.RaldError("rald_b200 runs on CUDA devices only: move the module to a B200 (no CPU fallback)")
         dim, heads = m.dim, m.heads
+        self.deterministic = not hasattr(m, "proj")     # AutoEncoder: latents of width dim, no proj / mean_fc / logvar_fc
         if dim != 512 or dim // heads != 64 or m.num_latents != 512:
             raise _lib.RaldError(f"unsupported autoencoder geometry dim={dim} heads={heads} latents={m.num_latents}: "
                                  "kernels are built for dim 512 = 8 x 64 and 512 latents")
@@ -66,8 +67,11 @@ class AeRuntime:
             self.ln1_b = stack(lambda a, f: a.norm.bias, torch.float32)
             self.ln2_w = stack(lambda a, f: f.norm.weight, torch.float32)
             self.ln2_b = stack(lambda a, f: f.norm.bias, torch.float32)
-            self.proj_wt = m.proj.weight.detach().float().t().contiguous()
-            self.proj_b = m.proj.bias.detach().float().contiguous()
+            if self.deterministic:
+                self.proj_wt = self.proj_b = None
+            else:
+                self.proj_wt = m.proj.weight.detach().float().t().contiguous()
+                self.proj_b = m.proj.bias.detach().float().contiguous()
             # ---- decoder: constant folding in fp64 (weights only; see csrc/ae_query.cu) ----
             dca = m.decoder_cross_attn
             wq = dca.fn.to_q.weight.detach().double()
@@ -111,7 +115,7 @@ class AeRuntime:
         w.latent_dim, w.n_latents = m.latent_dim, m.num_latents
         for name in ("w_qkv", "w_o", "w_ff1", "w_ff2", "b_o", "b_ff1", "b_ff2", "ln1_w", "ln1_b", "ln2_w", "ln2_b",
                      "proj_wt", "proj_b"):
-            setattr(w, name, getattr(self, name).data_ptr())
+            setattr(w, name, _lib.ptr(getattr(self, name)) or None)
         return w
 
     def _workspace(self, frames: int):
@@ -201,6 +205,14 @@ class AeRuntime:
         self._check_cuda()
         self.ensure_packed()
         return encode_stats(self, pc)
+
+    def encode_deterministic(self, pc: torch.Tensor) -> torch.Tensor:
+        """AutoEncoder.encode (models_ae.py:226-257): pc [B, N, 3] -> latents [B, M, dim] fp32."""
+        from .runtime_ae_encode import encode_raw
+        self._check_cuda()
+        self.ensure_packed()
+        x, _ = encode_raw(self, pc)
+        return x.view(pc.shape[0], self.module.num_latents, self.dim)
 
     def encode(self, pc: torch.Tensor, noise: torch.Tensor):
         """(kl [B], z [B, M, latent_dim]) with the posterior noise injected (drawn by the caller exactly as the

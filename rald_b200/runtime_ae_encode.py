@@ -71,14 +71,18 @@ class AeEncodeState:
             put("ff_ln_w", cf.norm.weight, torch.float32); put("ff_ln_b", cf.norm.bias, torch.float32)
             put("ff_w1", cf.fn.net[0].weight[idx], bf); put("ff_b1", cf.fn.net[0].bias[idx], torch.float32)
             put("ff_w2", cf.fn.net[2].weight, bf); put("ff_b2", cf.fn.net[2].bias, torch.float32)
-            L = m.latent_dim
-            rows = -(-2 * L // 32) * 32
-            ws_ = torch.zeros(rows, dim, device=dev, dtype=torch.float32)
-            ws_[:L], ws_[L:2 * L] = m.mean_fc.weight.detach(), m.logvar_fc.weight.detach()
-            bs_ = torch.zeros(rows, device=dev, dtype=torch.float32)
-            bs_[:L], bs_[L:2 * L] = m.mean_fc.bias.detach(), m.logvar_fc.bias.detach()
-            put("w_stats", ws_, bf); put("b_stats", bs_, torch.float32)
-            w.stats_rows = rows
+            if rt.deterministic:
+                # AutoEncoder: no posterior head; the library copies the residual stream out (w_stats = NULL)
+                w.stats_rows = dim
+            else:
+                L = m.latent_dim
+                rows = -(-2 * L // 32) * 32
+                ws_ = torch.zeros(rows, dim, device=dev, dtype=torch.float32)
+                ws_[:L], ws_[L:2 * L] = m.mean_fc.weight.detach(), m.logvar_fc.weight.detach()
+                bs_ = torch.zeros(rows, device=dev, dtype=torch.float32)
+                bs_[:L], bs_[L:2 * L] = m.mean_fc.bias.detach(), m.logvar_fc.bias.detach()
+                put("w_stats", ws_, bf); put("b_stats", bs_, torch.float32)
+                w.stats_rows = rows
             if m.query_type == "learnable":
                 put("latents", m.latents.weight, torch.float32)
             elif m.query_type == "mix":

@@ -52,3 +52,34 @@ def test_decode_with_no_queries():
                                  latent_dim=32, heads=8, dim_head=64, query_type="learnable").eval().cuda()
     out = ae.decode(torch.zeros(2, 512, 32, device="cuda"), torch.zeros(2, 0, 3, device="cuda"))
     assert out.shape == (2, 0, 1)
+
+
+def test_deterministic_autoencoder_matches_reference():
+    """AutoEncoder (reference models_ae.py:181-282, ae_d512_m512): FPS indices bit-exact, latents and logits against
+    the fixture written from the unmodified reference (tests/golden/make_golden_ae_det.py)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from helpers import rel_l2
+    from rald_b200 import models_ae
+    g = np.load(os.path.join(GOLDEN, "ae_det.npz"))
+    pc, q = torch.from_numpy(g["pc"]).cuda(), torch.from_numpy(g["queries"]).cuda()
+    torch.manual_seed(1024)
+    ae = models_ae.ae_d512_m512(N=pc.shape[1]).eval().cuda()
+    idx = ae._runtime().fps(pc, 512)
+    assert np.array_equal(idx[0].cpu().numpy(), g["fps_idx"])
+    x = ae.encode(pc)
+    assert x.shape == (1, 512, 512) and x.dtype == torch.float32
+    err = rel_l2(x[0, ::8], torch.from_numpy(g["latents_rows"]))
+    print("deterministic AE latents rel-L2", err)
+    assert err < 1e-2
+    out = ae(pc, q)
+    assert set(out) == {"logits"} and out["logits"].shape == (1, q.shape[1])
+    ref = torch.from_numpy(g["logits"])
+    got = out["logits"][0].cpu()
+    offset = float((got - ref).mean())
+    resid = float(((got - ref) - offset).std())
+    print(f"logits: mean {float(ref.mean()):.4f} field std {float(ref.std()):.4f} common-mode {offset:.2e} residual {resid:.2e}")
+    assert abs(offset) < 2e-2 * abs(float(ref.mean())) + 1e-3
+    assert resid < 0.05 * float(ref.std())
+    assert torch.equal(ae.decode(x, q).squeeze(-1), out["logits"])
