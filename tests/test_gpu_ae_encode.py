@@ -49,6 +49,18 @@ def test_fps_matches_c_oracle_bit_exact(ae_point, kind):
     assert torch.equal(got[:1], orc.fps_indices(pc[:1], m))   # numpy restatement agrees with the C one
 
 
+@pytest.mark.parametrize("n,m", [(16384, 512), (4097, 33), (4096, 64), (40, 40), (32, 1)])
+def test_fps_size_limits_match_c_oracle(ae_point, n, m):
+    """Largest cloud one CTA holds, sizes around the 48 KB shared-memory opt-in, every point sampled, a single pick."""
+    pc = synth.lidar_points(2, n, seed=n + m)
+    got = ae_point._runtime().fps(pc.cuda(), m).cpu()
+    assert torch.equal(got, orc.fps_indices_c(pc, m))
+    if m == n:
+        assert sorted(got[0].tolist()) == list(range(n))
+    with pytest.raises(Exception):
+        ae_point._runtime().fps(synth.lidar_points(1, 16385, seed=1).cuda(), 8)
+
+
 def test_fps_full_size_batch_properties(ae_point):
     """BASELINE-size batch (64 clouds x 10000 points): first pick 0, no repeats, greedy max-min property on a sample."""
     pc = synth.lidar_points(64, 10000, seed=11)
