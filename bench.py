@@ -241,6 +241,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL_DEBUG=VERSION (set on some boxes) prints "NCCL version ..." there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     if args.no_graph:
