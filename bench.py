@@ -241,10 +241,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL_DEBUG=VERSION (set on some boxes) prints "NCCL version ..." there
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: NCCL prints its "NCCL version ..." banner there while the communicator is
+        # created (NCCL_DEBUG=VERSION is set on the boxes), so file descriptor 1 points at stderr until that is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.lib()
     if args.no_graph:
         os.environ["RALD_B200_GRAPH"] = "0"
