@@ -19,7 +19,9 @@ the headline instead.
 The line printed by rank 0 follows the driver contract; `value` is timed with inputs resident in HBM, `e2e` through
 the public module API from pinned host buffers (H2D of cube + queries, D2H of the occupied points, every step).
 `--impl reference` times the reference's CPU implementation of the same path (the oracle port of its PyTorch
-modules, all host threads) on a bounded sample of the same workload.
+modules, all host threads) on a bounded sample of the same workload. At N = 1 the line also carries
+`gpu_eager_baseline`: the same port run as plain PyTorch eager fp32 on THIS GPU (SURVEY.md §8d's "GPU reference
+baseline") — what the reference's own code path costs on the B200, a reported baseline like `cpu_baseline`.
 """
 from __future__ import annotations
 
@@ -58,6 +60,8 @@ def parse():
     ap.add_argument("--frames-per-gpu", type=int, default=64)
     ap.add_argument("--queries", type=int, default=500000)  # eval.inference.num_query_points
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
+                    help="skip the PyTorch-eager-on-this-GPU port of the reference (a reported baseline, ~3 s)")
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the sampler")
     return ap.parse_args()
 
@@ -190,6 +194,55 @@ def cpu_reference_sample(queries_total: int, sample_queries: int = 262144, sampl
                        f"{queries_total} decoder queries ({t_q:.2f} s) for 1 frame, extrapolated linearly; oracle port "
                        f"of the reference's fp32 PyTorch CPU path"),
             "s_per_frame": t_frame, "hoisted_value": 1.0 / t_frame_hoisted, "s_per_net_eval": t_eval}
+
+
+def gpu_eager_port_sample(dev, queries_total: int, frames: int = 8, sample_evals: int = 4, sample_queries: int = 65536):
+    """SURVEY.md §8d's "GPU reference baseline": what the reference's own code path costs on THIS B200 — plain PyTorch
+    eager fp32 (torch's cuBLAS / cuDNN kernels, one launch per op, the radar encoder inside every evaluation, scores and
+    per-query activations materialised), here through the oracle port of its modules moved to the device (the
+    reference tree itself cannot travel to the GPU box). Bounded sample like the CPU leg: `sample_evals` evaluations of
+    a `frames`-frame batch + latent stack + `sample_queries` decoder queries per frame, extrapolated linearly. A
+    reported baseline only — none of it is on the product path."""
+    from oracle import rald_oracle as orc
+    from rald_b200 import synth
+    net, vae = build_models("cpu")
+    sd = {k: v.detach().float().to(dev) for k, v in net.state_dict().items()}
+    sd_ae = {k: v.detach().float().to(dev) for k, v in vae.state_dict().items()}
+    del net, vae
+    cube = synth.radar_cube(frames, seed=SEED).to(dev)
+    lat = synth.unit_latents(range(frames)).to(dev)
+    q = synth.query_points(1, sample_queries).to(dev).expand(frames, -1, -1).contiguous()
+    sigmas = orc.karras_sigmas()
+
+    def one_eval(sigma):
+        tok = orc.process_radar_cond(sd, cube)
+        return orc.edm_precond(sd, lat * float(sigma), float(sigma), tok)
+
+    def timed(fn, n=1):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            out = fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n, out
+
+    with torch.no_grad():
+        one_eval(sigmas[0])   # warm-up (cuDNN algorithm selection, allocator)
+        t_eval, d = timed(lambda: one_eval(sigmas[1]), sample_evals)
+        z = d[:, :, :32].contiguous()
+        orc.ae_latent_stack(sd_ae, z)
+        t_stack, x = timed(lambda: orc.ae_latent_stack(sd_ae, z))
+        orc.ae_query(sd_ae, x, q)
+        t_q, _ = timed(lambda: orc.ae_query(sd_ae, x, q))
+    t_step = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
+    del sd, sd_ae
+    torch.cuda.empty_cache()
+    return {"value": frames / t_step, "unit": UNIT, "kind": "port, PyTorch eager fp32 on the same GPU",
+            "sample": (f"{sample_evals} of {NET_EVALS} network evaluations of a {frames}-frame batch as the reference "
+                       f"runs them (radar encoder inside, {t_eval * 1e3:.0f} ms each) + latent stack "
+                       f"({t_stack * 1e3:.0f} ms) + {sample_queries} of {queries_total} decoder queries per frame "
+                       f"({t_q * 1e3:.0f} ms), extrapolated linearly; oracle port of the reference's modules on the "
+                       f"device, torch {torch.__version__} eager, matmul fp32 / cuDNN defaults")}
 
 
 def run_reference(args, rank, world=1):
@@ -418,6 +471,13 @@ def run_ours(args, rank, world, local_rank):
                 "latency_b1": lat, "tflops_step": gflop_step / (ms_res / args.steps),
                 "roofline": roofline, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes, "clocks": clock_rec,
                 "occupancy_bias_shift": shift}
+        if world == 1 and not args.no_gpu_eager_baseline:
+            # after the timed regions; a failure here (e.g. out of memory next to the resident models) only drops the key
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_port_sample(dev, Q)
+            except Exception as e:  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+                torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(Q)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "hoisted_value")}

@@ -62,7 +62,7 @@ def _geglu_ff(x: torch.Tensor, w1, b1, w2, b2) -> torch.Tensor:
 def positional_embedding(x: torch.Tensor, num_channels: int = 256, max_positions: int = 10000) -> torch.Tensor:
     """models_radar_generation.py:27-33 — cos first, then sin; freqs = max_positions^(-j/half)."""
     half = num_channels // 2
-    freqs = torch.arange(half, dtype=torch.float32) / half
+    freqs = torch.arange(half, dtype=torch.float32, device=x.device) / half
     freqs = (1.0 / max_positions) ** freqs
     y = torch.outer(x.to(torch.float32), freqs)
     return torch.cat([y.cos(), y.sin()], dim=1)
@@ -118,7 +118,7 @@ def edm_precond(sd: SD, x: torch.Tensor, sigma: torch.Tensor, cond_tokens: torch
                 heads: int = 8) -> torch.Tensor:
     """EDMPrecond.forward after conditioning, models_radar_generation.py:418-430."""
     x = x.to(torch.float32)
-    sigma = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1, 1, 1)
+    sigma = torch.as_tensor(sigma, dtype=torch.float32).to(x.device).reshape(-1, 1, 1)
     c_skip = sigma_data ** 2 / (sigma ** 2 + sigma_data ** 2)
     c_out = sigma * sigma_data / (sigma ** 2 + sigma_data ** 2).sqrt()
     c_in = 1 / (sigma_data ** 2 + sigma ** 2).sqrt()
