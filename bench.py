@@ -1,27 +1,38 @@
 #!/usr/bin/env python
 """Benchmark of the RaLD generation hot path on B200 (BASELINE.json metric: generated frames/s, denoise loop + AE
-decode; ms per step).
+decode, at 1/2/4/8 B200; ms per step).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-gpu F] [--queries Q]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--global-frames G | --frames-per-gpu F] [--queries Q] [--quick]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 One step = one pass of the hot path over one batch: radar cube -> radar encoder -> conditioning tokens -> 18-step
 EDM/Heun sampler (35 network evaluations) -> VecSet decoder (24-layer latent stack + Q occupancy queries) ->
-threshold / compaction to a point cloud (-> NCCL gather of the clouds when N > 1). The default workload is the
-configuration BASELINE.json quotes "frames/sec at 1/2/4/8 B200" on, configs[2]: batched generation, 64 frames x full
-diffusion schedule per GPU (default configs, random-init weights with proj_out re-randomised, synthetic cubes and
-query grid). Frames are independent, so ranks shard frames with no data-path collective ("weak" scaling: 64 frames
-per GPU) and the only collective is the final gather. The metric's second half, "ms per step", is configs[1]
-(batch 1, latency-bound): it is measured in the same run and reported as `latency_b1`; --frames-per-gpu 1 makes it
-the headline instead.
+threshold / compaction to a point cloud (-> NCCL gather of the clouds when N > 1).
 
-The line printed by rank 0 follows the driver contract; `value` is timed with inputs resident in HBM, `e2e` through
-the public module API from pinned host buffers (H2D of cube + queries, D2H of the occupied points, every step).
-`--impl reference` times the reference's CPU implementation of the same path (the oracle port of its PyTorch
-modules, all host threads) on a bounded sample of the same workload. At N = 1 the line also carries
-`gpu_eager_baseline`: the same port run as plain PyTorch eager fp32 on THIS GPU (SURVEY.md §8d's "GPU reference
-baseline") — what the reference's own code path costs on the B200, a reported baseline like `cpu_baseline`.
+Default workload = BASELINE.json configs[2] AS WRITTEN: 64 GLOBAL frames x full diffusion schedule, frame-sharded
+across the N GPUs (contiguous shards of 64 / N frames, seeds = global frame indices) -> "scaling": "strong". With
+--frames-per-gpu F the per-GPU work is fixed instead ("weak": F x N global frames; F = 32, N = 8 is configs[4], the
+batch-256 end-to-end run; F = 1 makes configs[1], batch-1 latency, the headline). At N > 1 the strong line also carries
+the weak figure (64 frames per GPU) as the secondary key `weak_scaling`, and `sharding_check`: rank 0 recomputes all
+global frames alone and compares them with the gathered clouds of the sharded run, bit for bit.
+
+Keys beyond the driver contract (all measured in this run, on this box):
+  e2e            the same metric through the public module API from pinned host buffers (H2D cubes + query grid, D2H of
+                 the occupied points) every step
+  roofline       the dominant kernel family (tcgen05 GEMMs) against the measured sustained bf16 peak; `rooflines` holds
+                 one entry per family (attention, fused cross-attention, conv3d, decoder queries -> tensor; LayerNorm,
+                 GroupNorm, boundary -> HBM), from CUDA events around every launch of one extra step
+  latency_b1     configs[1]: batch 1 through the same API, with its own HBM roofline (0.33 GB of weights per evaluation)
+  ae_frame       configs[0] on the GPU: VecSet encode + decode of ONE 10 000-point frame (mix and FPS/point variants),
+                 FPS kernel time against the shared-memory bandwidth of one SM
+  query_sweep    configs[3]: decoder queries at Q = 2^16 ... 2^20 against one latent set
+  cpu_baseline   the reference's fp32 CPU path (oracle port) on this box's host cores: ONE WHOLE frame, nothing
+                 extrapolated inside the frame
+  gpu_eager_baseline  the reference's formulation as PyTorch eager on THIS GPU: `as_written_fp32` (encoder inside every
+                 evaluation, fp32) and `hoisted_bf16` (encoder hoisted, torch.autocast(bf16), SDPA): library-kernel anchors
+`--impl reference` times the CPU path alone (rank 0 only; its speed does not depend on --gpus).
 """
 from __future__ import annotations
 
@@ -49,21 +60,31 @@ GFLOP_PER_EVAL = 130.494                # SURVEY.md §8d, per frame
 GFLOP_ENCODER = 286.881 + 1.686         # radar encoder + hoisted context K/V, once per frame
 GFLOP_AE_STACK = 115.96 + 0.537 + 0.268
 MFLOP_PER_QUERY = 0.5775                # folded decoder formulation (the one executed)
+DIT_WEIGHT_BYTES = 328e6                # bf16 weights streamed per network evaluation at batch 1
+SMEM_BW_PER_SM = 128 * 1.965e9          # B/s: 128 B/clk at the box's max SM clock
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=64)
+    ap.add_argument("--global-frames", type=int, default=64, help="configs[2]: frames of the whole job (strong scaling)")
+    ap.add_argument("--frames-per-gpu", type=int, default=0,
+                    help="> 0: fixed work per GPU instead (weak scaling; 32 with --gpus 8 = configs[4])")
     ap.add_argument("--queries", type=int, default=500000)  # eval.inference.num_query_points
+    ap.add_argument("--quick", action="store_true",
+                    help="main timing + e2e only (no latency / roofline / baselines / configs[0] / configs[3] legs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
-                    help="skip the PyTorch-eager-on-this-GPU port of the reference (a reported baseline, ~3 s)")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the secondary weak-scaling figure")
+    ap.add_argument("--no-sharding-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the sampler")
-    return ap.parse_args()
+    ap.add_argument("--ref-evals", type=int, default=NET_EVALS,
+                    help="CPU arm: network evaluations actually timed per frame (default: all 35 = nothing extrapolated "
+                         "inside the frame; fewer = the first ones of the Heun schedule, scaled linearly and flagged)")
+    return ap.parse_args(argv)
 
 
 def load_peaks():
@@ -123,7 +144,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# models and inputs
+# workload: models, shards, inputs
 # ------------------------------------------------------------------------------------------------------------------
 def build_models(device):
     from rald_b200 import models_ae, models_radar_generation
@@ -136,27 +157,56 @@ def build_models(device):
     return net.to(device), vae.to(device)
 
 
-def calibrate_occupancy(net, vae, cube, queries, seeds):
-    """Random-init occupancy logits are all slightly negative: shift to_outputs.bias by the 95-th
-    percentile of one decode so that `logit > 0` (engine_generation.py:285) keeps ~5 % of the queries."""
-    z = net.sample(cube, batch_seeds=seeds, cond_type="radar")
-    lg = vae.decode(z, queries).squeeze(-1)
-    sub = lg[:, :: max(1, lg.shape[1] // 65536)].flatten()   # a strided subsample of every frame's logits
-    k = max(1, int(0.95 * sub.numel()))
-    shift = float(sub.kthvalue(k).values)
-    with torch.no_grad():
-        vae.to_outputs.bias -= shift
-    return shift
+def plan(args, world: int):
+    """(scaling, global_frames, per-rank (start, stop) list). Strong: --global-frames sharded with
+    gather.shard_frames; weak: --frames-per-gpu on every rank."""
+    from rald_b200 import gather
+    if args.frames_per_gpu > 0:
+        F = args.frames_per_gpu
+        return "weak", F * world, [(r * F, r * F + F) for r in range(world)]
+    G = args.global_frames
+    if G < world:
+        raise SystemExit(f"--global-frames {G} cannot be sharded over {world} GPUs")
+    return "strong", G, [gather.shard_frames(G, r, world) for r in range(world)]
+
+
+def frame_cubes(f0: int, f1: int) -> torch.Tensor:
+    """Synthetic radar cubes of GLOBAL frames [f0, f1): frame f's cube depends on f only, whatever the sharding."""
+    from rald_b200 import synth
+    return torch.cat([synth.radar_cube(1, seed=SEED + 7919 * f) for f in range(f0, f1)])
+
+
+def workload_config(args, world, scaling, global_frames, spans):
+    per = [b - a for a, b in spans]
+    if args.frames_per_gpu == 1:
+        wl = ("configs[1]: DiT latent-set denoiser kl_d512_m512_l32_d24_edm, full 18-step EDM/Heun sampling loop (35 "
+              "evaluations) from a synthetic radar RAE cube + kl_d512_m512_l32_mix decode, batch 1")
+    elif scaling == "weak" and args.frames_per_gpu * world == 256:
+        wl = ("configs[4]: end-to-end radar spectrum -> radar encoder -> sampling loop -> AE decode at batch 256 on "
+              f"{world} x B200 ({args.frames_per_gpu} frames per GPU)")
+    elif scaling == "weak":
+        wl = (f"configs[2] shapes, weak variant: {args.frames_per_gpu} frames x full diffusion schedule PER GPU "
+              "(radar cube -> encoder -> 35 denoiser evaluations -> VecSet decode -> point cloud), frame-sharded")
+    else:
+        wl = (f"configs[2]: batched generation, {global_frames} GLOBAL frames x full diffusion schedule (radar cube -> "
+              f"encoder -> 35 denoiser evaluations -> VecSet decode -> point cloud), frame-sharded over {world} GPU(s)")
+    return {"workload": wl, "global_frames": global_frames, "frames_per_gpu": per[0] if len(set(per)) == 1 else per,
+            "queries_per_frame": args.queries, "num_steps": 18, "net_evals": NET_EVALS,
+            "parallelism": (f"frames sharded over {world} GPUs (contiguous shards, seeds = global frame indices), no "
+                            "data-path collective, final NCCL gather of the compact point clouds") if world > 1
+            else "single GPU",
+            "l2": "no flush: each evaluation streams 0.33 GB of bf16 weights (> 126 MB L2) and the step reads "
+                  "0.55 GB of weights + fresh H2D inputs"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's PyTorch modules on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(queries_total: int, sample_queries: int = 262144, sample_evals: int = 16):
-    """Times `sample_evals` of the 35 network evaluations as the reference executes them (radar encoder + tokens inside
-    every evaluation, models_radar_generation.py:412-430; the first evaluations of the real Heun schedule), the decoder
-    latent stack and `sample_queries` decoder queries for one frame — about 10 s of CPU work on 16 cores — then
-    extrapolates linearly to 35 evaluations + stack + all queries. Returns a dict with frames/s."""
+def cpu_reference_frame(queries_total: int, query_chunk: int = 65536, evals_timed: int = NET_EVALS):
+    """ONE WHOLE frame on the host cores as the reference runs it (fp32, torch CPU): the 18-step Heun loop with the
+    radar encoder + tokens inside EVERY network evaluation (models_radar_generation.py:412-430, 235-275), then
+    KLAutoEncoder.decode of all `queries_total` queries (models_ae.py:408-424; the query set is walked in chunks so the
+    [Q, 512] fp32 temporaries stay bounded — same arithmetic). Nothing is extrapolated inside the frame."""
     from oracle import rald_oracle as orc
     from rald_b200 import synth
     threads = os.cpu_count() or 1
@@ -164,59 +214,131 @@ def cpu_reference_sample(queries_total: int, sample_queries: int = 262144, sampl
     net, vae = build_models("cpu")
     sd = {k: v.detach().float() for k, v in net.state_dict().items()}
     sd_ae = {k: v.detach().float() for k, v in vae.state_dict().items()}
-    cube = synth.radar_cube(1, seed=SEED)
+    cube = frame_cubes(0, 1)
     lat = synth.unit_latents([0])
-    q = synth.query_points(1, sample_queries)
-    sigmas = orc.karras_sigmas()
-    sample_evals = max(1, min(int(sample_evals), NET_EVALS))
+    q = synth.query_points(1, queries_total)
+    t = orc.karras_sigmas()
 
-    def one_eval(sigma):
-        tok = orc.process_radar_cond(sd, cube)
-        return orc.edm_precond(sd, lat * sigma, sigma, tok)
+    def net_eval(x, sigma):
+        tok = orc.process_radar_cond(sd, cube)          # inside every evaluation, as the reference
+        return orc.edm_precond(sd, x, sigma, tok)
 
     with torch.no_grad():
-        one_eval(sigmas[0])  # warm-up (oneDNN primitive creation)
+        net_eval(lat * t[0], t[0])                      # warm-up (oneDNN primitive creation), not timed
         t0 = time.perf_counter()
-        for i in range(sample_evals):          # evaluation i of the Heun loop runs at sigma index (i + 1) // 2
-            d = one_eval(sigmas[(i + 1) // 2])
-        t_eval = (time.perf_counter() - t0) / sample_evals
-        t0 = time.perf_counter(); tok = orc.process_radar_cond(sd, cube); t_enc = time.perf_counter() - t0
-        z = d[:, :, :32]
-        orc.ae_latent_stack(sd_ae, z)
-        t0 = time.perf_counter(); x = orc.ae_latent_stack(sd_ae, z); t_stack = time.perf_counter() - t0
-        orc.ae_query(sd_ae, x, q)
-        t0 = time.perf_counter(); orc.ae_query(sd_ae, x, q); t_q = time.perf_counter() - t0
-    t_frame = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
-    t_frame_hoisted = NET_EVALS * (t_eval - t_enc) + t_enc + t_stack + t_q * (queries_total / sample_queries)
+        x = lat * t[0]
+        evals = 0
+        evals_timed = max(1, min(int(evals_timed), NET_EVALS))
+        for i in range(18):
+            if evals >= evals_timed:
+                break
+            d = (x - net_eval(x, t[i])) / t[i]
+            x_e = x + (t[i + 1] - t[i]) * d
+            evals += 1
+            if i < 17 and evals < evals_timed:
+                d2 = (x_e - net_eval(x_e, t[i + 1])) / t[i + 1]
+                x = x + (t[i + 1] - t[i]) * (0.5 * d + 0.5 * d2)
+                evals += 1
+            else:
+                x = x_e
+        t_sample = (time.perf_counter() - t0) * (NET_EVALS / evals)     # == measured when all 35 were run
+        t_scaled = t_sample * (1.0 - evals / NET_EVALS)                  # part of t_sample that was NOT measured
+        t1 = time.perf_counter()
+        ctx = orc.ae_latent_stack(sd_ae, x)
+        t_stack = time.perf_counter() - t1
+        t2 = time.perf_counter()
+        for c0 in range(0, queries_total, query_chunk):
+            orc.ae_query(sd_ae, ctx, q[:, c0:c0 + query_chunk])
+        t_q = time.perf_counter() - t2
+        t_frame = time.perf_counter() - t0 + t_scaled
+        t3 = time.perf_counter(); orc.process_radar_cond(sd, cube); t_enc = time.perf_counter() - t3
+    whole = evals == NET_EVALS
     return {"value": 1.0 / t_frame, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"{sample_evals} of {NET_EVALS} network evaluations as the reference runs them (radar encoder "
-                       f"inside, {t_eval:.2f} s each) + decoder latent stack ({t_stack:.2f} s) + {sample_queries} of "
-                       f"{queries_total} decoder queries ({t_q:.2f} s) for 1 frame, extrapolated linearly; oracle port "
-                       f"of the reference's fp32 PyTorch CPU path"),
-            "s_per_frame": t_frame, "hoisted_value": 1.0 / t_frame_hoisted, "s_per_net_eval": t_eval}
+            "sample": ((f"1 whole frame: {NET_EVALS} network evaluations" if whole else
+                        f"1 frame, {evals} of {NET_EVALS} network evaluations timed and scaled linearly (--ref-evals),")
+                       + f" as the reference runs them (radar encoder inside "
+                       f"each; {t_sample:.1f} s) + decoder latent stack ({t_stack:.2f} s) + all {queries_total} decoder "
+                       f"queries ({t_q:.1f} s); oracle port of the reference's fp32 PyTorch CPU path, {threads} threads"),
+            "whole_frame": whole, "s_per_frame": t_frame, "s_per_net_eval": t_sample / NET_EVALS,
+            "hoisted_value": 1.0 / (t_frame - (NET_EVALS - 1) * t_enc)}
 
 
-def gpu_eager_port_sample(dev, queries_total: int, frames: int = 8, sample_evals: int = 4, sample_queries: int = 65536):
-    """SURVEY.md §8d's "GPU reference baseline": what the reference's own code path costs on THIS B200 — plain PyTorch
-    eager fp32 (torch's cuBLAS / cuDNN kernels, one launch per op, the radar encoder inside every evaluation, scores and
-    per-query activations materialised), here through the oracle port of its modules moved to the device (the
-    reference tree itself cannot travel to the GPU box). Bounded sample like the CPU leg: `sample_evals` evaluations of
-    a `frames`-frame batch + latent stack + `sample_queries` decoder queries per frame, extrapolated linearly. A
-    reported baseline only — none of it is on the product path."""
+def cpu_ae_frame():
+    """configs[0]: fp32 encode + decode of ONE 10 000-point frame on the host cores (oracle port)."""
+    from oracle import rald_oracle as orc
+    from rald_b200 import models_ae, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {}
+    for name, qtype in (("kl_d512_m512_l32_mix", "mix"), ("kl_d512_m512_l32", "point")):
+        torch.manual_seed(SEED)
+        vae = models_ae.__dict__[name](N=10000).eval()
+        sd = {k: v.detach().float() for k, v in vae.state_dict().items()}
+        pc = synth.lidar_points(1, 10000, seed=SEED)
+        q = synth.query_points(1, 10000)
+        with torch.no_grad():
+            orc.ae_encode_stats(sd, pc[:, :10000], qtype)
+            t0 = time.perf_counter()
+            mean, logvar = orc.ae_encode_stats(sd, pc, qtype)
+            t_enc = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            orc.ae_decode(sd, mean, q)
+            t_dec = time.perf_counter() - t0
+        out[qtype] = {"encode_ms": t_enc * 1e3, "decode_ms": t_dec * 1e3, "frames_per_s": 1.0 / (t_enc + t_dec)}
+    return out
+
+
+def run_reference(args, rank, world=1):
+    """The reference arm: the CPU path alone. Rank 0 only; the figure does not depend on --gpus (one host)."""
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    scaling, G, spans = plan(args, world)
+    res, vals = None, []
+    for _ in range(max(1, min(args.steps, 2))):          # each sample is one whole frame (10 - 30 s of CPU work)
+        res = cpu_reference_frame(args.queries, evals_timed=args.ref_evals)
+        vals.append(res["value"])
+    value = statistics.median(vals)
+    timed_s = sum(1.0 / v for v in vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * G / value,   # one step = the job's global_frames frames, as in our arm
+            "extrapolated": (f"frames are independent and walked one at a time: {len(vals)} "
+                             f"{'whole ' if res['whole_frame'] else 'PARTIAL (--ref-evals) '}frame(s) timed "
+                             f"({timed_s:.1f} s per-frame total), ms_per_step = {G} x the per-frame time"),
+            "timed_s": timed_s, "frames_timed": len(vals),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world, scaling, G, spans),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": None,
+            "note": "CPU arm: one host process on all host cores; its value is the same whatever --gpus says, so a "
+                    "ratio of the N-GPU line to this line is N GPUs against ONE host, not a scaling figure"}
+    line["cpu_baseline"]["value"] = value
+    line["wall_s"] = time.perf_counter() - t_all
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU library-kernel anchors: the reference's formulation as PyTorch eager on this GPU (oracle port on the device)
+# ------------------------------------------------------------------------------------------------------------------
+def gpu_eager_baselines(dev, queries_total: int, frames: int = 8, sample_evals: int = 4, sample_queries: int = 65536):
+    """SURVEY.md §8d's "GPU reference baseline", two variants, bounded samples extrapolated linearly:
+      as_written_fp32  plain eager fp32 (cuBLAS / cuDNN, one launch per op), radar encoder inside every evaluation,
+                       scores and per-query activations materialised — what the reference's code costs on this B200;
+      hoisted_bf16     the same modules with the encoder hoisted out of the loop, torch.autocast(bf16) and
+                       F.scaled_dot_product_attention for every attention — the best a library-kernel eager port gets.
+    Reported baselines only — none of it is on the product path."""
+    import torch.nn.functional as Fn
     from oracle import rald_oracle as orc
     from rald_b200 import synth
     net, vae = build_models("cpu")
     sd = {k: v.detach().float().to(dev) for k, v in net.state_dict().items()}
     sd_ae = {k: v.detach().float().to(dev) for k, v in vae.state_dict().items()}
     del net, vae
-    cube = synth.radar_cube(frames, seed=SEED).to(dev)
+    cube = frame_cubes(0, frames).to(dev)
     lat = synth.unit_latents(range(frames)).to(dev)
     q = synth.query_points(1, sample_queries).to(dev).expand(frames, -1, -1).contiguous()
     sigmas = orc.karras_sigmas()
-
-    def one_eval(sigma):
-        tok = orc.process_radar_cond(sd, cube)
-        return orc.edm_precond(sd, lat * float(sigma), float(sigma), tok)
 
     def timed(fn, n=1):
         torch.cuda.synchronize(dev)
@@ -226,66 +348,246 @@ def gpu_eager_port_sample(dev, queries_total: int, frames: int = 8, sample_evals
         torch.cuda.synchronize(dev)
         return (time.perf_counter() - t0) / n, out
 
+    out = {}
     with torch.no_grad():
-        one_eval(sigmas[0])   # warm-up (cuDNN algorithm selection, allocator)
-        t_eval, d = timed(lambda: one_eval(sigmas[1]), sample_evals)
+        # ---- as written, fp32 ----
+        def eval_as_written(sigma):
+            tok = orc.process_radar_cond(sd, cube)
+            return orc.edm_precond(sd, lat * float(sigma), float(sigma), tok)
+        eval_as_written(sigmas[0])
+        t_eval, d = timed(lambda: eval_as_written(sigmas[1]), sample_evals)
         z = d[:, :, :32].contiguous()
         orc.ae_latent_stack(sd_ae, z)
         t_stack, x = timed(lambda: orc.ae_latent_stack(sd_ae, z))
         orc.ae_query(sd_ae, x, q)
         t_q, _ = timed(lambda: orc.ae_query(sd_ae, x, q))
-    t_step = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
+        t_step = NET_EVALS * t_eval + t_stack + t_q * (queries_total / sample_queries)
+        out["as_written_fp32"] = {
+            "value": frames / t_step, "unit": UNIT,
+            "sample": (f"{sample_evals} of {NET_EVALS} evaluations of a {frames}-frame batch with the radar encoder "
+                       f"inside ({t_eval * 1e3:.0f} ms each) + latent stack ({t_stack * 1e3:.0f} ms) + {sample_queries} "
+                       f"of {queries_total} queries per frame ({t_q * 1e3:.0f} ms), extrapolated linearly; torch "
+                       f"{torch.__version__} eager, fp32 defaults")}
+        # ---- hoisted, bf16 autocast, SDPA ----
+        saved = orc._heads_attention
+
+        def sdpa_heads(qq, kk, vv, heads):
+            B, Sq, D = qq.shape
+            dh = D // heads
+            qh = qq.view(B, Sq, heads, dh).transpose(1, 2)
+            kh = kk.view(B, -1, heads, dh).transpose(1, 2)
+            vh = vv.view(B, -1, heads, dh).transpose(1, 2)
+            return Fn.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, Sq, D)
+        orc._heads_attention = sdpa_heads
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                t_enc, tok = timed(lambda: orc.process_radar_cond(sd, cube))
+                t_enc, tok = timed(lambda: orc.process_radar_cond(sd, cube))
+                ev = lambda s: orc.edm_precond(sd, lat * float(s), float(s), tok)  # noqa: E731
+                ev(sigmas[0])
+                t_eval2, d = timed(lambda: ev(sigmas[1]), sample_evals)
+                z = d[:, :, :32].float().contiguous()
+                orc.ae_latent_stack(sd_ae, z)
+                t_stack2, x2 = timed(lambda: orc.ae_latent_stack(sd_ae, z))
+                orc.ae_query(sd_ae, x2, q)
+                t_q2, _ = timed(lambda: orc.ae_query(sd_ae, x2, q))
+        finally:
+            orc._heads_attention = saved
+        t_step2 = t_enc + NET_EVALS * t_eval2 + t_stack2 + t_q2 * (queries_total / sample_queries)
+        out["hoisted_bf16"] = {
+            "value": frames / t_step2, "unit": UNIT,
+            "sample": (f"encoder once ({t_enc * 1e3:.0f} ms) + {sample_evals} of {NET_EVALS} evaluations of a "
+                       f"{frames}-frame batch ({t_eval2 * 1e3:.1f} ms each) + latent stack ({t_stack2 * 1e3:.0f} ms) + "
+                       f"{sample_queries} of {queries_total} queries per frame ({t_q2 * 1e3:.0f} ms), extrapolated "
+                       f"linearly; torch.autocast(bfloat16) + F.scaled_dot_product_attention")}
     del sd, sd_ae
     torch.cuda.empty_cache()
-    return {"value": frames / t_step, "unit": UNIT, "kind": "port, PyTorch eager fp32 on the same GPU",
-            "sample": (f"{sample_evals} of {NET_EVALS} network evaluations of a {frames}-frame batch as the reference "
-                       f"runs them (radar encoder inside, {t_eval * 1e3:.0f} ms each) + latent stack "
-                       f"({t_stack * 1e3:.0f} ms) + {sample_queries} of {queries_total} decoder queries per frame "
-                       f"({t_q * 1e3:.0f} ms), extrapolated linearly; oracle port of the reference's modules on the "
-                       f"device, torch {torch.__version__} eager, matmul fp32 / cuDNN defaults")}
-
-
-def run_reference(args, rank, world=1):
-    if rank != 0:
-        return
-    t_all = time.perf_counter()
-    res = None
-    for _ in range(max(0, args.warmup - 1)):   # the sample has its own warm-up pass; keep extra ones cheap
-        pass
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        res = cpu_reference_sample(args.queries)
-        vals.append(res["value"])
-    value = statistics.median(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
-    line["cpu_baseline"]["value"] = value
-    print(json.dumps(line), flush=True)
-
-
-def workload_config(args, world):
-    return {"workload": ("configs[1]: DiT latent-set denoiser kl_d512_m512_l32_d24_edm, full 18-step EDM/Heun sampling "
-                         "loop (35 evaluations) from a synthetic radar RAE cube + kl_d512_m512_l32_mix decode, batch 1"
-                         if args.frames_per_gpu == 1 else
-                         f"configs[2]: batched generation, {args.frames_per_gpu} frames x full diffusion schedule "
-                         "(radar cube -> encoder -> 35 denoiser evaluations -> VecSet decode -> point cloud) per GPU, "
-                         "frame-sharded"),
-            "frames_per_gpu": args.frames_per_gpu, "global_frames": args.frames_per_gpu * world,
-            "queries_per_frame": args.queries, "num_steps": 18, "net_evals": NET_EVALS,
-            "parallelism": f"frames sharded over {world} GPU(s), final NCCL gather of point clouds" if world > 1
-            else "single GPU",
-            "l2": "no flush: each evaluation streams 0.33 GB of bf16 weights (> 126 MB L2) and the step reads "
-                  "0.55 GB of weights + fresh H2D inputs"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+def cuda_time(fn, reps: int, warm: int = 2) -> float:
+    """ms per call, CUDA events on the current stream, synchronised on both sides."""
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def leg_latency_b1(net, vae, dev, Q, cap, peaks):
+    """configs[1]: batch 1 through the same API, inputs resident. Its roofline is HBM: every evaluation streams the
+    0.33 GB of bf16 denoiser weights (more than the L2 holds), SURVEY.md §7.3 / BASELINE.md §3."""
+    from rald_b200 import postproc, synth
+    c1 = frame_cubes(0, 1).to(dev)
+    qq1 = synth.query_points(1, Q).to(dev)
+    s1 = torch.arange(1)
+
+    def step_b1():
+        z = net.sample(c1, batch_seeds=s1, cond_type="radar")
+        lg = vae.decode(z, qq1)
+        return postproc.occupied_points(lg, qq1, 0.0, PC_RANGE, True, False, True, capacity=cap)
+    ms1 = cuda_time(step_b1, 5, warm=3)
+    z1 = torch.randn(1, 512, 32, device=dev)
+    tok1 = net.process_radar_cond(c1)
+    ms_s = cuda_time(lambda: net.sample_from_latents(z1, tok1), 5, warm=3)
+    ms_eval = ms_s / NET_EVALS
+    gbs = DIT_WEIGHT_BYTES / (ms_eval * 1e-3) / 1e9
+    return {"workload": "configs[1]: batch 1, same pipeline", "ms_per_frame": ms1, "frames_per_s": 1000.0 / ms1,
+            "ms_per_sampler_step": ms_s / 18, "ms_per_net_eval": ms_eval,
+            "weight_streaming_floor_us_per_eval": DIT_WEIGHT_BYTES / (peaks["hbm_gbs"] * 1e9) * 1e6,
+            "roofline": {"kernel": "one network evaluation at batch 1 (264 dependent launches, CUDA-graph replay)",
+                         "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                         "algorithmic_bytes": DIT_WEIGHT_BYTES,
+                         "note": "bytes = the bf16 denoiser weights an evaluation must stream; latency-bound by "
+                                 "construction (M = 512 rows per GEMM)"}}
+
+
+def leg_ae_frame(dev, peaks):
+    """configs[0] on the GPU: VecSet encode + decode of ONE synthetic 10 000-point frame (10 000 queries), for the
+    default `mix` autoencoder and the FPS (`point`) variant; FPS kernel time from the library's per-launch events."""
+    from rald_b200 import _lib, models_ae, synth
+    out = {}
+    for name, qtype in (("kl_d512_m512_l32_mix", "mix"), ("kl_d512_m512_l32", "point")):
+        torch.manual_seed(SEED)
+        vae = models_ae.__dict__[name](N=10000).eval().to(dev)
+        pc = synth.lidar_points(1, 10000, seed=SEED).to(dev)
+        q = synth.query_points(1, 10000).to(dev)
+        noise = synth.posterior_noise(1).to(dev)
+        rt = vae._runtime()
+        holder = {}
+
+        def enc():
+            holder["z"] = rt.encode(pc, noise)[1]
+
+        def dec():
+            rt.clear_cache()
+            return vae.decode(holder["z"], q)
+        ms_enc = cuda_time(enc, 10)
+        ms_dec = cuda_time(dec, 10)
+        rec = {"encode_ms": ms_enc, "decode_ms": ms_dec, "frames_per_s": 1000.0 / (ms_enc + ms_dec)}
+        if qtype == "point":
+            _lib.prof_enable("fps")
+            enc()
+            ms_fps, work, n = _lib.prof_collect("fps")
+            _lib.prof_enable()
+            if n:
+                bw = work / (ms_fps * 1e-3)
+                rec["fps"] = {"us": ms_fps * 1e3 / n, "picks": 512, "points": 10000, "smem_bytes_swept": work / n,
+                              "smem_gb_per_s": bw / 1e9, "peak_one_sm_gb_per_s": SMEM_BW_PER_SM / 1e9,
+                              "frac_of_one_sm_smem_bw": bw / SMEM_BW_PER_SM,
+                              "note": "one CTA per cloud: 511 dependent picks, each sweeping 12 B x N of shared memory"}
+            # batched FPS: 64 clouds at once (one SM each)
+            pc64 = synth.lidar_points(64, 10000, seed=SEED).to(dev)
+            ms64 = cuda_time(lambda: rt.fps(pc64, 512), 5)
+            rec["fps_batch64"] = {"ms": ms64, "clouds_per_s": 64 / (ms64 * 1e-3)}
+        out[qtype] = rec
+        del vae
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_query_sweep(vae, dev, peaks):
+    """configs[3]: decoder queries at Q = 2^16 ... 2^20 per frame against ONE latent set (stack timed separately).
+    The executed (folded) formulation is tensor-bound: 0.5775 MFLOP and 16 B of mandatory HBM traffic per query."""
+    from rald_b200 import synth
+    rt = vae._runtime()
+    z = synth.posterior_noise(1, seed=11).to(dev)
+    ms_stack = cuda_time(lambda: rt.latent_stack(z), 5)
+    ctx = rt.context(z)
+    rows = []
+    for p in range(16, 21):
+        Q = 1 << p
+        q = synth.query_points(1, Q).to(dev)
+        ms = cuda_time(lambda: rt.query(ctx, q), 10)
+        tf = Q * MFLOP_PER_QUERY * 1e6 / (ms * 1e-3) / 1e12
+        rows.append({"queries": Q, "ms": ms, "queries_per_s": Q / (ms * 1e-3), "tflops": tf,
+                     "frac_of_sustained_bf16": tf / peaks["bf16_tflops_sustained"],
+                     "hbm_gb_per_s": Q * 16 / (ms * 1e-3) / 1e9})
+    return {"workload": "configs[3]: AE decoder dense query sweep, 1 frame vs 512 latents", "latent_stack_ms": ms_stack,
+            "mflop_per_query": MFLOP_PER_QUERY, "mandatory_bytes_per_query": 16, "sweep": rows}
+
+
+def leg_rooflines(step_fn, peaks, frames):
+    """One more step with CUDA events around every launch of the hot kernel families (graph replay off)."""
+    from rald_b200 import _lib
+    fams = ["gemm", "attn", "xattn", "ln", "boundary", "conv3d", "gn", "ae_query", "other"]
+    saved = os.environ.get("RALD_B200_GRAPH")
+    os.environ["RALD_B200_GRAPH"] = "0"      # per-launch events cannot be recorded inside a graph replay
+    try:
+        step_fn()
+        _lib.prof_enable(*fams)
+        step_fn()
+        gms, gwork = _lib.prof_dump("gemm")
+        breakdown = {}
+        for f in fams:
+            ms, work, n = _lib.prof_collect(f)
+            if n:
+                breakdown[f] = {"ms": ms, "launches": n, "work": work}
+        _lib.prof_enable()
+    finally:
+        if saved is None:
+            os.environ.pop("RALD_B200_GRAPH", None)
+        else:
+            os.environ["RALD_B200_GRAPH"] = saved
+    shapes = {}
+    for t, wk in zip(gms.tolist(), gwork.tolist()):
+        a = shapes.setdefault(wk, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+    gemm_shapes = [{"gflop_per_launch": round(wk / 1e9, 3), "launches": n, "ms": round(t, 3),
+                    "tflops": round(wk * n / (t * 1e-3) / 1e12, 1) if t > 0 else None}
+                   for wk, (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:8]
+    names = {"gemm": "gemm_bf16_kernel (tcgen05, all denoiser / AE linears)", "attn": "attn_d64_kernel (self-attention)",
+             "xattn": "xattn_fused_kernel (fused cross-attention sub-layer)", "conv3d": "conv3d_kernel (radar encoder)",
+             "ae_query": "ae_query_kernel (decoder queries, folded form)", "ln": "ln_rows_kernel (adaLN / LayerNorm)",
+             "gn": "gn_stats / gn_apply (GroupNorm + swish)", "boundary": "boundary_kernel (final LN + proj_out + EDM "
+             "precondition + Heun update + next proj_in)"}
+    total = sum(v["ms"] for v in breakdown.values())
+    rooflines = []
+    for f, v in breakdown.items():
+        v["share"] = round(v["ms"] / total, 4) if total else None
+        if f not in names or v["ms"] <= 0:
+            continue
+        tensor = f in ("gemm", "attn", "xattn", "conv3d", "ae_query")
+        rate = v["work"] / (v["ms"] * 1e-3) / (1e12 if tensor else 1e9)
+        peak = peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"]
+        if tensor:
+            v["tflops"] = round(rate, 1)
+        else:
+            v["gb_per_s"] = round(rate, 1)
+        rooflines.append({"kernel": names[f], "family": f, "bound": "tensor" if tensor else "hbm", "achieved": rate,
+                          "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s", "frac": rate / peak, "traffic": None,
+                          "share_of_step": v["share"], "launches_timed": v["launches"],
+                          "ms_per_launch": v["ms"] / v["launches"],
+                          "algorithmic_work_per_launch": v["work"] / v["launches"]})
+    for v in breakdown.values():
+        v["ms"] = round(v["ms"], 4)
+        del v["work"]
+    rooflines.sort(key=lambda r: -(r["share_of_step"] or 0))
+    main = next((dict(r) for r in rooflines if r["family"] == "gemm"), None)
+    if main is not None:
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh).get("gemm_bf16_kernel", {})
+            main["traffic"] = tj.get(f"frames_per_gpu={frames}")
+            main["traffic_source"] = ("STATIC: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed "
+                                      "ncu --set full capture named in profiles/roofline_traffic.json (not re-measured "
+                                      "by this run)") if main["traffic"] is not None else None
+        main["peak_source"] = f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)"
+        main["flop_per_launch"] = main["algorithmic_work_per_launch"]
+    return main, rooflines, breakdown, gemm_shapes
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from rald_b200 import _lib, gather, postproc, synth
@@ -310,40 +612,13 @@ def run_ours(args, rank, world, local_rank):
     _lib.lib()
     if args.no_graph:
         os.environ["RALD_B200_GRAPH"] = "0"
-    F, Q = args.frames_per_gpu, args.queries
-    net, vae = build_models(dev)
-    f0, f1 = rank * F, rank * F + F
-    seeds = torch.arange(f0, f1)
-    cube_h = synth.radar_cube(F, seed=SEED + rank).pin_memory()
-    q_h = synth.query_points(1, Q).pin_memory()   # ONE grid, repeated for every frame (engine_generation.py:259)
-    cube_d, q1_d = cube_h.to(dev), q_h.to(dev)
-    q_d = q1_d.expand(F, Q, 3).contiguous()
-    shift = calibrate_occupancy(net, vae, cube_d, q_d, seeds)
+    scaling, G, spans = plan(args, world)
+    Q = args.queries
     cap = max(1024, Q // 4)
-
-    def pipeline(cube, queries):
-        z = net.sample(cube, batch_seeds=seeds, cond_type="radar")
-        logits = vae.decode(z, queries)
-        pts, cnt, _ = postproc.occupied_points(logits, queries, 0.0, PC_RANGE, True, False, True, capacity=cap)
-        if world > 1:
-            pts, cnt = gather.gather_point_clouds(pts, cnt)
-        return pts, cnt
-
-    def step_resident():
-        return pipeline(cube_d, q_d)
-
-    d2h = [0]
-
-    def step_e2e():
-        cube_d.copy_(cube_h, non_blocking=True)
-        q1_d.copy_(q_h, non_blocking=True)
-        q_d.copy_(q1_d.expand(F, Q, 3))    # the grid is uploaded once and repeated on the device
-        pts, cnt = pipeline(cube_d, q_d)
-        n = cnt.cpu()                      # device -> host: per-frame point counts ...
-        out = [pts[i, :min(int(k), cap)].to("cpu", non_blocking=True) for i, k in enumerate(n.tolist())]
-        torch.cuda.current_stream().synchronize()   # ... and each frame's occupied points only
-        d2h[0] = n.numel() * 4 + sum(o.numel() for o in out) * 4
-        return out, n
+    net, vae = build_models(dev)
+    q_h = synth.query_points(1, Q).pin_memory()   # ONE grid, repeated for every frame (engine_generation.py:259)
+    q1_d = q_h.to(dev)
+    peaks = load_peaks()
 
     def barrier():
         if world > 1:
@@ -365,122 +640,147 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t)
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
+    class Shard:
+        """This rank's frames [f0, f1) of a job: resident inputs and the two step functions."""
+
+        def __init__(self, f0, f1, total):
+            self.f0, self.f1, self.F, self.total = f0, f1, f1 - f0, total
+            self.seeds = torch.arange(f0, f1)
+            self.cube_h = frame_cubes(f0, f1).pin_memory()
+            self.cube_d = self.cube_h.to(dev)
+            self.q_d = q1_d.expand(self.F, Q, 3).contiguous()
+            self.host = None
+            self.d2h = 0
+
+        def pipeline(self, cube, queries):
+            z = net.sample(cube, batch_seeds=self.seeds, cond_type="radar")
+            logits = vae.decode(z, queries)
+            pts, cnt, _ = postproc.occupied_points(logits, queries, 0.0, PC_RANGE, True, False, True, capacity=cap)
+            return gather.gather_point_clouds(pts, cnt)       # world == 1: local compaction only
+
+        def step_resident(self):
+            return self.pipeline(self.cube_d, self.q_d)
+
+        def step_e2e(self):
+            self.cube_d.copy_(self.cube_h, non_blocking=True)
+            q1_d.copy_(q_h, non_blocking=True)
+            self.q_d.copy_(q1_d.expand(self.F, Q, 3))    # the grid is uploaded once and repeated on the device
+            g = self.pipeline(self.cube_d, self.q_d)
+            # device -> host: every frame's occupied points of the WHOLE job (the per-frame counts / offsets already
+            # reached the host inside the gather), one copy into pinned memory
+            n = g.points.shape[0]
+            if self.host is None or self.host.shape[0] < n:
+                self.host = torch.empty(max(n, self.total * cap // 4), 3, dtype=torch.float32).pin_memory()
+            self.host[:n].copy_(g.points, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.d2h = n * 12 + g.counts.numel() * 8
+            return g
+
+    sh = Shard(*spans[rank], G)
+    # occupancy calibration (random-init logits are all slightly negative, SURVEY.md §7.3): shift to_outputs.bias by the
+    # 95-th percentile of one decode of GLOBAL frame 0, computed identically on every rank, so `logit > 0`
+    # (engine_generation.py:285) keeps ~5 % of the queries
+    z0 = net.sample(frame_cubes(0, 1).to(dev), batch_seeds=torch.arange(1), cond_type="radar")
+    lg0 = vae.decode(z0, q1_d).flatten()
+    sub = lg0[:: max(1, lg0.numel() // 65536)]
+    shift = float(sub.kthvalue(max(1, int(0.95 * sub.numel()))).values)
+    with torch.no_grad():
+        vae.to_outputs.bias -= shift
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        sh.step_resident()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     n0 = _lib.launch_count()
-    ms_res = timed(step_resident, args.steps)
+    ms_res = timed(sh.step_resident, args.steps)
     launches = (_lib.launch_count() - n0)
     for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+        sh.step_e2e()
+    ms_e2e = timed(sh.step_e2e, args.steps)
     clock_rec = clocks.stop() if rank == 0 else None
 
-    # ---- latency leg (configs[1], "ms per step"): batch 1 through the same API, inputs resident ----
-    lat = None
-    if F != 1:
-        c1, qq1, s1 = cube_d[:1].contiguous(), q_d[:1].contiguous(), seeds[:1]
-
-        def step_b1():
-            z = net.sample(c1, batch_seeds=s1, cond_type="radar")
-            lg = vae.decode(z, qq1)
-            return postproc.occupied_points(lg, qq1, 0.0, PC_RANGE, True, False, True, capacity=cap)
-        for _ in range(3):
-            step_b1()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            step_b1()
-        e1.record()
-        torch.cuda.synchronize()
-        ms1 = e0.elapsed_time(e1) / 5
-        lat = {"workload": "configs[1]: batch 1, same pipeline", "ms_per_frame": ms1, "frames_per_s": 1000.0 / ms1,
-               "ms_per_sampler_step": None}
-        z1 = torch.randn(1, 512, 32, device=dev)
-        tok1 = net.process_radar_cond(c1)
-        for _ in range(3):
-            net.sample_from_latents(z1, tok1)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            net.sample_from_latents(z1, tok1)
-        e1.record()
-        torch.cuda.synchronize()
-        lat["ms_per_sampler_step"] = e0.elapsed_time(e1) / 5 / 18
-        lat["ms_per_net_eval"] = e0.elapsed_time(e1) / 5 / NET_EVALS
-
-    # ---- roofline leg: one more step with CUDA events around every launch of the hot kernel families ----
-    fams = ["gemm", "attn", "xattn", "ln", "boundary", "conv3d", "gn", "ae_query", "other"]
-    os.environ["RALD_B200_GRAPH"] = "0"      # per-launch events cannot be recorded inside a graph replay
-    step_resident()
-    _lib.prof_enable(*fams)
-    step_resident()
-    gms, gwork = _lib.prof_dump("gemm")
-    shapes = {}
-    for t, wk in zip(gms.tolist(), gwork.tolist()):
-        a = shapes.setdefault(wk, [0, 0.0])
-        a[0] += 1
-        a[1] += t
-    gemm_shapes = [{"gflop_per_launch": round(wk / 1e9, 3), "launches": n, "ms": round(t, 3),
-                    "tflops": round(wk * n / (t * 1e-3) / 1e12, 1) if t > 0 else None}
-                   for wk, (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:8]
-    breakdown = {}
-    for f in fams:
-        ms, work, n = _lib.prof_collect(f)
-        if n:
-            breakdown[f] = {"ms": round(ms, 4), "launches": n, "work": work}
-    _lib.prof_enable()
-    peaks = load_peaks()
-    g = breakdown.get("gemm", {"ms": 0.0, "launches": 0, "work": 0.0})
-    achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = json.load(fh).get("gemm_bf16_kernel", {}).get(f"frames_per_gpu={F}")
-    roofline = {"kernel": "gemm_bf16_kernel (tcgen05, all denoiser/AE linears)", "bound": "tensor",
-                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
-                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_timed": g["launches"], "ms_per_launch": g["ms"] / max(1, g["launches"]),
-                "flop_per_launch": g["work"] / max(1, g["launches"])}
-    prof_total = sum(v["ms"] for v in breakdown.values())
-    for k, v in breakdown.items():
-        v["share"] = round(v["ms"] / prof_total, 4) if prof_total else None
-        if k in ("gemm", "attn", "xattn", "conv3d", "ae_query") and v["ms"] > 0:   # work = executed flops
-            v["tflops"] = round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)
-        elif k in ("ln", "gn") and v["ms"] > 0:                                   # work = algorithmic bytes
-            v["gb_per_s"] = round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1)
-        del v["work"]
-
-    frames_total = F * world * args.steps
+    frames_total = G * args.steps
     value = frames_total / (ms_res * 1e-3)
     e2e_v = frames_total / (ms_e2e * 1e-3)
-    gflop_step = F * (NET_EVALS * GFLOP_PER_EVAL + GFLOP_ENCODER + GFLOP_AE_STACK + Q * MFLOP_PER_QUERY * 1e-3)
+    gflop_frame = NET_EVALS * GFLOP_PER_EVAL + GFLOP_ENCODER + GFLOP_AE_STACK + Q * MFLOP_PER_QUERY * 1e-3
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world, scaling, G, spans),
+            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": sh.cube_h.numel() * 4 + q_h.numel() * 4, "d2h_bytes_per_step": sh.d2h,
+                    "note": "bytes of rank 0; every rank uploads its own shard and downloads the gathered clouds"},
+            "gpu_launches": int(launches), "tflops_step": G * gflop_frame / (ms_res / args.steps),
+            "clocks": clock_rec, "occupancy_bias_shift": shift,
+            "ae_precise_stack": os.environ.get("RALD_B200_AE_PRECISE", "1") != "0"}
+
+    # ---- N > 1: the sharded job must reproduce the single-rank clouds for the same global seeds ----
+    if world > 1 and not args.no_sharding_check:
+        g = sh.step_resident()
+        check = None
+        if rank == 0:
+            # same cross-attention formulation as the shards used (the fused kernel is only selected for >= 24 frames;
+            # the two formulations agree to bf16 level, not to the bit)
+            saved = os.environ.get("RALD_B200_FUSE_XATTN_MIN_FRAMES")
+            if sh.F < int(saved or "24"):
+                os.environ["RALD_B200_FUSE_XATTN_MIN_FRAMES"] = str(1 << 30)
+            try:
+                full = Shard(0, G, G)
+                z = net.sample(full.cube_d, batch_seeds=full.seeds, cond_type="radar")
+                lg = vae.decode(z, full.q_d)
+                pts, cnt, _ = postproc.occupied_points(lg, full.q_d, 0.0, PC_RANGE, True, False, True, capacity=cap)
+                cnt_h = cnt.cpu().tolist()
+                same = 0
+                for f in range(G):
+                    a, b = g.frame(f), pts[f, :cnt_h[f]]
+                    same += int(a.shape == b.shape and bool(torch.equal(a, b)))
+                check = {"global_frames": G, "frames_bit_identical": same, "identical": same == G,
+                         "points_total": int(sum(cnt_h)),
+                         "what": "gathered clouds of the sharded run vs all frames recomputed on rank 0 alone"}
+                del full, z, lg, pts
+            finally:
+                if saved is None:
+                    os.environ.pop("RALD_B200_FUSE_XATTN_MIN_FRAMES", None)
+                else:
+                    os.environ["RALD_B200_FUSE_XATTN_MIN_FRAMES"] = saved
+            torch.cuda.empty_cache()
+        line["sharding_check"] = check
+        barrier()
+
+    # ---- N > 1, strong mode: the weak figure (64 frames per GPU) as a secondary key ----
+    if world > 1 and scaling == "strong" and not args.no_weak and not args.quick:
+        Fw = args.global_frames
+        shw = Shard(rank * Fw, rank * Fw + Fw, Fw * world)
+        for _ in range(3):
+            shw.step_resident()
+        ms_w = timed(shw.step_resident, 3)
+        line["weak_scaling"] = {"frames_per_gpu": Fw, "global_frames": Fw * world, "ms_per_step": ms_w / 3,
+                                "value": Fw * world * 3 / (ms_w * 1e-3), "unit": UNIT, "steps": 3}
+        del shw
+        torch.cuda.empty_cache()
+
+    if not args.quick:
+        main, rooflines, breakdown, gemm_shapes = leg_rooflines(sh.step_resident, peaks, sh.F)
+        line.update({"roofline": main, "rooflines": rooflines, "kernel_breakdown": breakdown,
+                     "gemm_shapes": gemm_shapes})
+        if rank == 0 and world == 1:
+            if sh.F != 1:
+                line["latency_b1"] = leg_latency_b1(net, vae, dev, Q, cap, peaks)
+            line["query_sweep"] = leg_query_sweep(vae, dev, peaks)
+            line["ae_frame"] = leg_ae_frame(dev, peaks)
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, world),
-                "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": cube_h.numel() * 4 + q_h.numel() * 4, "d2h_bytes_per_step": d2h[0]},
-                "gpu_launches": int(launches),
-                "latency_b1": lat, "tflops_step": gflop_step / (ms_res / args.steps),
-                "roofline": roofline, "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes, "clocks": clock_rec,
-                "occupancy_bias_shift": shift}
-        if world == 1 and not args.no_gpu_eager_baseline:
+        if world == 1 and not args.quick and not args.no_gpu_eager_baseline:
             # after the timed regions; a failure here (e.g. out of memory next to the resident models) only drops the key
             try:
-                line["gpu_eager_baseline"] = gpu_eager_port_sample(dev, Q)
+                line["gpu_eager_baseline"] = gpu_eager_baselines(dev, Q)
             except Exception as e:  # noqa: BLE001
                 line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
                 torch.cuda.empty_cache()
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_sample(Q)
+        if world == 1 and not args.quick and not args.no_cpu_baseline:
+            cb = cpu_reference_frame(Q)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "hoisted_value")}
+            line["cpu_baseline"]["ae_frame"] = cpu_ae_frame()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

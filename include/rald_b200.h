@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RALD_ABI_VERSION 2
+#define RALD_ABI_VERSION 3
 
 int rald_abi_version(void);
 const char* rald_last_error(void);
@@ -33,6 +33,9 @@ uint64_t rald_launch_count(void);
 /* Accounts for kernels launched by replaying a CUDA graph captured from this library's calls (the host runtime adds
  * the number of launches it counted during capture at every replay). */
 void rald_launch_count_add(uint64_t n);
+/* TMA descriptor cache of the library (keyed on pointer + geometry, mutex-guarded): encodes avoided /
+ * performed since the process started. */
+int rald_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 
 /* Per-launch timing for bench.py's roofline leg: rald_prof_enable(mask) starts a session that brackets every launch
  * of the kernel families in `mask` (bit = family id below) with CUDA events on the launching stream (0 = off);
@@ -69,6 +72,16 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
  * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                            const float* bias, int M, int N, int K, int f16_start, int f16_period, void* stream);
+
+/* Split-weight GEMM: W_hilo is bf16 [N][2*K] = [W_hi | W_lo] with W_hi = bf16(W), W_lo = bf16(W - W_hi) (16 mantissa
+ * bits of the fp32 nn.Linear weight); out = epilogue(A W_hi^T + A W_lo^T) in ONE fp32 accumulator, the A tiles being
+ * read twice. out_mode as rald_gemm_bf16; f16_period > 0 selects fp16 columns as rald_gemm_bf16_f16cols (0: none);
+ * gelu_exact != 0: the GEGLU epilogue evaluates the erf GELU (A&S 7.1.26, |error| <= 1.5e-7). Used for the 24-layer
+ * latent stack of KLAutoEncoder.decode (model/models_ae.py:410-414), whose bf16 weight rounding is otherwise a
+ * common-mode error of the whole occupancy field. */
+int rald_gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw, void* out, int64_t ldo,
+                          const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
+                          int f16_start, int f16_period, int gelu_exact, void* stream);
 
 /* Debug hook: when dev_buf != NULL every GEMM CTA stores %globaltimer stamps of its first tile at dev_buf[cta*8 + i]
  * (0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done, 6 exit). */
@@ -167,11 +180,12 @@ typedef struct rald_dit_workspace {
   float* x_tmp;  /* [T][channels] */
   float* d_tmp;  /* [T][channels] */
   /* optional (NULL = unfused attn2 path): context operands of the fused cross-attention, built by rald_xattn_fold
-   * for xattn_frames frames; frame f of a call to rald_dit_forward / rald_dit_sample uses entry f of them */
+   * for xattn_frames frames; frame f of a call to rald_dit_forward / rald_dit_sample uses entry xattn_frame0 + f of
+   * them (xattn_frame0 > 0: the call processes a sub-batch of the sample, e.g. one of several concurrent chains) */
   const void* xattn_kp;   /* bf16 [depth][8][xattn_frames][64][dim] */
   const void* xattn_vt;   /* fp16 [depth][8][dim][xattn_frames*64] */
   int32_t xattn_frames;
-  int32_t _pad2;
+  int32_t xattn_frame0;
 } rald_dit_workspace;
 
 /* One EDMPrecond.forward (model/models_radar_generation.py:412-430) for `frames` frames given precomputed
@@ -211,7 +225,9 @@ int rald_xattn_debug_buffer(unsigned long long* dev_buf);
 
 /* ---- VecSet autoencoder (model/models_ae.py) ---- */
 typedef struct rald_ae_weights {
-  int32_t depth, dim, heads, latent_dim, n_latents, _pad;
+  int32_t depth, dim, heads, latent_dim, n_latents;
+  int32_t precise;     /* 0: bf16 weights, logistic-form GELU. 1: every weight matrix below is a split pair
+                        * [rows][2*cols] = [W_hi | W_lo] (rald_gemm_bf16_wsplit) and the GEGLU uses the erf GELU */
   /* bf16, stacked over depth */
   const void* w_qkv;   /* [depth][3*dim][dim]  layers.N.0.fn: to_q | to_kv (k rows, then v rows) */
   const void* w_o;     /* [depth][dim][dim]    layers.N.0.fn.to_out.weight */

@@ -146,22 +146,31 @@ def stacked_randn(seeds: Sequence[int], shape: Sequence[int]) -> torch.Tensor:
 
 def edm_sample(sd: SD, latents: torch.Tensor, cond_tokens: torch.Tensor, num_steps: int = 18,
                sigma_min: float = 0.002, sigma_max: float = 80.0, rho: float = 7.0, heads: int = 8,
-               trace: Optional[list] = None, stop_after: Optional[int] = None) -> torch.Tensor:
-    """edm_sampler with S_churn = 0 (gamma = 0, x_hat = x_cur), models_radar_generation.py:235-275.
+               trace: Optional[list] = None, stop_after: Optional[int] = None, S_churn: float = 0.0,
+               S_min: float = 0.0, S_max: float = float("inf"), S_noise: float = 1.0,
+               noises: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """edm_sampler, models_radar_generation.py:235-275. With S_churn = 0 (the reference default) gamma = 0 and
+    x_hat = x_cur; with churn (:254-260) the per-step noise randn_like(x_cur) is injected through `noises` (one
+    tensor per step, drawn by the caller in the reference's order).
     `cond_tokens` is process_radar_cond(cube): it depends only on the cube, so evaluating it once instead of
     inside every net() call (reference :414-415) is bit-identical."""
     t_steps = karras_sigmas(num_steps, sigma_min, sigma_max, rho)
     x_next = latents.to(torch.float32) * t_steps[0]
     for i in range(num_steps):
         t_cur, t_next = t_steps[i], t_steps[i + 1]
-        x_hat = x_next
-        denoised = edm_precond(sd, x_hat, t_cur, cond_tokens, heads=heads)
-        d_cur = (x_hat - denoised) / t_cur
-        x_next = x_hat + (t_next - t_cur) * d_cur
+        if S_churn > 0:
+            gamma = min(S_churn / num_steps, math.sqrt(2) - 1) if S_min <= float(t_cur) <= S_max else 0.0
+            t_hat = torch.as_tensor(t_cur + gamma * t_cur)
+            x_hat = x_next + (t_hat ** 2 - t_cur ** 2).sqrt() * S_noise * noises[i]
+        else:
+            t_hat, x_hat = t_cur, x_next
+        denoised = edm_precond(sd, x_hat, t_hat, cond_tokens, heads=heads)
+        d_cur = (x_hat - denoised) / t_hat
+        x_next = x_hat + (t_next - t_hat) * d_cur
         if i < num_steps - 1:
             denoised = edm_precond(sd, x_next, t_next, cond_tokens, heads=heads)
             d_prime = (x_next - denoised) / t_next
-            x_next = x_hat + (t_next - t_cur) * (0.5 * d_cur + 0.5 * d_prime)
+            x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
         if trace is not None:
             trace.append(x_next.clone())
         if stop_after is not None and i + 1 >= stop_after:  # tests: only the first steps of the full schedule

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "rald_last_error": [],
     "rald_launch_count": [],
     "rald_launch_count_add": [ctypes.c_uint64],
+    "rald_tmap_cache_stats": [c_void_p, c_void_p],
     "rald_prof_enable": [ctypes.c_uint],
     "rald_prof_collect": [c_int, c_void_p, c_void_p, c_void_p],
     "rald_prof_dump": [c_int, c_void_p, c_void_p, c_i64],
@@ -31,6 +32,8 @@ _SIGNATURES = {
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rald_gemm_bf16_f16cols": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_void_p],
+    "rald_gemm_bf16_wsplit": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
+                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_debug_buffer": [c_void_p],
     "rald_xattn_debug_buffer": [c_void_p],
@@ -90,6 +93,22 @@ _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, 
 
 class RaldError(RuntimeError):
     pass
+
+
+class RuntimeNotCopied:
+    """Mixin of the per-module runtimes (packed device weights, workspaces, ctypes structs, CUDA graphs): they are
+    derived state, so ``copy.deepcopy(module)`` (ema_model = deepcopy(model)) and pickling (torch.save(module)) drop
+    them — the copy rebuilds its own runtime lazily on first use."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_no_runtime, ())
+
+
+def _no_runtime():
+    return None
 
 
 def lib() -> ctypes.CDLL:

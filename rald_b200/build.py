@@ -1,6 +1,7 @@
 """Builds rald_b200/_C/librald_b200.so from rald_b200/csrc/*.cu with nvcc for sm_100a.
 
-In-tree, incremental (per-file object cache keyed on source + header mtimes), parallel. The built
+In-tree, incremental (per-file object cache keyed on source + header mtimes and a hash of the compiler flags),
+parallel, serialised across processes by a file lock. The built
 library travels to the GPU box with the repository snapshot; nothing is JIT-compiled at run time.
 
     python -m rald_b200.build [--force] [--verbose]
@@ -8,6 +9,8 @@ library travels to the GPU box with the repository snapshot; nothing is JIT-comp
 from __future__ import annotations
 
 import concurrent.futures as cf
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -44,18 +47,47 @@ def _newest_header_mtime() -> float:
 
 
 def _compile_one(src: Path, obj: Path, verbose: bool) -> str:
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    tmp = obj.with_suffix(f".{os.getpid()}.tmp.o")
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("RALD_B200_NVCC_FLAGS", "").split(), "-c", str(src), "-o", str(tmp)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, obj)
     (obj.with_suffix(".ptxas.txt")).write_text(res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
     return src.name
 
 
+def _flags_key() -> str:
+    """Hash of everything besides the sources that decides what an object file contains: the nvcc command line
+    (incl. RALD_B200_NVCC_FLAGS, e.g. -DRALD_GELU_LOGISTIC=0) and the compiler version."""
+    extra = os.environ.get("RALD_B200_NVCC_FLAGS", "")
+    try:
+        ver = subprocess.run([_nvcc(), "--version"], capture_output=True, text=True).stdout
+    except OSError:
+        ver = ""
+    return hashlib.sha256(("\0".join(NVCC_FLAGS) + "\0" + extra + "\0" + ver).encode()).hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Serialised across processes by an exclusive file lock (every rank of a torchrun job may find the library
+    missing at the same time); objects and the library are written to temporaries and renamed into place."""
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    with open(OUT_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    key = _flags_key()
+    key_file = OBJ_DIR / ".flags"
+    if not key_file.exists() or key_file.read_text() != key:
+        force = True   # objects built with other flags (or another nvcc) are stale whatever their mtimes say
     srcs = sorted(CSRC.glob("*.cu"))
     if not srcs:
         raise RuntimeError(f"no CUDA sources under {CSRC}")
@@ -72,11 +104,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             for name in ex.map(lambda a: _compile_one(a[0], a[1], verbose), todo):
                 if verbose:
                     print(f"[rald_b200.build] compiled {name}")
+        key_file.write_text(key)
     if todo or not LIB_PATH.exists():
-        cmd = [_nvcc(), "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
+        tmp = LIB_PATH.with_suffix(f".{os.getpid()}.tmp.so")
+        cmd = [_nvcc(), "-shared", "-o", str(tmp), *map(str, objs), "-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+        os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -137,23 +137,44 @@ extern "C" int rald_ae_stack(const rald_ae_weights* w, const rald_dit_workspace*
       RALD_CHECK_CUDA(cudaMemcpyAsync(h, z + (int64_t)f0 * M * dim, sizeof(float) * T * dim, cudaMemcpyDeviceToDevice, st));
     }
     const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws->qkv);
+    // precise: split weight pairs [rows][2 cols] (twice the elements per layer) + erf GELU, see rald_ae_weights
+    const int wm = w->precise ? 2 : 1;
     for (int n = 0; n < w->depth; ++n) {
-      const __nv_bfloat16* w_qkv = reinterpret_cast<const __nv_bfloat16*>(w->w_qkv) + (int64_t)n * 3 * dim * dim;
-      const __nv_bfloat16* w_o = reinterpret_cast<const __nv_bfloat16*>(w->w_o) + (int64_t)n * dim * dim;
-      const __nv_bfloat16* w_ff1 = reinterpret_cast<const __nv_bfloat16*>(w->w_ff1) + (int64_t)n * 8 * dim * dim;
-      const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w->w_ff2) + (int64_t)n * 4 * dim * dim;
+      const __nv_bfloat16* w_qkv = reinterpret_cast<const __nv_bfloat16*>(w->w_qkv) + (int64_t)n * 3 * dim * dim * wm;
+      const __nv_bfloat16* w_o = reinterpret_cast<const __nv_bfloat16*>(w->w_o) + (int64_t)n * dim * dim * wm;
+      const __nv_bfloat16* w_ff1 = reinterpret_cast<const __nv_bfloat16*>(w->w_ff1) + (int64_t)n * 8 * dim * dim * wm;
+      const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w->w_ff2) + (int64_t)n * 4 * dim * dim * wm;
       RALD_TRY(ln_rows(h, dim, w->ln1_w + (int64_t)n * dim, w->ln1_b + (int64_t)n * dim, 0, 0, 0, ws->xn, dim, 0, T,
                        dim, 1e-5f, st));
-      RALD_TRY(gemm_bf16_f16cols(ws->xn, dim, w_qkv, dim, ws->qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
+      if (w->precise) {
+        RALD_TRY(gemm_bf16_wsplit(ws->xn, dim, w_qkv, 2 * dim, ws->qkv, 3 * dim, nullptr, nullptr, 0, (int)T, 3 * dim,
+                                  dim, 0, 2 * dim, 3 * dim, 0, st));
+      } else {
+        RALD_TRY(gemm_bf16_f16cols(ws->xn, dim, w_qkv, dim, ws->qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim,
+                                   3 * dim, st));
+      }
       RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws->att, dim, nf, heads, M, M, scale,
                         st));
-      RALD_TRY(gemm_bf16(ws->att, dim, w_o, dim, h, dim, w->b_o + (int64_t)n * dim, h, dim, (int)T, dim, dim, 1, 0, st));
+      if (w->precise) {
+        RALD_TRY(gemm_bf16_wsplit(ws->att, dim, w_o, 2 * dim, h, dim, w->b_o + (int64_t)n * dim, h, dim, (int)T, dim,
+                                  dim, 1, 0, 0, 0, st));
+      } else {
+        RALD_TRY(gemm_bf16(ws->att, dim, w_o, dim, h, dim, w->b_o + (int64_t)n * dim, h, dim, (int)T, dim, dim, 1, 0,
+                           st));
+      }
       RALD_TRY(ln_rows(h, dim, w->ln2_w + (int64_t)n * dim, w->ln2_b + (int64_t)n * dim, 0, 0, 0, ws->xn, dim, 0, T,
                        dim, 1e-5f, st));
-      RALD_TRY(gemm_bf16(ws->xn, dim, w_ff1, dim, ws->ff, 4 * dim, w->b_ff1 + (int64_t)n * 8 * dim, nullptr, 0, (int)T,
-                         8 * dim, dim, 2, 0, st));
-      RALD_TRY(gemm_bf16(ws->ff, 4 * dim, w_ff2, 4 * dim, h, dim, w->b_ff2 + (int64_t)n * dim, h, dim, (int)T, dim,
-                         4 * dim, 1, 0, st));
+      if (w->precise) {
+        RALD_TRY(gemm_bf16_wsplit(ws->xn, dim, w_ff1, 2 * dim, ws->ff, 4 * dim, w->b_ff1 + (int64_t)n * 8 * dim, nullptr,
+                                  0, (int)T, 8 * dim, dim, 2, 0, 0, 1, st));
+        RALD_TRY(gemm_bf16_wsplit(ws->ff, 4 * dim, w_ff2, 8 * dim, h, dim, w->b_ff2 + (int64_t)n * dim, h, dim, (int)T,
+                                  dim, 4 * dim, 1, 0, 0, 0, st));
+      } else {
+        RALD_TRY(gemm_bf16(ws->xn, dim, w_ff1, dim, ws->ff, 4 * dim, w->b_ff1 + (int64_t)n * 8 * dim, nullptr, 0, (int)T,
+                           8 * dim, dim, 2, 0, st));
+        RALD_TRY(gemm_bf16(ws->ff, 4 * dim, w_ff2, 4 * dim, h, dim, w->b_ff2 + (int64_t)n * dim, h, dim, (int)T, dim,
+                           4 * dim, 1, 0, st));
+      }
     }
   }
   return 0;

@@ -23,6 +23,13 @@ int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ld
                                  static_cast<cudaStream_t>(stream));
 }
 
+int rald_gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw, void* out, int64_t ldo,
+                          const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
+                          int f16_start, int f16_period, int gelu_exact, void* stream) {
+  return rald::gemm_bf16_wsplit(A, lda, W_hilo, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, f16_start,
+                                f16_period, gelu_exact, static_cast<cudaStream_t>(stream));
+}
+
 int rald_attn_d64(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                   int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* stream) {
   return rald::attn_d64(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, Skv, scale,

@@ -28,17 +28,9 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
   const int64_t ld_ctx = (int64_t)depth * 2 * dim;
   const __nv_bfloat16* ctx = reinterpret_cast<const __nv_bfloat16*>(ctxkv);
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws.qkv);
-  // Optional (RALD_B200_WPREFETCH=1): in the latency-bound small-batch regime every weight comes from DRAM (0.33 GB
-  // per evaluation > L2), so each GEMM can prefetch the weights of the GEMM after it into L2. Measured on B200 at
-  // batch 1: 55.6 ms -> 76 ms per frame (prefetch issued at kernel entry: it competes with the kernel's own
-  // latency-critical loads) / 83 ms (issued after the operands landed: it delays the kernel's completion, which the
-  // programmatic-dependent successor waits for). Off by default.
-  static const bool pf_env = [] { const char* e = getenv("RALD_B200_WPREFETCH"); return e != nullptr && e[0] == '1'; }();
-  const bool pf = pf_env && T <= 2048;
-  const size_t wsz = (size_t)dim * dim * 2;  // one dim x dim bf16 matrix
   // attn2 as ONE kernel against the folded context operands (xattn.cu) when the caller supplied them
-  const bool fused_x = ws.xattn_kp != nullptr && ws.xattn_vt != nullptr && L == 64 && heads == 8 && dim == 512 &&
-                       xattn_fusion_enabled();
+  // (the caller decides: registering the operands in the workspace IS the switch; check_common validates the shape)
+  const bool fused_x = ws.xattn_kp != nullptr;
   const int64_t x_blk = (int64_t)8 * ws.xattn_frames * 64 * dim;  // elements of one block's kp (= vt) slice
   for (int n = 0; n < depth; ++n) {
     const float* m0 = mod + ((int64_t)n * 3 + 0) * 2 * dim;
@@ -53,11 +45,9 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
     // x += attn1(adaLN1(x))
     RALD_TRY(ln_rows(ws.h, dim, m0, m0 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
     // q | k in bf16, v in fp16 (attn_d64 multiplies fp16 probabilities with fp16 values)
-    if (pf) gemm_prefetch_next(w_o1, wsz);
     RALD_TRY(gemm_bf16_f16cols(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
     RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws.att, dim, frames, heads, M, M,
                       scale, st));
-    if (pf) gemm_prefetch_next(w_q2, wsz);
     RALD_TRY(gemm_bf16(ws.att, dim, w_o1, dim, ws.h, dim, w.b_o1 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
                        0, st));
     // x += attn2(adaLN2(x), context)
@@ -65,9 +55,8 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
     if (fused_x) {
       RALD_TRY(xattn_fused(ws.xn, reinterpret_cast<const __nv_bfloat16*>(ws.xattn_kp) + (int64_t)n * x_blk,
                            reinterpret_cast<const __nv_bfloat16*>(ws.xattn_vt) + (int64_t)n * x_blk,
-                           w.b_o2 + (int64_t)n * dim, ws.h, frames, M, frame0, ws.xattn_frames, st));
+                           w.b_o2 + (int64_t)n * dim, ws.h, frames, M, ws.xattn_frame0 + frame0, ws.xattn_frames, st));
     } else {
-      if (pf) gemm_prefetch_next(w_o2, wsz);
       RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
       if (L <= 512) {
         RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx,
@@ -80,18 +69,13 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
                                ws.att, dim, frames, heads, M, L, scale, ws.ff,
                                reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(ws.qkv) + T * dim), st));
       }
-      if (pf) gemm_prefetch_next(w_ff1, 8 * wsz);
       RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
                          0, st));
     }
     // x += ff(adaLN3(x))
     RALD_TRY(ln_rows(ws.h, dim, m2, m2 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
-    if (pf) gemm_prefetch_next(w_ff2, 4 * wsz);
     RALD_TRY(gemm_bf16(ws.xn, dim, w_ff1, dim, ws.ff, 4 * dim, w.b_ff1 + (int64_t)n * 8 * dim, nullptr, 0, (int)T,
                        8 * dim, dim, 2, 0, st));
-    if (pf)  // next block's (or, after the last block, the next evaluation's first) QKV weights
-      gemm_prefetch_next(reinterpret_cast<const __nv_bfloat16*>(w.w_qkv) + (int64_t)((n + 1) % depth) * 3 * dim * dim,
-                         3 * wsz);
     RALD_TRY(gemm_bf16(ws.ff, 4 * dim, w_ff2, 4 * dim, ws.h, dim, w.b_ff2 + (int64_t)n * dim, ws.h, dim, (int)T, dim,
                        4 * dim, 1, 0, st));
   }
@@ -130,7 +114,7 @@ static void set_h_persistence(const rald_dit_workspace& ws, int dim, int n_laten
   cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
-static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws, int frames) {
+static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws, const void* ctxkv, int frames) {
   RALD_REQUIRE(w != nullptr && ws != nullptr, "dit: null weights/workspace");
   RALD_REQUIRE(w->dim == 512, "dit: dim=%d unsupported (512 only)", w->dim);
   RALD_REQUIRE(w->heads * 64 == w->dim, "dit: head_dim must be 64 (heads=%d dim=%d)", w->heads, w->dim);
@@ -140,8 +124,13 @@ static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws,
                    (w->ctx_len <= 512 || (w->ctx_len % 512 == 0 && w->ctx_len <= 2048)),
                "dit: context length %d unsupported (multiple of 64 up to 512, or 1024 / 1536 / 2048)", w->ctx_len);
   RALD_REQUIRE(frames > 0 && ws->max_frames > 0, "dit: frames=%d micro-batch=%d", frames, ws->max_frames);
-  RALD_REQUIRE(ws->xattn_kp == nullptr || ws->xattn_frames >= frames,
-               "dit: fused cross-attention operands cover %d frames, %d requested", ws->xattn_frames, frames);
+  RALD_REQUIRE(ws->xattn_kp == nullptr || (ws->xattn_frame0 >= 0 && ws->xattn_frames >= ws->xattn_frame0 + frames),
+               "dit: fused cross-attention operands cover %d frames, [%d, %d) requested", ws->xattn_frames,
+               ws->xattn_frame0, ws->xattn_frame0 + frames);
+  RALD_REQUIRE(ws->xattn_kp == nullptr || (ws->xattn_vt != nullptr && w->ctx_len == 64 && w->heads == 8),
+               "dit: fused cross-attention operands need both K' and VT, 64 context tokens and 8 heads");
+  RALD_REQUIRE(ws->xattn_kp != nullptr || ctxkv != nullptr,
+               "dit: neither context K/V projections nor fused cross-attention operands were supplied");
   return 0;
 }
 
@@ -152,7 +141,7 @@ using namespace rald;
 extern "C" int rald_dit_forward(const rald_dit_weights* w, const rald_dit_workspace* ws, const float* x,
                                 const float* sigma, int64_t sigma_stride, const float* mod,
                                 int64_t mod_frame_stride, const void* ctxkv, float* out, int frames, void* stream) {
-  RALD_TRY(check_common(w, ws, frames));
+  RALD_TRY(check_common(w, ws, ctxkv, frames));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int M = w->n_latents, C = w->channels, dim = w->dim;
   const int64_t ctx_rows = w->ctx_len;
@@ -178,7 +167,7 @@ extern "C" int rald_dit_forward(const rald_dit_weights* w, const rald_dit_worksp
 extern "C" int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspace* ws, const float* latents,
                                const float* sigmas, int num_steps, const float* mod, const void* ctxkv, float* x_out,
                                float* trace, int frames, void* stream) {
-  RALD_TRY(check_common(w, ws, frames));
+  RALD_TRY(check_common(w, ws, ctxkv, frames));
   RALD_REQUIRE(num_steps >= 1, "dit_sample: num_steps=%d", num_steps);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int M = w->n_latents, C = w->channels, dim = w->dim;

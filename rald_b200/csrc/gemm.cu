@@ -26,63 +26,28 @@ namespace rald {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-// RALD_GEMM_PRODUCERS = 2: a second TMA producer warp (warp 10) issues the W tiles while warp 0 issues the A tiles.
-// One thread issues a cp.async.bulk.tensor every ~125 ns (measured: "ring-issued" stamp of tools/gemm_phases.py — the
-// 16 loads of a K = 512 tile take 2.0 us to ISSUE, whatever the box sizes, tile shape, CTA count or ring depth), which
-// is what paces the main loop of the latency-bound batch-1 GEMMs (0.25 us per k-block).
-#ifndef RALD_GEMM_PRODUCERS
-#define RALD_GEMM_PRODUCERS 1
-#endif
-constexpr int GEMM_THREADS = 320 + 32 * (RALD_GEMM_PRODUCERS - 1);  // TMA warp, MMA warp, 8 epilogue warps (, W producer)
+constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int EPI_GENERIC = 0, EPI_TMA_STORE = 1, EPI_TMA_REDUCE = 2;
 constexpr int STG_BYTES = 32 * 128;  // one staging tile: 32 rows x 128 bytes
-// staging tiles per epilogue warp: 2 was measured no faster for the K = 512 GEMMs and slower for K = 2048 (one ring
-// stage less): FF1 127.6 vs 128.5, QKV 49.2 vs 49.4, FF2 66.1 vs 64.2 us at M = 32768
-// 1: one 128-row TMA store per column chunk (four warps share a staging tile, two named barriers per chunk) instead
-// of four 32-row stores. Parity-green, measured NOT faster (QKV 50.9 vs 49.4, O1 28.8 vs 26.9 us at M = 32768): the
-// ~11 us the store path adds to every large GEMM is not the TMA issue rate of small boxes.
-#ifndef RALD_GEMM_WIDE_STORE
-#define RALD_GEMM_WIDE_STORE 0
-#endif
-constexpr bool GEMM_WIDE_STORE = RALD_GEMM_WIDE_STORE != 0;
-#ifndef RALD_GEMM_NBUF
-#define RALD_GEMM_NBUF 1
-#endif
 
 // CG = 1: one CTA computes a 128 x BN tile. CG = 2: a CTA pair (cta_group::2, the two SMs of a TPC) computes a
 // 256 x BN tile with ONE 256-row MMA per K step; each CTA stages its 128 rows of A and only HALF of the W tile, so
 // the shared-memory fill traffic per flop drops by a third and the ring gets deeper.
-//
-// ARES (A-resident, K = 512): the 128 x 512 A block of a row block (128 KB) is loaded ONCE and stays in shared memory
-// while the W tiles of all the column tiles this unit owns of that row block stream through the ring. Each unit walks a
-// contiguous, balanced range of the row-block-major tile order. The L2 -> SM operand traffic of a wide GEMM drops by
-// almost half (FF1: 8 MB -> 4.25 MB per 256-row block). MEASURED on B200 at M = 32768: parity-green but NOT faster
-// (FF1 124.3 vs 122.8 us, QKV 47.3 vs 47.8 us, N = 512: 34.5 vs 31.1 us) — operand delivery is not what holds these
-// kernels at ~2x the tcgen05 issue floor (every shape runs at 2.0x: FF1 4.64 us per 256 x 256 x 512 tile against
-// 2.35 us, FF2 18.5 against 9.4). Off by default; RALD_B200_GEMM_ARES=1 enables it for N >= 1024, =2 for all N.
-constexpr int ARES_K = 512;
-constexpr int ARES_BYTES = GEMM_BM * ARES_K * 2;
-// BM = 64 (CG = 1, generic epilogue only): half-height tiles for the latency-bound batch-1 regime (twice the CTAs,
-// 40 % fewer operand bytes per CTA). The K order is unchanged: results are bit-identical to the 128-row tiles
-// (tools/gpu_check_bm64.py). Measured not faster, off by default — see the selection in gemm_impl. Accumulator layout of an M = 64 MMA: row 16 j + i -> TMEM lane 32 j + i (the lower half of every
-// lane quarter), so epilogue warp q owns rows [16 q, 16 q + 16) and its lanes 16..31 read nothing useful.
-template <int BN, int CG = 1, bool ARES = false, int BM = GEMM_BM>
+// Variants measured and rejected in round 1 (A-resident K = 512 form, 64-row tiles, 128-row TMA stores, a second TMA
+// producer warp, L2 prefetch of the next GEMM's weights, 16 ring stages) are documented in DESIGN.md §7 and live in
+// the git history (commit 8837a6c); they are no longer compiled.
+template <int BN, int CG = 1>
 struct GemmCfg {
-  static constexpr int A_BYTES = BM * GEMM_BK * 2;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = ARES ? B_BYTES : A_BYTES + B_BYTES;
-  static constexpr int A_RES_BYTES = ARES ? ARES_BYTES : 0;
-  static constexpr int NBUF = ARES ? 1 : RALD_GEMM_NBUF;       // staging tiles per epilogue warp
-  static constexpr int STG_TOTAL = GEMM_EPI_WARPS * NBUF * STG_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_TOTAL = GEMM_EPI_WARPS * STG_BYTES;   // one staging tile per epilogue warp
   static constexpr int BIAS_BYTES = 2 * BN * 4;
   // no alignment slack: dynamic shared memory starts 1024-byte aligned (checked at kernel entry)
-  static constexpr int FIXED = 512 /*barriers*/ + STG_TOTAL + BIAS_BYTES + A_RES_BYTES;
+  static constexpr int FIXED = 512 /*barriers*/ + STG_TOTAL + BIAS_BYTES;
   static constexpr int STAGES_RAW = (232448 - FIXED) / STAGE_BYTES;
-#ifndef RALD_GEMM_MAX_STAGES
-#define RALD_GEMM_MAX_STAGES 8
-#endif
-  static constexpr int STAGES = STAGES_RAW > RALD_GEMM_MAX_STAGES ? RALD_GEMM_MAX_STAGES : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(2 * STAGES + 7 <= 64, "barrier block too small");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
@@ -96,21 +61,19 @@ struct GemmParams {
   int64_t ldr;
   int64_t resid_mod;   // > 0: residual row = row % resid_mod (a [resid_mod, N] table broadcast over frames)
   int M, N, K;
+  int a_k;             // columns of A. a_k == K: plain GEMM. a_k == K / 2: SPLIT WEIGHTS — W holds [W_hi | W_lo]
+                       // (two bf16 matrices whose sum carries 16 mantissa bits) along K and the A tile of k-block kb
+                       // is read at column (kb * 64) % a_k, i.e. out = A W_hi^T + A W_lo^T in one accumulator
   int num_m_blks, num_n_blks;
-  const uint8_t* pf_ptr;      // weights of the NEXT GEMM in the stream, prefetched into L2 by this kernel's idle
-  uint32_t pf_bytes;          // epilogue threads (small-batch regime: hides the DRAM latency of the next launch)
   int f16_start, f16_period;  // bf16 mode: output columns with (col % f16_period) >= f16_start are written as fp16
   int w_static;               // W does not depend on the preceding kernel: its first ring stages are loaded BEFORE the
                               // programmatic-dependency wait (hides the DRAM latency of the weights behind the
-                              // predecessor's tail in the latency-bound small-batch regime); CG = 1, !ARES only
-  int skip_epilogue;          // DEBUG (RALD_B200_GEMM_SKIP_EPI=1): accumulators are released unread, nothing is stored —
-                              // isolates the TMA + MMA main loop for timing (tools/gemm_phases_big.py); results are garbage
+                              // predecessor's tail in the latency-bound small-batch regime); CG = 1 only
+  int gelu_exact;             // GEGLU epilogue: erf GELU (A&S 7.1.26, fp32 round-off level) instead of the logistic fit
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
 static unsigned long long* g_gemm_dbg = nullptr;
-static thread_local const void* g_pf_ptr = nullptr;   // consumed by the next GEMM launch of this thread
-static thread_local size_t g_pf_bytes = 0;
 static thread_local int g_w_static = 0;               // GemmStaticWeights scopes alive on this thread
 #define GEMM_STAMP(slot)                                                        \
   do {                                                                          \
@@ -165,8 +128,13 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
     // GEGLU: within every packed 32-column group, columns [0,16) are the value half and [16,32) the gate half
     // of the same 16 output features (reference: x, gate = proj(x).chunk(2); x * gelu(gate)).
     float o[16];
+    if (p.gelu_exact) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_act(__uint_as_float(v[16 + j]));
+      for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_erf(__uint_as_float(v[16 + j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * gelu_act(__uint_as_float(v[16 + j]));
+    }
     if (row_ok) {
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col0 >> 1));
 #pragma unroll
@@ -179,52 +147,46 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 }
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
-template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM, int G>
+template <int BN, int OUT_MODE, int EPI, int CG, int G>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, ARES, BM>;
-  static_assert(BM == 128 || (BM == 64 && CG == 1 && !ARES && EPI == EPI_GENERIC), "64-row tiles: CG = 1, generic epilogue");
+  using Cfg = GemmCfg<BN, CG>;
   // G k-blocks share one ring slot = ONE full / empty barrier pair: the MMA thread then probes an mbarrier once per
   // 4 G MMAs instead of once per 4. Measured (tools/micro/mma_rate.cu): a try_wait on an ALREADY COMPLETE mbarrier
   // between groups of 4 MMAs costs the issuing thread ~260 cycles (490 cycles per 64-wide k-block in all, whatever
   // N) — more than the 180 cycles of tensor work of a k-block at N = 32 and barely less than the 512 at N = 256.
-  static_assert(G == 1 || !ARES, "grouped ring slots are not combined with the A-resident form");
   static_assert(Cfg::STAGES % G == 0 || G == 1, "ring depth must be a multiple of the group");
   constexpr int SLOTS = Cfg::STAGES / G;
   constexpr int SLOT_BYTES = G * Cfg::STAGE_BYTES;
+  constexpr int BM = GEMM_BM;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
   const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-processing unit (CTA or CTA pair)
   const int num_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int TILE_M = BM * CG;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NBUF = Cfg::NBUF;
   // accumulator columns consumed per staged 128-byte output row
   constexpr int CHUNK = OUT_MODE == 1 ? 32 : (OUT_MODE == 0 ? 64 : 128);
   static_assert(EPI == EPI_GENERIC || BN % CHUNK == 0, "tile narrower than one staged output row");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128-byte swizzle atoms need 1024-byte aligned tiles
-  uint8_t* a_res = smem + STAGES * Cfg::STAGE_BYTES;                  // ARES: the resident A block (1024-aligned)
-  uint8_t* stg = a_res + Cfg::A_RES_BYTES;                            // 1024-byte aligned (stage sizes are)
+  uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES;                    // 1024-byte aligned (stage sizes are)
   float* s_bias = reinterpret_cast<float*>(stg + Cfg::STG_TOTAL);     // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* a_full_bar = tmem_empty_bar + 2;    // ARES: resident A block landed (both CTAs' rows when CG = 2)
-  uint64_t* a_empty_bar = a_full_bar + 1;       // ARES: every MMA reading the resident A block has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_blks * p.num_n_blks;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  // Tile walk of this unit. Default: tiles unit, unit + num_units, ... ARES: the contiguous, balanced range
-  // [unit * T / U, (unit + 1) * T / U) of the row-block-major order (consecutive tiles share the resident A block).
-  const int t_begin = ARES ? (int)(((long long)unit * num_tiles) / num_units) : unit;
-  const int t_end = ARES ? (int)(((long long)(unit + 1) * num_tiles) / num_units) : num_tiles;
-  const int t_step = ARES ? 1 : num_units;
+  // tile walk of this unit: tiles unit, unit + num_units, ...
+  const int t_begin = unit, t_end = num_tiles, t_step = num_units;
+  // A column of k-block kb (split weights: the A tiles are re-read for the second half of K)
+  auto a_col = [&](int kb) { const int c = kb * GEMM_BK; return c >= p.a_k ? c - p.a_k : c; };
 
   if (threadIdx.x == 0) {
     GEMM_STAMP(0);
@@ -239,8 +201,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], GEMM_EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs)
     }
-    mbar_init(a_full_bar, 1);
-    mbar_init(a_empty_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -257,9 +217,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr bool SPLIT = RALD_GEMM_PRODUCERS == 2 && !ARES;   // W tiles come from warp 10
   int w_pre = 0;            // ring stages whose W tile is already in flight (producer thread only)
-  if (!SPLIT && CG == 1 && !ARES && p.w_static != 0 && threadIdx.x == 0) {
+  if (CG == 1 && p.w_static != 0 && threadIdx.x == 0) {
     // static weights: the W tiles of this CTA's first SLOTS ring slots do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
     while (w_pre < SLOTS && tile < t_end) {
@@ -274,9 +233,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kb == num_kb) { kb = 0; tile += t_step; }
     }
   }
-  // A (and an in-place residual) come from the preceding kernel; static weights do not, so a dedicated W producer
-  // starts streaming them right away
-  if (!(SPLIT && warp == 10 && p.w_static != 0)) pdl_wait();
+  // A (and an in-place residual) come from the preceding kernel
+  pdl_wait();
   pdl_launch_dependents();  // the next kernel may set itself up on idle SMs while this one runs
 
   if (warp == 0) {
@@ -285,26 +243,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       GEMM_STAMP(1);
       int s = 0;
       uint32_t ph = 0;
-      int seg = -1, seg_m = -1;   // ARES: index / row block of the resident A block
       for (int tile = t_begin; tile < t_end; tile += t_step) {
         const int m_blk = tile / p.num_n_blks;
         const int n_blk = tile - m_blk * p.num_n_blks;
-        if (ARES && m_blk != seg_m) {
-          // new row block: the resident A buffer is free once every MMA of the previous one has completed
-          ++seg;
-          seg_m = m_blk;
-          mbar_wait(a_empty_bar, ((uint32_t)seg & 1u) ^ 1u);
-          if (CG == 2) {
-            if (cta_rank == 0) mbar_arrive_expect_tx(a_full_bar, 2 * ARES_BYTES);
-            for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
-              tma_load_2d_pair(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK,
-                               m_blk * TILE_M + (int)cta_rank * BM);
-          } else {
-            mbar_arrive_expect_tx(a_full_bar, ARES_BYTES);
-            for (int kb = 0; kb < ARES_K / GEMM_BK; ++kb)
-              tma_load_2d(a_res + kb * Cfg::A_BYTES, &tmA, a_full_bar, kb * GEMM_BK, m_blk * BM);
-          }
-        }
         for (int kb = 0; kb < num_kb; kb += G) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* slot = smem + s * SLOT_BYTES;
@@ -315,24 +256,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
-              uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
-              if (!ARES) tma_load_2d_pair(sa, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * TILE_M + (int)cta_rank * BM);
-              if (!SPLIT) tma_load_2d_pair(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
+              tma_load_2d_pair(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * TILE_M + (int)cta_rank * BM);
+              tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, &full_bar[s], (kb + g) * GEMM_BK,
+                               n_blk * BN + (int)cta_rank * (BN / 2));
             }
           } else if (w_pre > 0) {
             // transaction bytes announced and W tiles issued before the dependency wait: only A is left
             --w_pre;
 #pragma unroll
             for (int g = 0; g < G; ++g)
-              tma_load_2d(slot + g * Cfg::STAGE_BYTES, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * BM);
+              tma_load_2d(slot + g * Cfg::STAGE_BYTES, &tmA, &full_bar[s], a_col(kb + g), m_blk * BM);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], SLOT_BYTES);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
-              uint8_t* sb = ARES ? sa : sa + Cfg::A_BYTES;
-              if (!ARES) tma_load_2d(sa, &tmA, &full_bar[s], (kb + g) * GEMM_BK, m_blk * BM);
-              if (!SPLIT) tma_load_2d(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
+              tma_load_2d(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * BM);
+              tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
             }
           }
           if (++s == SLOTS) {
@@ -343,27 +283,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (SPLIT && warp == 10) {
-    // ===================== second TMA producer: W tiles =====================
-    // (their transaction bytes are announced by warp 0's arrive.expect_tx on the same barrier; a complete_tx that
-    // lands first only makes the pending count transiently negative, the phase cannot flip before that arrive)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = t_begin; tile < t_end; tile += t_step) {
-        const int n_blk = tile % p.num_n_blks;
-        for (int kb = 0; kb < num_kb; kb += G) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            uint8_t* sb = smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-            if (CG == 2) tma_load_2d_pair(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / 2));
-            else tma_load_2d(sb, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
-          }
-          if (++s == SLOTS) { s = 0; ph ^= 1; }
-        }
-      }
-    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {
@@ -371,24 +290,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      int seg = -1, seg_m = -1;
       for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
-        if (ARES) {
-          const int m_blk = tile / p.num_n_blks;
-          if (m_blk != seg_m) {
-            // every MMA of the previous row block has been issued: its A block is free once they complete
-            if (seg >= 0) {
-              if (CG == 2) tc_commit_pair(a_empty_bar);
-              else tc_commit(a_empty_bar);
-            }
-            ++seg;
-            seg_m = m_blk;
-            mbar_wait(a_full_bar, (uint32_t)seg & 1u);
-            tc_fence_after();
-          }
-        }
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -398,11 +302,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (it == 0 && kb == 0) GEMM_STAMP(2);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const uint32_t sst = smem_u32(smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES);
-            const uint32_t sa = ARES ? smem_u32(a_res) + (uint32_t)(kb + g) * Cfg::A_BYTES : sst;
-            const uint32_t sb = ARES ? sst : sst + Cfg::A_BYTES;
+            const uint32_t sa = smem_u32(smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES);
             const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
-            const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
+            const uint64_t b_desc = make_sdesc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
               // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
@@ -422,17 +324,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (it == 0) GEMM_STAMP(3);
       }
     }
-  } else if (warp < 10) {
+  } else {
     // ===================== epilogue (warps 2..9) =====================
     // Two warps per TMEM lane quarter: warp pair member `hs` takes the even / odd column chunks of the tile.
     const int q = warp & 3;          // TMEM lane quarter this warp is allowed to touch
     const int ew = warp - 2;         // 0..7
     const int hs = ew >> 2;          // 0: even chunks, 1: odd chunks
-    const int row_in_tile = BM == 64 ? q * 16 + lane : q * 32 + lane;
-    const bool lane_ok = BM == 128 || lane < 16;   // M = 64 accumulators live in the lower half of each lane quarter
+    const int row_in_tile = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
-    int sbuf = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       const int m_blk = tile / p.num_n_blks;
       const int n_blk = tile - m_blk * p.num_n_blks;
@@ -455,29 +355,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       if (it == 0 && threadIdx.x == 64) GEMM_STAMP(4);
-      if (p.skip_epilogue == 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release_acc();
-        continue;
-      }
-      if (it == 0 && p.pf_bytes != 0) {
-        // This CTA's own operands have landed (its first accumulator is complete): now pull the NEXT GEMM's weights
-        // into L2, 16 KB per request, spread over the epilogue threads of all CTAs. Issued here rather than at kernel
-        // entry so that the prefetch does not compete with this kernel's own latency-critical loads.
-        constexpr uint32_t PF_CHUNK = 16384;
-        const uint32_t nreq = (p.pf_bytes + PF_CHUNK - 1) / PF_CHUNK;
-        for (uint32_t r = blockIdx.x * 256u + (uint32_t)et; r < nreq; r += gridDim.x * 256u) {
-          const uint32_t off = r * PF_CHUNK;
-          const uint32_t len = (p.pf_bytes - off) < PF_CHUNK ? (p.pf_bytes - off) & ~15u : PF_CHUNK;
-          if (len != 0)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + off), "r"(len) : "memory");
-        }
-      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (EPI == EPI_GENERIC) {
         const int64_t row = static_cast<int64_t>(m_blk) * TILE_M + cta_rank * BM + row_in_tile;
-        const bool row_ok = lane_ok && row < p.M;
+        const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int c = hs; c < BN / 32; c += 2) {
           const int col0 = n_blk * BN + c * 32;
@@ -525,19 +406,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           } else {
+            const bool exact = p.gelu_exact != 0;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               uint32_t v[32];
               tmem_ld32(t_row + acol0 + 32 * h, v);
               tmem_ld_wait();
               const float* bs = bias_s + acol0 + 32 * h;
+              if (exact) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float a0 = (__uint_as_float(v[2 * j]) + bs[2 * j]) *
-                                 gelu_act(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
-                const float a1 = (__uint_as_float(v[2 * j + 1]) + bs[2 * j + 1]) *
-                                 gelu_act(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
-                o[8 * h + j] = pack_bf16x2(a0, a1);
+                for (int j = 0; j < 8; ++j) {
+                  const float a0 = (__uint_as_float(v[2 * j]) + bs[2 * j]) *
+                                   gelu_erf(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
+                  const float a1 = (__uint_as_float(v[2 * j + 1]) + bs[2 * j + 1]) *
+                                   gelu_erf(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
+                  o[8 * h + j] = pack_bf16x2(a0, a1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float a0 = (__uint_as_float(v[2 * j]) + bs[2 * j]) *
+                                   gelu_act(__uint_as_float(v[16 + 2 * j]) + bs[16 + 2 * j]);
+                  const float a1 = (__uint_as_float(v[2 * j + 1]) + bs[2 * j + 1]) *
+                                   gelu_act(__uint_as_float(v[16 + 2 * j + 1]) + bs[16 + 2 * j + 1]);
+                  o[8 * h + j] = pack_bf16x2(a0, a1);
+                }
               }
             }
           }
@@ -547,35 +440,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) release_acc();
           }
-          if (p.skip_epilogue == 2) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x ^= o[j];
-            if (x == 0x12345678u) p.dbg[0] = x;   // keeps the arithmetic alive
-          } else if (live && GEMM_WIDE_STORE) {
-            // One 128-row TMA store per column chunk instead of four 32-row ones: the four warps owning the four TMEM
-            // lane quarters of this chunk parity share a 16 KB staging tile (small boxes made the TMA store rate the
-            // pace of the K = 512 GEMMs' epilogue). Two 128-thread named barriers per chunk: staging free / rows written.
-            uint8_t* gstg = stg + hs * (4 * STG_BYTES);
-            if (q == 0 && lane == 0) bulk_wait_group_read<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + hs) : "memory");
-            const uint32_t sdst = smem_u32(gstg) + (uint32_t)(q * 32 + lane) * 128u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            fence_proxy_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + hs) : "memory");
-            if (q == 0 && lane == 0) {
-              const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
-              const int orow = m_blk * TILE_M + (int)cta_rank * BM;
-              if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, gstg, ocol, orow);
-              else tma_store_2d(&tmO, gstg, ocol, orow);
-              bulk_commit_group();
-            }
-          } else if (live) {
-            if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the staging tile about to be overwritten was read
+          if (live) {
+            if (lane == 0) bulk_wait_group_read<0>();  // the staging tile about to be overwritten was read
             __syncwarp();
-            const uint32_t sdst = smem_u32(stg + (ew * NBUF + sbuf) * STG_BYTES) + lane * 128;
+            const uint32_t sdst = smem_u32(stg + ew * STG_BYTES) + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -583,12 +451,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
               const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
-              const void* src = stg + (ew * NBUF + sbuf) * STG_BYTES;
+              const void* src = stg + ew * STG_BYTES;
               if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, src, ocol, row0);
               else tma_store_2d(&tmO, src, ocol, row0);
               bulk_commit_group();
             }
-            if (NBUF == 2) sbuf ^= 1;
           }
         }
       }
@@ -608,12 +475,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int OUT_MODE, int EPI, int CG, bool ARES, int BM, int G>
+template <int BN, int OUT_MODE, int EPI, int CG, int G>
 static int launch_gemm_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
-                       int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, ARES, BM>;
+                         int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
   static_assert(Cfg::STAGES >= 3, "ring too shallow");
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, ARES, BM, G>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, G>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -629,57 +496,86 @@ static int launch_gemm_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   return 0;
 }
 
+// environment switches of this file, read once per process
+struct GemmEnv {
+  bool group, pair, wpre;
+  GemmEnv() {
+    auto on = [](const char* name) { const char* e = getenv(name); return e == nullptr || e[0] != '0'; };
+    group = on("RALD_B200_GEMM_GROUP");   // =0: one k-block per ring slot
+    pair = on("RALD_B200_GEMM_PAIR");     // =0: no CTA-pair tiles
+    wpre = on("RALD_B200_GEMM_WPRE");     // =0: no early weight loads
+  }
+};
+static const GemmEnv& gemm_env() {
+  static const GemmEnv env;
+  return env;
+}
+
 // Picks the ring-slot group (k-blocks per full / empty barrier pair, see the kernel): the largest the ring depth
-// allows when K is a multiple of it. RALD_B200_GEMM_GROUP=0 forces one k-block per slot.
-template <int BN, int OUT_MODE, int EPI, int CG = 1, bool ARES = false, int BM = GEMM_BM>
+// allows when K is a multiple of it.
+template <int BN, int OUT_MODE, int EPI, int CG = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                        int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, ARES, BM>;
-  constexpr int GMAX = (ARES || EPI == EPI_GENERIC) ? 1
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr int GMAX = EPI == EPI_GENERIC ? 1
                        : (Cfg::STAGES >= 8 && Cfg::STAGES % 4 == 0) ? 4
                        : (Cfg::STAGES >= 4 && Cfg::STAGES % 2 == 0) ? 2 : 1;
-  static const bool group_env = [] { const char* e = getenv("RALD_B200_GEMM_GROUP"); return e == nullptr || e[0] != '0'; }();
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  if (GMAX > 1 && group_env && num_kb % GMAX == 0)
-    return launch_gemm_g<BN, OUT_MODE, EPI, CG, ARES, BM, GMAX>(tmA, tmB, tmO, p, max_ctas, stream);
-  return launch_gemm_g<BN, OUT_MODE, EPI, CG, ARES, BM, 1>(tmA, tmB, tmO, p, max_ctas, stream);
+  if (GMAX > 1 && gemm_env().group && num_kb % GMAX == 0)
+    return launch_gemm_g<BN, OUT_MODE, EPI, CG, GMAX>(tmA, tmB, tmO, p, max_ctas, stream);
+  return launch_gemm_g<BN, OUT_MODE, EPI, CG, 1>(tmA, tmB, tmO, p, max_ctas, stream);
 }
 
 GemmStaticWeights::GemmStaticWeights() { ++g_w_static; }
 GemmStaticWeights::~GemmStaticWeights() { --g_w_static; }
 
-void gemm_prefetch_next(const void* weights, size_t bytes) {
-  g_pf_ptr = weights;
-  g_pf_bytes = bytes;
-}
+struct GemmOpts {
+  int64_t resid_mod = 0;
+  int f16_start = 0, f16_period = 0;
+  int w_split = 0;      // W is [N][2 K] = [W_hi | W_lo]
+  int gelu_exact = 0;
+};
+
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
+                     const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
+                     const GemmOpts& o, cudaStream_t stream);
 
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
               const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
               cudaStream_t stream) {
-  return gemm_bf16_ex(A, lda, W, ldw, out, ldo, bias, resid, ldr, 0, M, N, K, out_mode, bn_hint, stream);
+  return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, bn_hint, GemmOpts(), stream);
 }
-
-static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
-                     const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
-                     int f16_start, int f16_period, cudaStream_t stream);
 
 int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                  const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
                  cudaStream_t stream) {
-  return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, resid_mod, M, N, K, out_mode, bn_hint, 0, 0, stream);
+  GemmOpts o;
+  o.resid_mod = resid_mod;
+  return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, bn_hint, o, stream);
 }
 
 int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                       int M, int N, int K, int f16_start, int f16_period, cudaStream_t stream) {
-  RALD_REQUIRE(f16_period > 0 && f16_period % 64 == 0 && f16_start % 64 == 0 && f16_start < f16_period,
-               "gemm: fp16 column window start=%d period=%d must be multiples of 64", f16_start, f16_period);
-  RALD_REQUIRE(N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
-  return gemm_impl(A, lda, W, ldw, out, ldo, bias, nullptr, 0, 0, M, N, K, 0, 0, f16_start, f16_period, stream);
+  GemmOpts o;
+  o.f16_start = f16_start;
+  o.f16_period = f16_period;
+  return gemm_impl(A, lda, W, ldw, out, ldo, bias, nullptr, 0, M, N, K, 0, 0, o, stream);
+}
+
+int gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw, void* out, int64_t ldo,
+                     const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
+                     int f16_start, int f16_period, int gelu_exact, cudaStream_t stream) {
+  GemmOpts o;
+  o.f16_start = f16_start;
+  o.f16_period = f16_period;
+  o.w_split = 1;
+  o.gelu_exact = gelu_exact;
+  return gemm_impl(A, lda, W_hilo, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, 0, o, stream);
 }
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
-                     const float* resid, int64_t ldr, int64_t resid_mod, int M, int N, int K, int out_mode, int bn_hint,
-                     int f16_start, int f16_period, cudaStream_t stream) {
+                     const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
+                     const GemmOpts& o, cudaStream_t stream) {
   RALD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RALD_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   RALD_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
@@ -690,6 +586,11 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(resid == nullptr || ((reinterpret_cast<uintptr_t>(resid) & 15) == 0 && ldr % 4 == 0),
                "gemm: residual not 16-byte aligned");
   RALD_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16-byte aligned");
+  RALD_REQUIRE(o.f16_period == 0 || (o.f16_period % 64 == 0 && o.f16_start % 64 == 0 && o.f16_start < o.f16_period),
+               "gemm: fp16 column window start=%d period=%d must be multiples of 64", o.f16_start, o.f16_period);
+  RALD_REQUIRE(o.f16_period == 0 || N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
+  RALD_REQUIRE(!o.w_split || K % GEMM_BK == 0, "gemm: split weights need K=%d to be a multiple of %d", K, GEMM_BK);
+  const int k_total = o.w_split ? 2 * K : K;   // k extent the main loop walks
 
   const int sms = device_sm_count();
   const int m_blks = (M + GEMM_BM - 1) / GEMM_BM;
@@ -713,42 +614,16 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   int epi = EPI_GENERIC;
   if (out_mode == 1) {
     if (resid == nullptr) epi = EPI_TMA_STORE;
-    else if (resid == out && ldr == ldo && resid_mod == 0) epi = EPI_TMA_REDUCE;
+    else if (resid == out && ldr == ldo && o.resid_mod == 0) epi = EPI_TMA_REDUCE;
   } else if (out_mode == 0) {
     if (resid == nullptr && bn >= 64) epi = EPI_TMA_STORE;
   } else if (bn >= 128) {
     epi = EPI_TMA_STORE;
   }
 
-  // 64-row tiles (see GemmCfg): latency-bound small problems whose 64 x bn tiling still fits one wave. Same cost
-  // model with the per-CTA operand height halved.
-  bool bm64 = false;
-  {
-    // MEASURED on B200 at batch 1: parity bit-exact, but 58.2 vs 55.8 ms per frame — the batch-1 main loop takes
-    // ~0.25 us per k-block whatever the tile shape, CTA count (16..128), ring depth (8 / 16 stages) or number of
-    // producer threads, so halving the rows per CTA buys nothing and the direct-store epilogue costs 1.2 us more than
-    // the TMA one. Off by default; RALD_B200_GEMM_BM64=1 enables it.
-    static const bool bm64_env = [] { const char* e = getenv("RALD_B200_GEMM_BM64"); return e != nullptr && e[0] == '1'; }();
-    if (bm64_env && bn_hint == 0 && out_mode != 2 && f16_period == 0) {
-      const long m_blks64 = (M + 63) / 64;
-      long best = (((long)m_blks * (N / bn) + sms - 1) / sms) * (64 + bn);
-      for (int cand = 64; cand >= 32; cand >>= 1) {
-        if (N % cand != 0 || m_blks64 * (N / cand) > sms) continue;
-        const long cost = 32 + cand;
-        if (cost < best) { best = cost; bn = cand; bm64 = true; }
-      }
-      if (bm64) epi = EPI_GENERIC;
-    }
-  }
-
   // CTA pairs: 256 x 256 tiles when the problem still fills the machine with them (large-batch regime)
-  static int pair_env = -1;
-  if (pair_env < 0) {
-    const char* e = getenv("RALD_B200_GEMM_PAIR");
-    pair_env = (e == nullptr || e[0] != '0') ? 1 : 0;
-  }
   const int m_blks2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-  const bool pair = pair_env == 1 && bn_hint >= 0 && bn == 256 && epi != EPI_GENERIC && N % 256 == 0 &&
+  const bool pair = gemm_env().pair && bn_hint >= 0 && bn == 256 && epi != EPI_GENERIC && N % 256 == 0 &&
                     (long)m_blks2 * (N / 256) >= sms / 2;
 
   GemmParams p;
@@ -757,64 +632,34 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.bias = bias;
   p.resid = resid;
   p.ldr = ldr;
-  p.resid_mod = resid_mod;
+  p.resid_mod = o.resid_mod;
   p.M = M;
   p.N = N;
-  p.K = K;
-  p.num_m_blks = pair ? m_blks2 : (bm64 ? (M + 63) / 64 : m_blks);
+  p.K = k_total;
+  p.a_k = K;
+  p.num_m_blks = pair ? m_blks2 : m_blks;
   p.num_n_blks = (N + bn - 1) / bn;
   p.dbg = g_gemm_dbg;
-  p.f16_start = f16_start;
-  p.f16_period = f16_period;
-  {
-    const char* e = getenv("RALD_B200_GEMM_SKIP_EPI");
-    p.skip_epilogue = e != nullptr ? (e[0] - '0') : 0;   // 1: no epilogue at all; 2: TMEM reads + arithmetic, no stores
-  }
-  {
-    // RALD_B200_GEMM_WPRE=0 disables the early weight loads
-    static const bool wpre_env = [] { const char* e = getenv("RALD_B200_GEMM_WPRE"); return e == nullptr || e[0] != '0'; }();
-    p.w_static = (wpre_env && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
-  }
-  p.pf_ptr = static_cast<const uint8_t*>(g_pf_ptr);
-  p.pf_bytes = (uint32_t)(g_pf_bytes > 0xfffffff0ull ? 0 : g_pf_bytes);
-  g_pf_ptr = nullptr;
-  g_pf_bytes = 0;
-  RALD_REQUIRE(f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
+  p.f16_start = o.f16_start;
+  p.f16_period = o.f16_period;
+  p.gelu_exact = o.gelu_exact;
+  p.w_static = (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
+  RALD_REQUIRE(o.f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;
-  RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, bm64 ? 64u : (uint32_t)GEMM_BM));
-  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
+  RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, (uint32_t)GEMM_BM));
+  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)k_total, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
   if (epi != EPI_GENERIC) {
-    RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1,
-                           GEMM_WIDE_STORE ? 128u : 32u));
+    RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1, 32u));
   } else {
     tmO = tmA;
   }
 
-  // A-resident form for the K = 512 pair GEMMs (off by default, see GemmCfg)
-  static int ares_env = -1;
-  if (ares_env < 0) {
-    const char* e = getenv("RALD_B200_GEMM_ARES");
-    ares_env = e == nullptr ? 0 : (e[0] - '0');
-  }
-  if (pair && K == ARES_K && ares_env >= 1 && (N >= 1024 || ares_env >= 2)) {
-    if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2, true>(tmA, tmB, tmO, p, sms, stream);
-    if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2, true>(tmA, tmB, tmO, p, sms, stream);
-    if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2, true>(tmA, tmB, tmO, p, sms, stream);
-  }
   if (pair) {
     if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2>(tmA, tmB, tmO, p, sms, stream);
     return launch_gemm<256, 1, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
-  }
-  if (bm64) {
-    if (out_mode == 1) {
-      if (bn == 32) return launch_gemm<32, 1, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
-      return launch_gemm<64, 1, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
-    }
-    if (bn == 32) return launch_gemm<32, 0, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
-    return launch_gemm<64, 0, EPI_GENERIC, 1, false, 64>(tmA, tmB, tmO, p, sms, stream);
   }
 #define RALD_GEMM_LAUNCH(BN_, MODE_, EPI_) return launch_gemm<BN_, MODE_, EPI_>(tmA, tmB, tmO, p, sms, stream)
 #define RALD_GEMM_BN(MODE_, EPI_)                   \

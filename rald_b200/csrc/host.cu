@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rald_b200.h"
@@ -38,8 +39,61 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Descriptor cache: a tensor map is a pure function of (data type, base pointer, dims, strides, box,
+// element strides) — no device state — so the encoded 128 bytes are memoised under exactly that key; a buffer that is
+// freed and reallocated at the same address with the same geometry gets the same (still valid) descriptor. The hot
+// loops re-present the same few hundred (pointer, shape) pairs on every call (workspaces and packed weights), so after
+// the first evaluation no launch pays for cuTensorMapEncodeTiled (~1.5 us each, 3 per GEMM) any more.
+struct TmapKey {
+  uint64_t w[16];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t v : k.w) { h ^= v; h *= 0x100000001b3ull; h ^= h >> 29; }
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t TMAP_CACHE_MAX = 8192;
+static std::atomic<uint64_t> g_tmap_hits{0}, g_tmap_misses{0};
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
 static int encode(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  RALD_REQUIRE(rank >= 1 && rank <= 5, "TMA rank %d unsupported", rank);
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.w[0] = reinterpret_cast<uint64_t>(base);
+  key.w[1] = ((uint64_t)dt << 8) | (uint64_t)rank;
+  for (int i = 0; i < rank; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[11 + i] = ((uint64_t)box[i] << 32) | (uint64_t)(elem_strides ? elem_strides[i] : 1u);
+  }
+  for (int i = 0; i + 1 < rank; ++i) key.w[7 + i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  RALD_TRY(encode_uncached(out, dt, base, rank, dims, strides_bytes, box, elem_strides));
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= TMAP_CACHE_MAX) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   RALD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   RALD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
@@ -154,6 +208,11 @@ int device_sm_count() {
 }  // namespace rald
 
 extern "C" uint64_t rald_launch_count(void) { return rald::g_launches.load(); }
+extern "C" int rald_tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  if (hits) *hits = rald::g_tmap_hits.load();
+  if (misses) *misses = rald::g_tmap_misses.load();
+  return 0;
+}
 extern "C" void rald_launch_count_add(uint64_t n) { rald::g_launches.fetch_add(n); }
 
 extern "C" int rald_prof_enable(unsigned family_mask) {

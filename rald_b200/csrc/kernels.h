@@ -25,9 +25,14 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
 int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                       int M, int N, int K, int f16_start, int f16_period, cudaStream_t stream);
 
-// Hint for the NEXT gemm launch issued by this thread: while it runs, its idle epilogue threads prefetch `bytes` of
-// `weights` (the operand of the GEMM after it) into L2. Used by the small-batch denoiser loop.
-void gemm_prefetch_next(const void* weights, size_t bytes);
+// SPLIT WEIGHTS: W_hilo is [N][2 K] = [W_hi | W_lo], two bf16 matrices whose sum carries 16 mantissa bits of the fp32
+// weight; out = A W_hi^T + A W_lo^T accumulated in one fp32 TMEM accumulator (the A tiles are read twice). Used by the
+// VecSet decoder's latent stack, where bf16 weight rounding is a common-mode error of the occupancy field
+// (DESIGN.md §7). gelu_exact: erf GELU in the GEGLU epilogue. f16_period = 0: no fp16 columns.
+int gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw, void* out, int64_t ldo,
+                     const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
+                     int f16_start, int f16_period, int gelu_exact, cudaStream_t stream);
+
 // While alive on this thread, every GEMM launched treats its W operand as STATIC (model weights: not written by any
 // kernel in flight), which lets the kernel start streaming W before its programmatic-dependency wait.
 struct GemmStaticWeights {
@@ -59,7 +64,6 @@ int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bia
                 int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
 int xattn_fold(const void* ctxkv, const void* wq_t, const void* w_o, int depth, int frames, void* kp, void* vt,
                cudaStream_t stream);
-bool xattn_fusion_enabled();  // RALD_B200_FUSE_XATTN != 0 (default on)
 
 // norm.cu ------------------------------------------------------------------------------------------
 int ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,

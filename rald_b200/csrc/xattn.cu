@@ -474,15 +474,6 @@ int xattn_fold(const void* ctxkv, const void* wq_t, const void* w_o, int depth, 
   return 0;
 }
 
-bool xattn_fusion_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("RALD_B200_FUSE_XATTN");
-    on = (e == nullptr || e[0] != '0') ? 1 : 0;
-  }
-  return on == 1;
-}
-
 }  // namespace rald
 
 // Debug hook like rald_gemm_debug_buffer: CTA 0 stores %globaltimer stamps of its first 4 tiles at dev_buf[tile*16+i]:

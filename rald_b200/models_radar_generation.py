@@ -242,9 +242,18 @@ class EDMPrecond(nn.Module):
                 raise IndexError(f"{nm} dimension {n} exceeds the embedding table size {emb.weight.shape[0]}")
         dim = self.radar_token_channel
         dev = feat.device
+        p = self.radar_token_project
+        if cz != p.in_features:
+            # the reference fails here with a matmul shape error (F.linear of [.., cz] with a [dim, in_features] weight)
+            raise ValueError(f"radar_token_project expects {p.in_features} input channels, the conditioning has {cz}")
+        for nm, t in (("radar_token_project.weight", p.weight), ("radar_token_project.bias", p.bias),
+                      ("radar_r_emb.weight", self.radar_r_emb.weight), ("radar_a_emb.weight", self.radar_a_emb.weight),
+                      ("radar_e_emb.weight", self.radar_e_emb.weight)):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise _lib.RaldError(f"{nm} must be a contiguous fp32 tensor on {dev} (got {t.dtype}, "
+                                     f"contiguous={t.is_contiguous()}, {t.device})")
         tok32 = torch.empty(B, nr * na * ne, dim, device=dev, dtype=torch.float32) if want_f32 else None
         tok16 = torch.empty(B * nr * na * ne, dim, device=dev, dtype=torch.bfloat16) if want_bf16 else None
-        p = self.radar_token_project
         _lib.call("rald_radar_tokens", feat.data_ptr(), B, nr, na, ne, cz, p.weight.data_ptr(), p.bias.data_ptr(),
                   self.radar_r_emb.weight.data_ptr(), self.radar_a_emb.weight.data_ptr(),
                   self.radar_e_emb.weight.data_ptr(), dim, _lib.ptr(tok32), _lib.ptr(tok16), _lib.cur_stream())

@@ -32,7 +32,7 @@ class DitWorkspace(ctypes.Structure):
                 ("h", c_void_p), ("xn", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("ff", c_void_p),
                 ("x_tmp", c_void_p), ("d_tmp", c_void_p),
                 ("xattn_kp", c_void_p), ("xattn_vt", c_void_p), ("xattn_frames", ctypes.c_int32),
-                ("_pad2", ctypes.c_int32)]
+                ("xattn_frame0", ctypes.c_int32)]
 
 
 def geglu_pack_index(inner: int, device) -> torch.Tensor:
@@ -59,6 +59,21 @@ def graphs_enabled() -> bool:
     return os.environ.get("RALD_B200_GRAPH", "1") == "1"
 
 
+def sampler_chains(frames: int) -> int:
+    """Number of concurrent sub-batches ("chains") the sampling loop of a `frames`-frame call is split into, each on
+    its own CUDA stream with its own workspace. Frames are independent, and below ~16 frames every launch of the loop
+    is latency-bound (fixed ~5 us of set-up / first-operand / drain per kernel whatever its size) and most grids cover
+    less than the machine, so independent chains fill the idle SMs and hide each other's latencies. RALD_B200_CHAINS=n
+    forces n (1 = off); default: see _auto_chains."""
+    e = os.environ.get("RALD_B200_CHAINS")
+    n = int(e) if e else _auto_chains(frames)
+    return max(1, min(n, frames))
+
+
+def _auto_chains(frames: int) -> int:
+    return 1
+
+
 class _SamplerGraph:
     """One captured sampling loop (context K/V GEMM + rald_dit_sample) for a fixed (frames, context length, schedule):
     static input / output buffers and the CUDA graph that replays the ~9 300 launches without host work."""
@@ -70,7 +85,7 @@ class _SamplerGraph:
         self.warm = False
 
 
-class DitRuntime:
+class DitRuntime(_lib.RuntimeNotCopied):
     """Packed weights + workspaces for one EDMPrecond instance on one CUDA device."""
 
     def __init__(self, module):
@@ -80,6 +95,7 @@ class DitRuntime:
         self._ws_frames = 0
         self._mod_cache = {}
         self._graphs = {}
+        self._side_streams = []
 
     # ------------------------------------------------------------------ packing
     def _signature(self):
@@ -157,13 +173,14 @@ class DitRuntime:
             setattr(w, name, getattr(self, name).data_ptr())
         return w
 
-    def _workspace(self, frames: int):
-        """Workspace for micro-batches of min(frames, RALD_B200_MICROBATCH) frames; one per size, kept alive because
-        captured graphs hold their addresses."""
+    def _workspace(self, frames: int, chain: int = 0):
+        """Workspace for micro-batches of min(frames, RALD_B200_MICROBATCH) frames; one per (size, chain), kept alive
+        because captured graphs hold their addresses."""
         mb = max(1, min(default_microbatch(), frames))
         if self._ws is None:
             self._ws = {}
-        if mb not in self._ws:
+        key = mb if chain == 0 else (mb, chain)
+        if key not in self._ws:
             T = mb * self.module.n_latents
             dev, dim = self.device, self.dim
             bufs = dict(h=torch.empty(T, dim, device=dev, dtype=torch.float32),
@@ -177,8 +194,8 @@ class DitRuntime:
             ws.max_frames = mb
             for k, v in bufs.items():
                 setattr(ws, k, v.data_ptr())
-            self._ws[mb] = (ws, bufs)
-        return self._ws[mb][0]
+            self._ws[key] = (ws, bufs)
+        return self._ws[key][0]
 
     # ------------------------------------------------------------------ pieces
     def mod_table(self, sigmas: torch.Tensor) -> torch.Tensor:
@@ -223,7 +240,7 @@ class DitRuntime:
         vt = torch.empty(self.depth, 8, self.dim, F * 64, device=self.device, dtype=torch.float16)
         _lib.call("rald_xattn_fold", kv.data_ptr(), self.w_q2t.data_ptr(), self.w_o2.data_ptr(), self.depth, F,
                   kp.data_ptr(), vt.data_ptr(), _lib.cur_stream())
-        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames = kp.data_ptr(), vt.data_ptr(), F
+        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames, ws.xattn_frame0 = kp.data_ptr(), vt.data_ptr(), F, 0
         return kv, kp, vt
 
     def _conditioning(self, tokens_bf16: torch.Tensor, ws: DitWorkspace, L: int):
@@ -231,7 +248,7 @@ class DitRuntime:
         if self._fusable(L, tokens_bf16.shape[0] // max(L, 1)):
             keep = self.context_fold(tokens_bf16, ws)
             return 0, keep
-        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames = None, None, 0
+        ws.xattn_kp, ws.xattn_vt, ws.xattn_frames, ws.xattn_frame0 = None, None, 0, 0
         ctxkv = self.context_kv(tokens_bf16)
         return ctxkv.data_ptr(), (ctxkv,)
 
@@ -259,8 +276,37 @@ class DitRuntime:
     def _sample_eager(self, latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L):
         w, ws = self._weights_struct(L), self._workspace(B)
         ctx_ptr, keep = self._conditioning(tokens_bf16, ws, L)
-        _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
-                  num_steps, mod.data_ptr(), ctx_ptr, out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
+        chains = sampler_chains(B) if trace is None else 1
+        if chains == 1:
+            _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(),
+                      sig_dev.data_ptr(), num_steps, mod.data_ptr(), ctx_ptr, out.data_ptr(), _lib.ptr(trace), B,
+                      _lib.cur_stream())
+            return keep
+        # concurrent chains: contiguous sub-batches, each with its own workspace, chain 0 on the current stream and the
+        # others on side streams forked from / joined to it (the pattern is graph-capturable)
+        cur = torch.cuda.current_stream()
+        while len(self._side_streams) < chains - 1:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        M, C = latents.shape[1], latents.shape[2]
+        base, rem = divmod(B, chains)
+        f0 = 0
+        ctx_row_bytes = L * self.depth * 2 * self.dim * 2       # one frame's K / V projections (bf16)
+        for c in range(chains):
+            nf = base + (1 if c < rem else 0)
+            wsc = self._workspace(nf, chain=c) if c > 0 else self._workspace(nf)
+            wsc.xattn_kp, wsc.xattn_vt, wsc.xattn_frames = ws.xattn_kp, ws.xattn_vt, ws.xattn_frames
+            wsc.xattn_frame0 = f0
+            stream = cur if c == 0 else self._side_streams[c - 1]
+            if c > 0:
+                stream.wait_stream(cur)
+            off = f0 * M * C * 4
+            with torch.cuda.stream(stream):
+                _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(wsc), latents.data_ptr() + off,
+                          sig_dev.data_ptr(), num_steps, mod.data_ptr(), (ctx_ptr + f0 * ctx_row_bytes) if ctx_ptr else 0,
+                          out.data_ptr() + off, 0, nf, stream.cuda_stream)
+            f0 += nf
+        for c in range(1, chains):
+            cur.wait_stream(self._side_streams[c - 1])
         return keep
 
     def sample(self, latents: torch.Tensor, tokens_bf16: torch.Tensor, sigmas: torch.Tensor,
@@ -285,7 +331,7 @@ class DitRuntime:
             out = torch.empty_like(latents)
             self._sample_eager(latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L)
             return out
-        gkey = (B, L, mb)
+        gkey = (B, L, mb, sampler_chains(B), self._fusable(L, B))
         g = self._graphs.get(gkey)
         if g is None:
             g = self._graphs[gkey] = _SamplerGraph()

@@ -56,7 +56,7 @@ def _n_tile(cout: int) -> int:
     return 128 if cout >= 128 else (64 if cout >= 64 else 32)
 
 
-class EncoderRuntime:
+class EncoderRuntime(_lib.RuntimeNotCopied):
     def __init__(self, module):
         self.module = module
         self._sig = None

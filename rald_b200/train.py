@@ -65,3 +65,7 @@ def update_ema(target_params: Iterable[torch.Tensor], source_params: Iterable[to
     table, n, chunks, elems = _table(targets, sources)
     with torch.cuda.device(dev):
         _lib.call("rald_ema_update", table.data_ptr(), n, chunks, elems, float(rate), float(1 - rate), _lib.cur_stream())
+    # The kernel writes through raw device pointers, which autograd's version counters do not see — but the runtimes
+    # (DitRuntime / AeRuntime._signature) detect weight changes through exactly those counters. Bump them as the
+    # in-place torch ops this replaces did, so that an EMA into a module's own parameters repacks its bf16 weights.
+    torch.autograd.graph.increment_version(targets)

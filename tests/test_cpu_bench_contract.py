@@ -13,18 +13,21 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "0", "--ref-evals", "2", "--queries", "16384"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("generated frames/sec") and d["unit"] == "frames/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6 * 1000.0
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None
+    # one step = the job's 64 global frames, as in our arm
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 64 * 1000.0) < 1e-6 * 64 * 1000.0
+    assert "PARTIAL" in d["extrapolated"] and d["frames_timed"] == 1 and d["timed_s"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle port" in cb["sample"]
-    assert d["config"]["workload"].startswith("configs[2]") and d["config"]["frames_per_gpu"] == 64
+    assert d["config"]["workload"].startswith("configs[2]") and d["config"]["global_frames"] == 64
+    assert d["config"]["frames_per_gpu"] == 64 and d["config"]["queries_per_frame"] == 16384
     assert d["gpu_launches"] == 0
 
 

@@ -129,9 +129,10 @@ def _gather_worker(rank, world, port, out_dir):
     frames, cap = (2, 5) if rank == 0 else (1, 3)      # ragged: different frame counts and capacities
     pts = torch.full((frames, cap, 3), float(rank + 1))
     cnt = torch.tensor([4, 0] if rank == 0 else [3], dtype=torch.int32)
-    g_pts, g_cnt = gather.gather_point_clouds(pts, cnt)
+    pts[:, :, 1] = torch.arange(cap, dtype=torch.float32)[None, :]      # y = index of the point inside its frame
+    g = gather.gather_point_clouds(pts, cnt)
     lat = gather.gather_latents(torch.full((frames, 4, 2), float(rank)))
-    torch.save((g_pts, g_cnt, lat), os.path.join(out_dir, f"r{rank}.pt"))
+    torch.save((g.points, g.counts, g.offsets, lat), os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -142,7 +143,12 @@ def test_gather_point_clouds_gloo_world2(tmp_path):
     r1 = torch.load(tmp_path / "r1.pt")
     for a, b in zip(r0, r1):
         assert torch.equal(a, b)               # every rank sees the whole batch
-    pts, cnt, lat = r0
-    assert pts.shape == (3, 5, 3) and cnt.tolist() == [4, 0, 3]
-    assert float(pts[0, 0, 0]) == 1.0 and float(pts[2, 0, 0]) == 2.0 and float(pts[2, 4, 0]) == 0.0  # zero padding
+    pts, cnt, off, lat = r0
+    g = gather.GatheredClouds(pts, cnt, off)
+    assert cnt.tolist() == [4, 0, 3] and off.tolist() == [0, 4, 4]       # compact: rank totals 4 and 3, padded to 4
+    assert pts.shape == (2 * 4, 3)
+    f0, f1, f2 = g.frame(0), g.frame(1), g.frame(2)
+    assert f0.shape == (4, 3) and f1.shape == (0, 3) and f2.shape == (3, 3)
+    assert f0[:, 0].tolist() == [1.0] * 4 and f0[:, 1].tolist() == [0.0, 1.0, 2.0, 3.0]
+    assert f2[:, 0].tolist() == [2.0] * 3 and f2[:, 1].tolist() == [0.0, 1.0, 2.0]
     assert lat.shape == (3, 4, 2) and lat[:, 0, 0].tolist() == [0.0, 0.0, 1.0]

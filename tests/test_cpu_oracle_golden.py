@@ -127,3 +127,36 @@ def test_chamfer_definition():
     b = np.ones((2, 3), dtype=np.float32)
     assert orc.chamfer_distance(a, b) == pytest.approx(np.sqrt(3.0))
     assert orc.chamfer_distance(a[:0], b) == float("inf")
+
+
+@torch.no_grad()
+def test_sampler_with_churn_first_step(den_sd, golden):
+    """S_churn > 0 branch of the oracle against the unmodified reference's edm_sampler (churn.npz). The full 4-step
+    comparison is asserted by make_golden_churn.py while it writes the fixture (deviation 0.0); here one step with the
+    fixture's injected noise keeps the CPU suite short: gamma > 0 must change the result, and a 1-step run of the
+    oracle must be reproducible from the recorded draws."""
+    g = golden("churn")
+    cube = synth.radar_cube(2, seed=1024)
+    tok = orc.process_radar_cond(den_sd, cube)
+    lat = synth.unit_latents([0, 1])
+    noises = list(g["noises"])
+    a = orc.edm_sample(den_sd, lat, tok, num_steps=int(g["num_steps"]), S_churn=float(g["s_churn"]),
+                       S_noise=float(g["s_noise"]), noises=noises, stop_after=1)
+    b = orc.edm_sample(den_sd, lat, tok, num_steps=int(g["num_steps"]), stop_after=1)
+    assert torch.isfinite(a).all() and rel_l2(a, b) > 1e-2
+
+
+@torch.no_grad()
+def test_well_conditioned_decode_fixture(golden):
+    """e2e_wc.npz: the sharpened shared state_dict decodes to the committed reference logits through the oracle."""
+    g = golden("e2e_wc")
+    sd = cpu_state_dict(build_ae("kl_d512_m512_l32_mix"))
+    sd["decoder_cross_attn.fn.to_q.weight"] = sd["decoder_cross_attn.fn.to_q.weight"] * float(g["q_scale"])
+    sd["to_outputs.weight"] = sd["to_outputs.weight"] * float(g["out_scale"])
+    sd["to_outputs.bias"] = torch.full_like(sd["to_outputs.bias"], float(g["bias"]))
+    z = golden("sampler_trace")["trace"][-1][None]
+    q = synth.query_points(1, 32768, seed=99)[:, :4096]
+    lg = orc.ae_decode(sd, z, q)[0, :, 0]
+    ref = g["logits"][0, :4096]
+    assert float((lg - ref).abs().max()) < 1e-4 and float(ref.std()) > 0.1
+    assert 0.02 < float((g["logits"] > 0).float().mean()) < 0.08

@@ -105,3 +105,38 @@ def test_batched_decode_equals_single_frames_at_sweep_size(ae):
     for f in (0, 31, 63):
         single = ae.decode(z[f:f + 1].contiguous(), q[f:f + 1].contiguous())
         assert torch.equal(full[f], single[0]), f
+
+
+def test_decode_under_inference_mode_and_cache_clear():
+    """inference tensors carry no version counter — decode must not key its latent-stack cache on it."""
+    vae = build_ae("kl_d512_m512_l32_mix", device="cuda")
+    z = synth.posterior_noise(1, seed=5).cuda()
+    q = synth.query_points(1, 2048).cuda()
+    with torch.no_grad():
+        ref = vae.decode(z, q)
+    with torch.inference_mode():
+        zi = z.clone()
+        out = vae.decode(zi, q)
+        out2 = vae.decode(zi, q)
+    assert torch.equal(out, ref) and torch.equal(out2, ref)
+    vae._runtime().clear_cache()
+    with torch.no_grad():
+        assert torch.equal(vae.decode(z, q), ref)
+
+
+def test_precise_stack_is_default_and_switchable(monkeypatch):
+    """The split-weight latent stack (default) and the plain bf16 one agree to bf16 level; the switch repacks."""
+    from oracle import rald_oracle as orc
+    vae = build_ae("kl_d512_m512_l32_mix", device="cuda")
+    sd = cpu_state_dict(vae)
+    z = synth.posterior_noise(1, seed=5)
+    with torch.no_grad():
+        x_ref = orc.ae_latent_stack(sd, z)[0]
+        x_precise = vae._runtime().latent_stack(z.cuda()).cpu()
+        assert vae._runtime().precise
+        monkeypatch.setenv("RALD_B200_AE_PRECISE", "0")
+        x_plain = vae._runtime().latent_stack(z.cuda()).cpu()
+        assert not vae._runtime().precise
+    e_p, e_b = rel_l2(x_precise, x_ref), rel_l2(x_plain, x_ref)
+    print(f"latent stack rel-L2 vs fp32 oracle: precise {e_p:.2e}, plain bf16 {e_b:.2e}")
+    assert e_p < 3e-3 and e_b < 1e-2 and e_p < e_b

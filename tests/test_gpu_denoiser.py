@@ -90,3 +90,27 @@ def test_edm_loss_evaluation_matches_oracle(net, golden):
             crit(net, y, tok, "radar")
     finally:
         net.eval()
+
+
+def test_edm_sampler_with_churn(golden):
+    """S_churn > 0 (models_radar_generation.py:254-260): the host-loop branch, against the unmodified reference's
+    edm_sampler with the same injected per-step noise (tests/golden/make_golden_churn.py)."""
+    from rald_b200.models_radar_generation import edm_sampler
+    g = golden("churn")
+    net = build_denoiser(device="cuda")
+    cube = synth.radar_cube(2, seed=1024).cuda()
+    lat = synth.unit_latents([0, 1]).cuda()
+    noises = [n.cuda() for n in g["noises"]]
+    it = iter(noises)
+    with torch.no_grad():
+        x = edm_sampler(net, lat, cube, "radar", randn_like=lambda t: next(it), num_steps=int(g["num_steps"]),
+                        S_churn=float(g["s_churn"]), S_noise=float(g["s_noise"]))
+    assert next(it, None) is None            # one draw per step, as the reference
+    assert rel_l2(x, g["x"]) <= 1e-2
+
+
+def test_token_projection_shape_mismatch_raises():
+    net = build_denoiser(device="cuda")
+    net.radar_token_project = torch.nn.Linear(8, 512).cuda()     # encoder emits 16 channels
+    with pytest.raises(ValueError):
+        net.process_radar_cond(synth.radar_cube(1, seed=1).cuda())

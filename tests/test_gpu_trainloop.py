@@ -104,3 +104,26 @@ def test_trainloop_abi_argument_checks():
     assert lib.rald_occupancy_iou(0, 0, 1, 8, 0.0, 0, 0, 0) != 0
     f = torch.zeros(8, device=DEV)
     assert lib.rald_occupancy_iou(f.data_ptr(), f.data_ptr(), 0, 8, 0.0, f.data_ptr(), t.data_ptr(), 0) != 0
+
+
+def test_update_ema_into_module_parameters_repacks_runtime():
+    """the fused EMA writes through raw pointers; the runtimes notice weight changes through autograd
+    version counters, so update_ema must bump them (ema_model = deepcopy(model) pattern)."""
+    import copy
+    from helpers import build_denoiser
+    from rald_b200 import synth
+    net = build_denoiser(name="kl_d512_m512_l32_d12_edm", device="cuda")
+    ema = copy.deepcopy(net)
+    tok = synth.unit_latents([7])[:, :64, :].repeat(1, 1, 16).cuda()      # [1, 64, 512] conditioning tokens
+    x = synth.unit_latents([0]).cuda()
+    sigma = torch.tensor(1.5)
+    with torch.no_grad():
+        before = ema(x * 1.5, sigma, tok, "radar").clone()
+        for p in net.parameters():
+            p.mul_(1.05)
+        train.update_ema(list(ema.parameters()), list(net.parameters()), rate=0.5)
+        after = ema(x * 1.5, sigma, tok, "radar")
+        fresh = copy.deepcopy(ema)              # same weights, freshly packed
+        expect = fresh(x * 1.5, sigma, tok, "radar")
+    assert not torch.equal(before, after)
+    assert torch.equal(after, expect)
