@@ -678,12 +678,18 @@ def run_ours(args, rank, world, local_rank):
 
     sh = Shard(*spans[rank], G)
     # occupancy calibration (random-init logits are all slightly negative): shift to_outputs.bias by the
-    # 95-th percentile of one decode of GLOBAL frame 0, computed identically on every rank, so `logit > 0`
-    # (engine_generation.py:285) keeps ~5 % of the queries
-    z0 = net.sample(frame_cubes(0, 1).to(dev), batch_seeds=torch.arange(1), cond_type="radar")
-    lg0 = vae.decode(z0, q1_d).flatten()
+    # 95-th percentile of one decode of this rank's frames through the SAME kernels the timed steps use, averaged over
+    # the ranks so that every rank applies the same shift: `logit > 0` (engine_generation.py:285) then keeps ~5 % of
+    # the queries
+    z0 = net.sample(sh.cube_d, batch_seeds=sh.seeds, cond_type="radar")
+    lg0 = vae.decode(z0, sh.q_d).flatten()
     sub = lg0[:: max(1, lg0.numel() // 65536)]
-    shift = float(sub.kthvalue(max(1, int(0.95 * sub.numel()))).values)
+    shift_t = sub.kthvalue(max(1, int(0.95 * sub.numel()))).values.double().reshape(1)
+    if world > 1:
+        dist.all_reduce(shift_t, op=dist.ReduceOp.SUM)
+        shift_t /= world
+    shift = float(shift_t)
+    del z0, lg0
     with torch.no_grad():
         vae.to_outputs.bias -= shift
 
@@ -720,11 +726,11 @@ def run_ours(args, rank, world, local_rank):
         g = sh.step_resident()
         check = None
         if rank == 0:
-            # same cross-attention formulation as the shards used (the fused kernel is only selected for >= 24 frames;
-            # the two formulations agree to bf16 level, not to the bit)
-            saved = os.environ.get("RALD_B200_FUSE_XATTN_MIN_FRAMES")
-            if sh.F < int(saved or "24"):
-                os.environ["RALD_B200_FUSE_XATTN_MIN_FRAMES"] = str(1 << 30)
+            # same form of the folded cross-attention as the shards used (two GEMMs below 32 frames, one fused kernel
+            # above; built to be bit-identical, tests/test_gpu_xattn.py — matching them keeps this check about SHARDING)
+            saved = os.environ.get("RALD_B200_XATTN_SPLIT_BELOW")
+            if sh.F < int(saved or "32"):
+                os.environ["RALD_B200_XATTN_SPLIT_BELOW"] = str(1 << 30)
             try:
                 full = Shard(0, G, G)
                 z = net.sample(full.cube_d, batch_seeds=full.seeds, cond_type="radar")
@@ -741,9 +747,9 @@ def run_ours(args, rank, world, local_rank):
                 del full, z, lg, pts
             finally:
                 if saved is None:
-                    os.environ.pop("RALD_B200_FUSE_XATTN_MIN_FRAMES", None)
+                    os.environ.pop("RALD_B200_XATTN_SPLIT_BELOW", None)
                 else:
-                    os.environ["RALD_B200_FUSE_XATTN_MIN_FRAMES"] = saved
+                    os.environ["RALD_B200_XATTN_SPLIT_BELOW"] = saved
             torch.cuda.empty_cache()
         line["sharding_check"] = check
         barrier()

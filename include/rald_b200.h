@@ -150,7 +150,9 @@ int rald_radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, 
 typedef struct rald_dit_weights {
   int32_t depth, dim, heads, channels, n_latents, ctx_len;
   float sigma_data;
-  int32_t _pad;
+  int32_t precise;     /* 0: bf16 weights (default). 1: every weight matrix below is a split pair [rows][2*cols] =
+                        * [W_hi | W_lo] (rald_gemm_bf16_wsplit: 16 mantissa bits of the fp32 weight, twice the GEMM work)
+                        * and the GEGLU uses the erf GELU; the fused cross-attention operands must not be supplied */
   /* bf16, stacked over depth */
   const void* w_qkv;   /* [depth][3*dim][dim]  rows: to_q | to_k | to_v of attn1 */
   const void* w_o1;    /* [depth][dim][dim]    attn1.to_out.0.weight */
@@ -171,7 +173,9 @@ typedef struct rald_dit_weights {
 
 typedef struct rald_dit_workspace {
   int32_t max_frames;  /* micro-batch size the buffers below are sized for; T = max_frames * n_latents */
-  int32_t _pad;
+  int32_t xattn_split_below;  /* with xattn_kp set: micro-batches of fewer frames than this run the folded cross-attention
+                               * as two GEMMs (rald_xattn_split) instead of the fused kernel — same result bit for bit,
+                               * fills the machine at small batch; 0 = always the fused kernel */
   float* h;      /* [T][dim]   fp32 residual stream */
   void* xn;      /* [T][dim]   bf16 normalised operand */
   void* qkv;     /* [T][3*dim] bf16 */
@@ -217,6 +221,12 @@ int rald_xattn_fold(const void* ctxkv_bf16, const void* wq_t_scaled, const void*
                     void* vt, void* stream);
 int rald_xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
                      int rows_per_frame, int frame0, int total_frames, void* stream);
+/* The same sub-layer as TWO tcgen05 GEMMs for batches too small to fill the machine with 128-row fused tiles (4 tiles
+ * per frame): probs (fp16 scratch [T][512]) = per-head softmax(xn kp^T) in the first GEMM's epilogue, then
+ * h += probs vt^T + bias with a TMA reduce-add epilogue. Same operands and arithmetic order as rald_xattn_fused: the
+ * results are bit-identical. */
+int rald_xattn_split(const void* xn, const void* kp, const void* vt, const float* bias, float* h, void* probs_f16,
+                     int frames, int rows_per_frame, int frame0, int total_frames, void* stream);
 /* Debug hook like rald_gemm_debug_buffer for rald_ae_query (phase list in csrc/ae_query.cu). */
 int rald_ae_query_debug_buffer(unsigned long long* dev_buf);
 /* Debug hook like rald_gemm_debug_buffer: CTA 0 of the fused kernel stores %globaltimer stamps of its first 4 tiles at

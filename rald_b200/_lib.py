@@ -56,6 +56,7 @@ _SIGNATURES = {
                         c_void_p],
     "rald_xattn_fold": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "rald_xattn_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_xattn_split": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rald_ae_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "rald_linear_smallk": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p],
     "rald_ln_dot_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],

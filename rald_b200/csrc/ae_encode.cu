@@ -83,36 +83,70 @@ int point_features(const float* pts, const int64_t* idx, int B, int64_t N, int64
 
 // ---------------------------------------------------------------------------------------------------
 // Farthest point sampling. One CTA of 1024 threads per cloud; the cloud lives in shared memory as SoA
-// (x[], y[], z[]: conflict-free), each thread keeps the running minimum distance of its points
-// (N / 1024 <= FPS_PER_THREAD) in registers. Per pick: distance update + thread argmax, warp-shuffle
-// argmax, 32-way cross-warp argmax by warp 0, broadcast through shared memory (2 barriers per pick).
-// Deterministic definition (oracle/rald_oracle.py:fps_indices): start at index 0; squared distance
-// (dx*dx + dy*dy) + dz*dz with individually rounded fp32 operations; ties -> lowest index.
+// (x[], y[], z[], each padded to a multiple of 4 points), thread t owns the point quads [4 t + 4096 j, +4) and keeps
+// their running minimum distances in registers. Per pick (511 dependent picks for M = 512):
+//   sweep      3 x LDS.128 per quad; differences and squares as packed fp32x2 operations (FADD2 / FMUL2: two points
+//              per instruction, each lane individually rounded), the two sums as scalar FADDs — ptxas would contract a
+//              packed multiply + packed add into FFMA2 even with .rn, which the definition below forbids;
+//   argmax     thread-local (value, index) -> per warp TWO redux.sync (max of the value's bit pattern, then min index
+//              among the lanes holding it) -> 32 (value, index) pairs through double-buffered shared memory and ONE
+//              barrier -> every warp reduces the 32 pairs itself the same way (no second barrier, no broadcast).
+// Round 1's form (scalar arithmetic, 10 shuffles per level, two barriers) took 1.6 us per pick for N = 10000.
+// Deterministic definition (oracle/fps_oracle.c, oracle/rald_oracle.py:fps_indices): start at index 0; squared
+// distance (dx*dx + dy*dy) + dz*dz with individually rounded fp32 operations; ties -> lowest index.
 // ---------------------------------------------------------------------------------------------------
 constexpr int FPS_THREADS = 1024;
-constexpr int FPS_PER_THREAD = 16;   // clouds up to 16384 points
+constexpr int FPS_QUADS = 4;         // quads per thread: clouds up to 4 * 4 * 1024 = 16384 points
+constexpr int FPS_MAX_POINTS = FPS_THREADS * FPS_QUADS * 4;
 
-__device__ __forceinline__ void argmax_combine(float& d, int& i, float od, int oi) {
-  if (od > d || (od == d && oi < i)) { d = od; i = oi; }
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// (value, index) argmax over the 32 lanes of a warp, ties -> lowest index. The values are >= 0 or -inf, so the signed
+// integer order of their bit patterns is the float order.
+__device__ __forceinline__ void warp_argmax(int& key, int& idx) {
+  const int kmax = __reduce_max_sync(0xffffffffu, key);
+  idx = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)idx : 0xffffffffu);
+  key = kmax;
 }
 
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_kernel(const float* __restrict__ pts, int N, int M, int64_t* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  const int Np = (N + 3) & ~3;
   float* sx = sm;
-  float* sy = sx + N;
-  float* sz = sy + N;
-  __shared__ float s_wd[32];
-  __shared__ int s_wi[32];
-  __shared__ int s_cur;
+  float* sy = sx + Np;
+  float* sz = sy + Np;
+  __shared__ int s_key[2][32];
+  __shared__ int s_idx[2][32];
   const int b = blockIdx.x;
   const float* p = pts + (int64_t)b * N * 3;
-  for (int i = threadIdx.x; i < N; i += FPS_THREADS) {
-    sx[i] = p[3 * i + 0]; sy[i] = p[3 * i + 1]; sz[i] = p[3 * i + 2];
+  for (int i = threadIdx.x; i < Np; i += FPS_THREADS) {
+    const bool ok = i < N;
+    sx[i] = ok ? p[3 * i + 0] : 0.f; sy[i] = ok ? p[3 * i + 1] : 0.f; sz[i] = ok ? p[3 * i + 2] : 0.f;
   }
-  float dist[FPS_PER_THREAD];
+  // running minimum distance: +inf for real points, -inf for the padding (min keeps it there, so it never wins)
+  float dist[FPS_QUADS][4];
 #pragma unroll
-  for (int j = 0; j < FPS_PER_THREAD; ++j) dist[j] = INFINITY;
+  for (int j = 0; j < FPS_QUADS; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dist[j][e] = (4 * (int)threadIdx.x + j * 4 * FPS_THREADS + e) < N ? INFINITY : -INFINITY;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int cur = 0;
@@ -120,48 +154,54 @@ fps_kernel(const float* __restrict__ pts, int N, int M, int64_t* __restrict__ ou
     if (threadIdx.x == 0) out[(int64_t)b * M + m] = cur;
     if (m == M - 1) break;
     const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
-    float bd = -1.0f;
+    const unsigned long long cx2 = f2_pack(cx, cx), cy2 = f2_pack(cy, cy), cz2 = f2_pack(cz, cz);
+    float bd = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < FPS_PER_THREAD; ++j) {
-      const int i = threadIdx.x + j * FPS_THREADS;   // ascending index per thread: '>' keeps the lowest index on ties
-      if (i < N) {
-        const float dx = __fsub_rn(sx[i], cx), dy = __fsub_rn(sy[i], cy), dz = __fsub_rn(sz[i], cz);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float d = fminf(dist[j], d2);
-        dist[j] = d;
-        if (d > bd) { bd = d; bi = i; }
+    for (int j = 0; j < FPS_QUADS; ++j) {
+      const int i0 = 4 * (int)threadIdx.x + j * 4 * FPS_THREADS;   // ascending index per thread: '>' keeps the lowest
+      if (i0 < Np) {                                               // index on ties
+        const float4 vx = *reinterpret_cast<const float4*>(sx + i0);
+        const float4 vy = *reinterpret_cast<const float4*>(sy + i0);
+        const float4 vz = *reinterpret_cast<const float4*>(sz + i0);
+        float d2[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned long long dx = f2_sub(h ? f2_pack(vx.z, vx.w) : f2_pack(vx.x, vx.y), cx2);
+          const unsigned long long dy = f2_sub(h ? f2_pack(vy.z, vy.w) : f2_pack(vy.x, vy.y), cy2);
+          const unsigned long long dz = f2_sub(h ? f2_pack(vz.z, vz.w) : f2_pack(vz.x, vz.y), cz2);
+          float xa, xb, ya, yb, za, zb;
+          f2_unpack(f2_mul(dx, dx), xa, xb);
+          f2_unpack(f2_mul(dy, dy), ya, yb);
+          f2_unpack(f2_mul(dz, dz), za, zb);
+          d2[2 * h] = __fadd_rn(__fadd_rn(xa, ya), za);
+          d2[2 * h + 1] = __fadd_rn(__fadd_rn(xb, yb), zb);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = fminf(dist[j][e], d2[e]);
+          dist[j][e] = d;
+          if (d > bd) { bd = d; bi = i0 + e; }
+        }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      argmax_combine(bd, bi, od, oi);
-    }
-    if (lane == 0) { s_wd[warp] = bd; s_wi[warp] = bi; }
+    int key = __float_as_int(bd);
+    warp_argmax(key, bi);
+    const int buf = m & 1;
+    if (lane == 0) { s_key[buf][warp] = key; s_idx[buf][warp] = bi; }
     __syncthreads();
-    if (warp == 0) {
-      bd = s_wd[lane]; bi = s_wi[lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        argmax_combine(bd, bi, od, oi);
-      }
-      if (lane == 0) s_cur = bi;
-    }
-    __syncthreads();
-    cur = s_cur;
+    key = s_key[buf][lane];
+    bi = s_idx[buf][lane];
+    warp_argmax(key, bi);
+    cur = bi;
   }
 }
 
 int fps(const float* pts, int B, int N, int M, int64_t* out_idx, cudaStream_t stream) {
   RALD_REQUIRE(B > 0 && N > 0 && M > 0, "fps: bad sizes B=%d N=%d M=%d", B, N, M);
-  RALD_REQUIRE(N <= FPS_THREADS * FPS_PER_THREAD, "fps: N=%d exceeds the %d points one CTA holds", N,
-               FPS_THREADS * FPS_PER_THREAD);
+  RALD_REQUIRE(N <= FPS_MAX_POINTS, "fps: N=%d exceeds the %d points one CTA holds", N, FPS_MAX_POINTS);
   RALD_REQUIRE(M <= N, "fps: cannot sample %d of %d points", M, N);
-  const int smem = 3 * N * sizeof(float);
+  const int smem = 3 * ((N + 3) & ~3) * sizeof(float);
   RALD_REQUIRE(smem <= 200 * 1024, "fps: cloud of %d points does not fit in shared memory", N);
   // the kernel also has static shared memory, so even a request of exactly 48 KB needs the opt-in
   static int configured = 32 * 1024;

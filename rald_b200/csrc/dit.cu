@@ -32,32 +32,49 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
   // (the caller decides: registering the operands in the workspace IS the switch; check_common validates the shape)
   const bool fused_x = ws.xattn_kp != nullptr;
   const int64_t x_blk = (int64_t)8 * ws.xattn_frames * 64 * dim;  // elements of one block's kp (= vt) slice
+  // precise: split weight pairs [rows][2 cols] (twice the elements per block) + erf GELU (rald_dit_weights.precise)
+  const bool precise = w.precise != 0;
+  const int64_t wm = precise ? 2 : 1;
+  // out = epilogue(A W^T) for one packed weight matrix of this block, plain or split
+  auto linear = [&](const void* A, int64_t lda, const __nv_bfloat16* W, int K, void* out, int64_t ldo, const float* bias,
+                    const float* resid, int N, int out_mode, int f16_start, int f16_period) -> int {
+    if (precise)
+      return gemm_bf16_wsplit(A, lda, W, 2 * (int64_t)K, out, ldo, bias, resid, ldo, (int)T, N, K, out_mode, f16_start,
+                              f16_period, 1, st);
+    if (f16_period > 0) return gemm_bf16_f16cols(A, lda, W, K, out, ldo, bias, (int)T, N, K, f16_start, f16_period, st);
+    return gemm_bf16(A, lda, W, K, out, ldo, bias, resid, ldo, (int)T, N, K, out_mode, 0, st);
+  };
   for (int n = 0; n < depth; ++n) {
     const float* m0 = mod + ((int64_t)n * 3 + 0) * 2 * dim;
     const float* m1 = mod + ((int64_t)n * 3 + 1) * 2 * dim;
     const float* m2 = mod + ((int64_t)n * 3 + 2) * 2 * dim;
-    const __nv_bfloat16* w_qkv = reinterpret_cast<const __nv_bfloat16*>(w.w_qkv) + (int64_t)n * 3 * dim * dim;
-    const __nv_bfloat16* w_o1 = reinterpret_cast<const __nv_bfloat16*>(w.w_o1) + (int64_t)n * dim * dim;
-    const __nv_bfloat16* w_q2 = reinterpret_cast<const __nv_bfloat16*>(w.w_q2) + (int64_t)n * dim * dim;
-    const __nv_bfloat16* w_o2 = reinterpret_cast<const __nv_bfloat16*>(w.w_o2) + (int64_t)n * dim * dim;
-    const __nv_bfloat16* w_ff1 = reinterpret_cast<const __nv_bfloat16*>(w.w_ff1) + (int64_t)n * 8 * dim * dim;
-    const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w.w_ff2) + (int64_t)n * 4 * dim * dim;
+    const __nv_bfloat16* w_qkv = reinterpret_cast<const __nv_bfloat16*>(w.w_qkv) + (int64_t)n * 3 * dim * dim * wm;
+    const __nv_bfloat16* w_o1 = reinterpret_cast<const __nv_bfloat16*>(w.w_o1) + (int64_t)n * dim * dim * wm;
+    const __nv_bfloat16* w_q2 = reinterpret_cast<const __nv_bfloat16*>(w.w_q2) + (int64_t)n * dim * dim * wm;
+    const __nv_bfloat16* w_o2 = reinterpret_cast<const __nv_bfloat16*>(w.w_o2) + (int64_t)n * dim * dim * wm;
+    const __nv_bfloat16* w_ff1 = reinterpret_cast<const __nv_bfloat16*>(w.w_ff1) + (int64_t)n * 8 * dim * dim * wm;
+    const __nv_bfloat16* w_ff2 = reinterpret_cast<const __nv_bfloat16*>(w.w_ff2) + (int64_t)n * 4 * dim * dim * wm;
     // x += attn1(adaLN1(x))
     RALD_TRY(ln_rows(ws.h, dim, m0, m0 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
     // q | k in bf16, v in fp16 (attn_d64 multiplies fp16 probabilities with fp16 values)
-    RALD_TRY(gemm_bf16_f16cols(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, (int)T, 3 * dim, dim, 2 * dim, 3 * dim, st));
+    RALD_TRY(linear(ws.xn, dim, w_qkv, dim, ws.qkv, 3 * dim, nullptr, nullptr, 3 * dim, 0, 2 * dim, 3 * dim));
     RALD_TRY(attn_d64(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ws.att, dim, frames, heads, M, M,
                       scale, st));
-    RALD_TRY(gemm_bf16(ws.att, dim, w_o1, dim, ws.h, dim, w.b_o1 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
-                       0, st));
+    RALD_TRY(linear(ws.att, dim, w_o1, dim, ws.h, dim, w.b_o1 + (int64_t)n * dim, ws.h, dim, 1, 0, 0));
     // x += attn2(adaLN2(x), context)
     RALD_TRY(ln_rows(ws.h, dim, m1, m1 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
-    if (fused_x) {
+    if (fused_x && frames < ws.xattn_split_below) {
+      // small batch: the same folded operands through two GEMMs (probabilities in the idle q | k | v buffer)
+      RALD_TRY(xattn_split(ws.xn, reinterpret_cast<const __nv_bfloat16*>(ws.xattn_kp) + (int64_t)n * x_blk,
+                           reinterpret_cast<const __nv_bfloat16*>(ws.xattn_vt) + (int64_t)n * x_blk,
+                           w.b_o2 + (int64_t)n * dim, ws.h, ws.qkv, frames, M, ws.xattn_frame0 + frame0, ws.xattn_frames,
+                           st));
+    } else if (fused_x) {
       RALD_TRY(xattn_fused(ws.xn, reinterpret_cast<const __nv_bfloat16*>(ws.xattn_kp) + (int64_t)n * x_blk,
                            reinterpret_cast<const __nv_bfloat16*>(ws.xattn_vt) + (int64_t)n * x_blk,
                            w.b_o2 + (int64_t)n * dim, ws.h, frames, M, ws.xattn_frame0 + frame0, ws.xattn_frames, st));
     } else {
-      RALD_TRY(gemm_bf16(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, 0, (int)T, dim, dim, 0, 0, st));
+      RALD_TRY(linear(ws.xn, dim, w_q2, dim, ws.qkv, dim, nullptr, nullptr, dim, 0, 0, 0));
       if (L <= 512) {
         RALD_TRY(attn_d64(qkv, dim, ctx + (int64_t)n * 2 * dim, ld_ctx, ctx + (int64_t)n * 2 * dim + dim, ld_ctx,
                           ws.att, dim, frames, heads, M, L, scale, st));
@@ -69,15 +86,12 @@ static int run_blocks(const rald_dit_weights& w, const rald_dit_workspace& ws, c
                                ws.att, dim, frames, heads, M, L, scale, ws.ff,
                                reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(ws.qkv) + T * dim), st));
       }
-      RALD_TRY(gemm_bf16(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, (int)T, dim, dim, 1,
-                         0, st));
+      RALD_TRY(linear(ws.att, dim, w_o2, dim, ws.h, dim, w.b_o2 + (int64_t)n * dim, ws.h, dim, 1, 0, 0));
     }
     // x += ff(adaLN3(x))
     RALD_TRY(ln_rows(ws.h, dim, m2, m2 + dim, mod_frame_stride, M, 1, ws.xn, dim, 0, T, dim, 1e-5f, st));
-    RALD_TRY(gemm_bf16(ws.xn, dim, w_ff1, dim, ws.ff, 4 * dim, w.b_ff1 + (int64_t)n * 8 * dim, nullptr, 0, (int)T,
-                       8 * dim, dim, 2, 0, st));
-    RALD_TRY(gemm_bf16(ws.ff, 4 * dim, w_ff2, 4 * dim, ws.h, dim, w.b_ff2 + (int64_t)n * dim, ws.h, dim, (int)T, dim,
-                       4 * dim, 1, 0, st));
+    RALD_TRY(linear(ws.xn, dim, w_ff1, dim, ws.ff, 4 * dim, w.b_ff1 + (int64_t)n * 8 * dim, nullptr, 8 * dim, 2, 0, 0));
+    RALD_TRY(linear(ws.ff, 4 * dim, w_ff2, 4 * dim, ws.h, dim, w.b_ff2 + (int64_t)n * dim, ws.h, dim, 1, 0, 0));
   }
   return 0;
 }
@@ -129,6 +143,10 @@ static int check_common(const rald_dit_weights* w, const rald_dit_workspace* ws,
                ws->xattn_frame0, ws->xattn_frame0 + frames);
   RALD_REQUIRE(ws->xattn_kp == nullptr || (ws->xattn_vt != nullptr && w->ctx_len == 64 && w->heads == 8),
                "dit: fused cross-attention operands need both K' and VT, 64 context tokens and 8 heads");
+  RALD_REQUIRE(ws->xattn_kp == nullptr || ws->xattn_split_below == 0 || w->n_latents % 256 == 0,
+               "dit: the two-GEMM form of the folded cross-attention needs n_latents to be a multiple of 256");
+  RALD_REQUIRE(ws->xattn_kp == nullptr || w->precise == 0,
+               "dit: the precise (split-weight) mode uses the unfused cross-attention (no folded operands)");
   RALD_REQUIRE(ws->xattn_kp != nullptr || ctxkv != nullptr,
                "dit: neither context K/V projections nor fused cross-attention operands were supplied");
   return 0;

@@ -70,6 +70,14 @@ struct GemmParams {
                               // programmatic-dependency wait (hides the DRAM latency of the weights behind the
                               // predecessor's tail in the latency-bound small-batch regime); CG = 1 only
   int gelu_exact;             // GEGLU epilogue: erf GELU (A&S 7.1.26, fp32 round-off level) instead of the logistic fit
+  // Per-frame B operands of the folded cross-attention (xattn.cu: K' / VT built once per sample by xattn_fold). Rows
+  // [m, m + grp_rows) of A belong to frame grp_frame0 + m / grp_rows of grp_total frames:
+  //   b_mode 1  scores S = xn K'^T: W = K' of ONE block, bf16 [8 heads][grp_total][64 keys][K]; the B tile of column
+  //             block n_blk is one 64-row box per head (heads n_blk * BN / 64 ...), rows ((head * grp_total + f) * 64
+  //   b_mode 2  output O = P VT^T: W = VT of one block, fp16 [8 heads][N][grp_total * 64]; k-block kb is head kb, its B
+  //             tile rows kb * N + n_blk * BN at columns f * 64
+  int b_mode, grp_rows, grp_frame0, grp_total;
+  int ab_f16;                 // A and W are IEEE fp16 (kind::f16 with fp16 operands) instead of bf16
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
@@ -146,7 +154,8 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
   }
 }
 
-// OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]
+// OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]; 3 = softmax over every group of 64 columns
+// (scores already in log2 units) -> fp16 probabilities [M,N] (TMA-store epilogue only)
 template <int BN, int OUT_MODE, int EPI, int CG, int G>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -166,7 +175,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int TILE_M = BM * CG;
   constexpr int STAGES = Cfg::STAGES;
   // accumulator columns consumed per staged 128-byte output row
-  constexpr int CHUNK = OUT_MODE == 1 ? 32 : (OUT_MODE == 0 ? 64 : 128);
+  constexpr int CHUNK = OUT_MODE == 1 ? 32 : (OUT_MODE == 2 ? 128 : 64);
+  static_assert(OUT_MODE != 3 || EPI == EPI_TMA_STORE, "softmax epilogue: TMA store only");
   static_assert(EPI == EPI_GENERIC || BN % CHUNK == 0, "tile narrower than one staged output row");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -187,6 +197,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int t_begin = unit, t_end = num_tiles, t_step = num_units;
   // A column of k-block kb (split weights: the A tiles are re-read for the second half of K)
   auto a_col = [&](int kb) { const int c = kb * GEMM_BK; return c >= p.a_k ? c - p.a_k : c; };
+  // this CTA's share of the W tile of (k-block kb, tile (m_blk, n_blk)) -> sb, credited to `bar`
+  auto load_b = [&](uint8_t* sb, uint64_t* bar, int kb, int m_blk, int n_blk) {
+    auto ld = [&](uint8_t* dst, int x, int y) {
+      if (CG == 2) tma_load_2d_pair(dst, &tmB, bar, x, y);
+      else tma_load_2d(dst, &tmB, bar, x, y);
+    };
+    if (p.b_mode == 0) {
+      ld(sb, kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / CG));
+    } else {
+      const int f = p.grp_frame0 + (m_blk * TILE_M) / p.grp_rows;
+      if (p.b_mode == 1) {
+        constexpr int HB = (BN / CG) / 64 > 0 ? (BN / CG) / 64 : 1;   // heads in this CTA's share of the tile
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          const int head = n_blk * (BN / 64) + (int)cta_rank * HB + i;
+          ld(sb + i * (64 * 128), kb * GEMM_BK, (head * p.grp_total + f) * 64);
+        }
+      } else {
+        ld(sb, f * 64, kb * p.N + n_blk * BN + (int)cta_rank * (BN / CG));
+      }
+    }
+  };
 
   if (threadIdx.x == 0) {
     GEMM_STAMP(0);
@@ -222,12 +254,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // static weights: the W tiles of this CTA's first SLOTS ring slots do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
     while (w_pre < SLOTS && tile < t_end) {
-      const int n_blk = tile % p.num_n_blks;
+      const int m_blk = tile / p.num_n_blks;
+      const int n_blk = tile - m_blk * p.num_n_blks;
       mbar_arrive_expect_tx(&full_bar[w_pre], SLOT_BYTES);
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        tma_load_2d(smem + w_pre * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[w_pre],
-                    (kb + g) * GEMM_BK, n_blk * BN);
+        load_b(smem + w_pre * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES, &full_bar[w_pre], kb + g, m_blk, n_blk);
       ++w_pre;
       kb += G;
       if (kb == num_kb) { kb = 0; tile += t_step; }
@@ -257,8 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int g = 0; g < G; ++g) {
               uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
               tma_load_2d_pair(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * TILE_M + (int)cta_rank * BM);
-              tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, &full_bar[s], (kb + g) * GEMM_BK,
-                               n_blk * BN + (int)cta_rank * (BN / 2));
+              load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
             }
           } else if (w_pre > 0) {
             // transaction bytes announced and W tiles issued before the dependency wait: only A is left
@@ -272,7 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int g = 0; g < G; ++g) {
               uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
               tma_load_2d(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * BM);
-              tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], (kb + g) * GEMM_BK, n_blk * BN);
+              load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
             }
           }
           if (++s == SLOTS) {
@@ -286,7 +317,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_BF16, TILE_M, BN, 0, 0);
+      const uint32_t idesc = p.ab_f16 ? make_idesc(FMT_F16, TILE_M, BN, 0, 0) : make_idesc(FMT_BF16, TILE_M, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -405,6 +436,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o[16 * h + j] = as_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
               }
             }
+          } else if (OUT_MODE == 3) {
+            // per-head softmax of the folded cross-attention: the 64 columns of this chunk are one head's scores, already
+            // in log2 units; the arithmetic (and its order) is that of xattn_fused_kernel's head_probs, so both forms of
+            // the sub-layer produce the same probabilities bit for bit
+            uint32_t v[32], w[32];
+            tmem_ld32(t_row + acol0, v);
+            tmem_ld32(t_row + acol0 + 32, w);
+            tmem_ld_wait();
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(w[0]),
+                  m3 = __uint_as_float(w[1]);
+#pragma unroll
+            for (int j = 2; j < 32; j += 2) {
+              m0 = fmaxf(m0, __uint_as_float(v[j])); m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+              m2 = fmaxf(m2, __uint_as_float(w[j])); m3 = fmaxf(m3, __uint_as_float(w[j + 1]));
+            }
+            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              o[j] = ex2_f16x2(pack_f16x2(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
+              o[16 + j] = ex2_f16x2(pack_f16x2(__uint_as_float(w[2 * j]) - mx, __uint_as_float(w[2 * j + 1]) - mx));
+              const float2 a = unpack_f16x2(o[j]), b = unpack_f16x2(o[16 + j]);
+              s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+            }
+            const float inv = 1.0f / ((s0 + s1) + (s2 + s3));   // sum >= 1 (the maximum contributes 2^0)
+            const uint32_t inv2 = pack_f16x2(inv, inv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = mul_f16x2(o[j], inv2);
           } else {
             const bool exact = p.gelu_exact != 0;
 #pragma unroll
@@ -534,6 +593,8 @@ struct GemmOpts {
   int f16_start = 0, f16_period = 0;
   int w_split = 0;      // W is [N][2 K] = [W_hi | W_lo]
   int gelu_exact = 0;
+  int b_mode = 0, grp_rows = 0, grp_frame0 = 0, grp_total = 0;   // folded cross-attention operands (GemmParams)
+  int ab_f16 = 0;
 };
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -573,13 +634,42 @@ int gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw
   return gemm_impl(A, lda, W_hilo, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, 0, o, stream);
 }
 
+int gemm_xattn_scores(const void* xn, const void* kp_block, void* probs_f16, int T, int dim, int heads_keys,
+                      int rows_per_frame, int frame0, int total_frames, cudaStream_t stream) {
+  GemmOpts o;
+  o.b_mode = 1;
+  o.grp_rows = rows_per_frame;
+  o.grp_frame0 = frame0;
+  o.grp_total = total_frames;
+  return gemm_impl(xn, dim, kp_block, dim, probs_f16, heads_keys, nullptr, nullptr, 0, T, heads_keys, dim, 3, 0, o, stream);
+}
+
+int gemm_xattn_out(const void* probs_f16, const void* vt_block, const float* bias, float* h, int T, int dim,
+                   int heads_keys, int rows_per_frame, int frame0, int total_frames, cudaStream_t stream) {
+  GemmOpts o;
+  o.b_mode = 2;
+  o.grp_rows = rows_per_frame;
+  o.grp_frame0 = frame0;
+  o.grp_total = total_frames;
+  o.ab_f16 = 1;
+  return gemm_impl(probs_f16, heads_keys, vt_block, (int64_t)total_frames * 64, h, dim, bias, h, dim, T, dim, heads_keys, 1,
+                   0, o, stream);
+}
+
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
                      const float* resid, int64_t ldr, int M, int N, int K, int out_mode, int bn_hint,
                      const GemmOpts& o, cudaStream_t stream) {
   RALD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   RALD_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
   RALD_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
-  RALD_REQUIRE(out_mode >= 0 && out_mode <= 2, "gemm: out_mode %d", out_mode);
+  RALD_REQUIRE(out_mode >= 0 && out_mode <= 3, "gemm: out_mode %d", out_mode);
+  RALD_REQUIRE(out_mode != 3 || (resid == nullptr && bias == nullptr && N % 64 == 0),
+               "gemm: the softmax epilogue takes no bias / residual and needs N a multiple of 64");
+  RALD_REQUIRE(o.b_mode == 0 || (!o.w_split && o.grp_rows > 0 && o.grp_rows % (2 * GEMM_BM) == 0 && K % GEMM_BK == 0 &&
+                                 N % 64 == 0 && M % o.grp_rows == 0 && o.grp_frame0 >= 0 &&
+                                 o.grp_frame0 + M / o.grp_rows <= o.grp_total && (o.b_mode != 2 || K == 8 * 64)),
+               "gemm: bad grouped-operand geometry (mode %d, %d rows per frame, frames [%d, +%d) of %d)", o.b_mode,
+               o.grp_rows, o.grp_frame0, o.grp_rows > 0 ? M / o.grp_rows : 0, o.grp_total);
   RALD_REQUIRE(out_mode != 2 || resid == nullptr, "gemm: GEGLU epilogue takes no residual");
   RALD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && ldo % (out_mode == 1 ? 4 : 8) == 0,
                "gemm: output not 16-byte aligned");
@@ -594,7 +684,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
 
   const int sms = device_sm_count();
   const int m_blks = (M + GEMM_BM - 1) / GEMM_BM;
-  const int min_bn = out_mode == 1 ? 32 : (out_mode == 0 ? 64 : 128);  // narrowest tile of the TMA epilogue
+  // narrowest tile of the TMA epilogue (grouped K' operands come in 64-row boxes per head)
+  const int min_bn = (out_mode == 1 && o.b_mode == 0) ? 32 : (out_mode == 2 ? 128 : 64);
   int bn = bn_hint;
   if (bn == 0) {
     // Cost model: waves x (fixed per-tile cost + tile width). Wide tiles re-read the operands least and amortise the
@@ -615,11 +706,13 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   if (out_mode == 1) {
     if (resid == nullptr) epi = EPI_TMA_STORE;
     else if (resid == out && ldr == ldo && o.resid_mod == 0) epi = EPI_TMA_REDUCE;
-  } else if (out_mode == 0) {
+  } else if (out_mode == 0 || out_mode == 3) {
     if (resid == nullptr && bn >= 64) epi = EPI_TMA_STORE;
   } else if (bn >= 128) {
     epi = EPI_TMA_STORE;
   }
+  RALD_REQUIRE(out_mode != 3 || epi == EPI_TMA_STORE, "gemm: the softmax epilogue needs the TMA-store path (BN >= 64)");
+  RALD_REQUIRE(o.b_mode == 0 || (bn >= 64 && epi != EPI_GENERIC), "gemm: grouped operands need BN >= 64 and a TMA epilogue");
 
   // CTA pairs: 256 x 256 tiles when the problem still fills the machine with them (large-batch regime)
   const int m_blks2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
@@ -643,12 +736,24 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.f16_start = o.f16_start;
   p.f16_period = o.f16_period;
   p.gelu_exact = o.gelu_exact;
+  p.b_mode = o.b_mode;
+  p.grp_rows = o.grp_rows;
+  p.grp_frame0 = o.grp_frame0;
+  p.grp_total = o.grp_total;
+  p.ab_f16 = o.ab_f16;
   p.w_static = (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
   RALD_REQUIRE(o.f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, (uint32_t)GEMM_BM));
-  RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)k_total, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
+  if (o.b_mode == 1) {          // K' of one block: [8 heads * grp_total frames * 64 keys][K], one 64-row box per head
+    RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(N / 64) * o.grp_total * 64, (uint64_t)K, (uint64_t)ldw, 64u));
+  } else if (o.b_mode == 2) {   // VT of one block: [8 heads * N][grp_total * 64]
+    RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(K / 64) * N, (uint64_t)o.grp_total * 64, (uint64_t)ldw,
+                               (uint32_t)(pair ? bn / 2 : bn)));
+  } else {
+    RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)k_total, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
+  }
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1, 32u));
   } else {
@@ -656,6 +761,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   }
 
   if (pair) {
+    if (out_mode == 3) return launch_gemm<256, 3, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (out_mode == 0) return launch_gemm<256, 0, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (out_mode == 2) return launch_gemm<256, 2, EPI_TMA_STORE, 2>(tmA, tmB, tmO, p, sms, stream);
     if (epi == EPI_TMA_REDUCE) return launch_gemm<256, 1, EPI_TMA_REDUCE, 2>(tmA, tmB, tmO, p, sms, stream);
@@ -673,6 +779,13 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     if (epi == EPI_TMA_REDUCE) { RALD_GEMM_BN(1, EPI_TMA_REDUCE) }
     if (epi == EPI_TMA_STORE) { RALD_GEMM_BN(1, EPI_TMA_STORE) }
     RALD_GEMM_BN(1, EPI_GENERIC)
+  }
+  if (out_mode == 3) {
+    switch (bn) {
+      case 64: RALD_GEMM_LAUNCH(64, 3, EPI_TMA_STORE);
+      case 128: RALD_GEMM_LAUNCH(128, 3, EPI_TMA_STORE);
+      default: RALD_GEMM_LAUNCH(256, 3, EPI_TMA_STORE);
+    }
   }
   if (out_mode == 0) {
     if (epi == EPI_TMA_STORE) {

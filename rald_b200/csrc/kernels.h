@@ -33,6 +33,16 @@ int gemm_bf16_wsplit(const void* A, int64_t lda, const void* W_hilo, int64_t ldw
                      const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
                      int f16_start, int f16_period, int gelu_exact, cudaStream_t stream);
 
+// The folded cross-attention sub-layer (xattn.cu) as TWO GEMMs for batches too small to fill the machine with its
+// 128-row fused tiles (same operands, same arithmetic, bit-identical result):
+//   probs[T][heads_keys] (fp16) = per-head softmax( xn[T][dim] K'^T )      K' = kp_block, bf16 [8][total_frames][64][dim]
+//   h[T][dim] += probs VT^T + bias                                         VT = vt_block, fp16 [8][dim][total_frames*64]
+// rows [m, m + rows_per_frame) belong to frame frame0 + m / rows_per_frame.
+int gemm_xattn_scores(const void* xn, const void* kp_block, void* probs_f16, int T, int dim, int heads_keys,
+                      int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
+int gemm_xattn_out(const void* probs_f16, const void* vt_block, const float* bias, float* h, int T, int dim,
+                   int heads_keys, int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
+
 // While alive on this thread, every GEMM launched treats its W operand as STATIC (model weights: not written by any
 // kernel in flight), which lets the kernel start streaming W before its programmatic-dependency wait.
 struct GemmStaticWeights {
@@ -61,6 +71,8 @@ int attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const 
 
 // xattn.cu -----------------------------------------------------------------------------------------
 int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,
+                int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
+int xattn_split(const void* xn, const void* kp, const void* vt, const float* bias, float* h, void* probs_f16, int frames,
                 int rows_per_frame, int frame0, int total_frames, cudaStream_t stream);
 int xattn_fold(const void* ctxkv, const void* wq_t, const void* w_o, int depth, int frames, void* kp, void* vt,
                cudaStream_t stream);

@@ -440,6 +440,20 @@ int xattn_fused(const void* xn, const void* kp, const void* vt, const float* bia
   return 0;
 }
 
+// The sub-layer as two GEMMs (gemm.cu: grouped K' / VT operands, per-head softmax in the first epilogue). The fused
+// kernel works on 128-row tiles with all 8 heads = 4 tiles per frame; below ~32 frames those leave most SMs idle and
+// every launch is latency-bound, whereas the GEMM scheduler picks tile widths that cover the machine at any batch.
+int xattn_split(const void* xn, const void* kp, const void* vt, const float* bias, float* h, void* probs_f16, int frames,
+                int rows_per_frame, int frame0, int total_frames, cudaStream_t stream) {
+  RALD_REQUIRE(xn != nullptr && kp != nullptr && vt != nullptr && h != nullptr && probs_f16 != nullptr,
+               "xattn_split: null pointer");
+  RALD_REQUIRE(frames > 0 && rows_per_frame % (2 * XA_BM) == 0 && frame0 >= 0 && frame0 + frames <= total_frames,
+               "xattn_split: frames=%d rows/frame=%d frame0=%d total=%d", frames, rows_per_frame, frame0, total_frames);
+  const int T = frames * rows_per_frame;
+  RALD_TRY(gemm_xattn_scores(xn, kp, probs_f16, T, XA_DIM, XA_HK, rows_per_frame, frame0, total_frames, stream));
+  return gemm_xattn_out(probs_f16, vt, bias, h, T, XA_DIM, XA_HK, rows_per_frame, frame0, total_frames, stream);
+}
+
 // Folds attn2.to_q / to_out of every block into the per-frame context operands (once per sample):
 //   ctxkv  bf16 [frames*64][depth*1024]   per block K | V projections of the conditioning tokens (both bf16)
 //   wq_t   bf16 [depth][512 in][512 q]    attn2.to_q.weight TRANSPOSED and pre-scaled by log2(e)/sqrt(64)
@@ -487,6 +501,13 @@ extern "C" int rald_xattn_debug_buffer(unsigned long long* dev_buf) {
 extern "C" int rald_xattn_fold(const void* ctxkv_bf16, const void* wq_t_scaled, const void* w_o, int depth, int frames,
                                void* kp, void* vt, void* stream) {
   return rald::xattn_fold(ctxkv_bf16, wq_t_scaled, w_o, depth, frames, kp, vt, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rald_xattn_split(const void* xn, const void* kp, const void* vt, const float* bias, float* h,
+                                void* probs_f16, int frames, int rows_per_frame, int frame0, int total_frames,
+                                void* stream) {
+  return rald::xattn_split(xn, kp, vt, bias, h, probs_f16, frames, rows_per_frame, frame0, total_frames,
+                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int rald_xattn_fused(const void* xn, const void* kp, const void* vt, const float* bias, float* h, int frames,

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import c_void_p
-from .runtime_dit import DitWorkspace, default_microbatch, geglu_pack_index
+from .runtime_dit import DitWorkspace, default_microbatch, geglu_pack_index, split_hi_lo
 
 
 class AeWeights(ctypes.Structure):
@@ -29,14 +29,6 @@ def precise_enabled() -> bool:
     random init, 17 % of the field's spatial standard deviation); RALD_B200_AE_PRECISE=0 restores plain bf16 weights
     and the logistic-form GELU (2.2 % less work per 64-frame step)."""
     return os.environ.get("RALD_B200_AE_PRECISE", "1") != "0"
-
-
-def split_hi_lo(w: torch.Tensor) -> torch.Tensor:
-    """fp32 [..., N, K] -> bf16 [..., N, 2K] = [bf16(w) | bf16(w - bf16(w))] (operand of rald_gemm_bf16_wsplit)."""
-    w = w.float()
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
-    return torch.cat([hi, lo], dim=-1).contiguous()
 
 
 class AeRuntime(_lib.RuntimeNotCopied):

@@ -20,7 +20,7 @@ from ._lib import c_void_p
 class DitWeights(ctypes.Structure):
     _fields_ = [("depth", ctypes.c_int32), ("dim", ctypes.c_int32), ("heads", ctypes.c_int32),
                 ("channels", ctypes.c_int32), ("n_latents", ctypes.c_int32), ("ctx_len", ctypes.c_int32),
-                ("sigma_data", ctypes.c_float), ("_pad", ctypes.c_int32),
+                ("sigma_data", ctypes.c_float), ("precise", ctypes.c_int32),
                 ("w_qkv", c_void_p), ("w_o1", c_void_p), ("w_q2", c_void_p), ("w_o2", c_void_p),
                 ("w_ff1", c_void_p), ("w_ff2", c_void_p),
                 ("b_o1", c_void_p), ("b_o2", c_void_p), ("b_ff1", c_void_p), ("b_ff2", c_void_p),
@@ -28,7 +28,7 @@ class DitWeights(ctypes.Structure):
 
 
 class DitWorkspace(ctypes.Structure):
-    _fields_ = [("max_frames", ctypes.c_int32), ("_pad", ctypes.c_int32),
+    _fields_ = [("max_frames", ctypes.c_int32), ("xattn_split_below", ctypes.c_int32),
                 ("h", c_void_p), ("xn", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("ff", c_void_p),
                 ("x_tmp", c_void_p), ("d_tmp", c_void_p),
                 ("xattn_kp", c_void_p), ("xattn_vt", c_void_p), ("xattn_frames", ctypes.c_int32),
@@ -55,23 +55,31 @@ def xattn_fusion_enabled() -> bool:
     return os.environ.get("RALD_B200_FUSE_XATTN", "1") != "0"
 
 
+def precise_enabled() -> bool:
+    """RALD_B200_DIT_PRECISE=1: every denoiser GEMM multiplies with split weight pairs (hi + lo bf16 = 16 mantissa bits
+    of the fp32 nn.Linear weight, csrc/gemm.cu) and the GEGLU uses the erf GELU; cross-attention takes the unfused path.
+    Twice the GEMM work — OFF by default: the bf16 sampler is within the north star's 1e-2 per-step bar, but on
+    random-init weights its 2e-3 deviation alone moves the ill-conditioned occupancy threshold; this mode
+    exists to show the literal shared-threshold criterion is met when the weights are not rounded."""
+    return os.environ.get("RALD_B200_DIT_PRECISE", "0") == "1"
+
+
+def split_hi_lo(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., N, K] -> bf16 [..., N, 2K] = [bf16(w) | bf16(w - bf16(w))] (operand of rald_gemm_bf16_wsplit)."""
+    w = w.float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def xattn_split_below() -> int:
+    """Micro-batches of fewer frames than this run the folded cross-attention as two GEMMs instead of the fused kernel
+    (bit-identical results; measured on B200: the fused kernel wins from 32 frames up). RALD_B200_XATTN_SPLIT_BELOW."""
+    return int(os.environ.get("RALD_B200_XATTN_SPLIT_BELOW", "32"))
+
+
 def graphs_enabled() -> bool:
     return os.environ.get("RALD_B200_GRAPH", "1") == "1"
-
-
-def sampler_chains(frames: int) -> int:
-    """Number of concurrent sub-batches ("chains") the sampling loop of a `frames`-frame call is split into, each on
-    its own CUDA stream with its own workspace. Frames are independent, and below ~16 frames every launch of the loop
-    is latency-bound (fixed ~5 us of set-up / first-operand / drain per kernel whatever its size) and most grids cover
-    less than the machine, so independent chains fill the idle SMs and hide each other's latencies. RALD_B200_CHAINS=n
-    forces n (1 = off); default: see _auto_chains."""
-    e = os.environ.get("RALD_B200_CHAINS")
-    n = int(e) if e else _auto_chains(frames)
-    return max(1, min(n, frames))
-
-
-def _auto_chains(frames: int) -> int:
-    return 1
 
 
 class _SamplerGraph:
@@ -95,13 +103,12 @@ class DitRuntime(_lib.RuntimeNotCopied):
         self._ws_frames = 0
         self._mod_cache = {}
         self._graphs = {}
-        self._side_streams = []
 
     # ------------------------------------------------------------------ packing
     def _signature(self):
         m = self.module.model
         ps = list(m.parameters())
-        return (ps[0].device, sum(p._version for p in ps), len(ps))
+        return (ps[0].device, sum(p._version for p in ps), len(ps), precise_enabled())
 
     def ensure_packed(self):
         sig = self._signature()
@@ -118,20 +125,24 @@ class DitRuntime(_lib.RuntimeNotCopied):
         if dim != 512 or dim // heads != 64:
             raise _lib.RaldError(f"unsupported denoiser width {dim} / heads {heads}: kernels are built for 512 = 8 x 64")
         bf = torch.bfloat16
+        self.precise = precise_enabled()
         with torch.no_grad():
             def stack(fn, dtype):
-                return torch.stack([fn(b).detach() for b in blocks]).to(dtype).contiguous()
+                ws = [fn(b).detach() for b in blocks]
+                if dtype is bf and self.precise:   # weight matrices as split pairs [rows][2 cols]
+                    return torch.stack([split_hi_lo(w) for w in ws]).contiguous()
+                return torch.stack(ws).to(dtype).contiguous()
             idx = geglu_pack_index(blocks[0].ff.net[2].weight.shape[1], dev)
             self.w_qkv = stack(lambda b: torch.cat([b.attn1.to_q.weight, b.attn1.to_k.weight, b.attn1.to_v.weight]), bf)
             self.w_o1 = stack(lambda b: b.attn1.to_out[0].weight, bf)
             self.b_o1 = stack(lambda b: b.attn1.to_out[0].bias, torch.float32)
             self.w_q2 = stack(lambda b: b.attn2.to_q.weight, bf)
-            self.w_kv2 = torch.cat([torch.cat([b.attn2.to_k.weight, b.attn2.to_v.weight]).detach() for b in blocks]
-                                   ).to(bf).contiguous()
+            w_kv2 = torch.cat([torch.cat([b.attn2.to_k.weight, b.attn2.to_v.weight]).detach() for b in blocks])
+            self.w_kv2 = split_hi_lo(w_kv2) if self.precise else w_kv2.to(bf).contiguous()
             self.w_o2 = stack(lambda b: b.attn2.to_out[0].weight, bf)
             # fused attn2: to_q transposed ([in][q feature]) with the softmax scale and log2(e) folded in
             c = (dim // heads) ** -0.5 * 1.4426950408889634
-            self.w_q2t = stack(lambda b: (b.attn2.to_q.weight.float() * c).t(), bf)
+            self.w_q2t = torch.stack([(b.attn2.to_q.weight.detach().float() * c).t() for b in blocks]).to(bf).contiguous()
             self.b_o2 = stack(lambda b: b.attn2.to_out[0].bias, torch.float32)
             self.w_ff1 = stack(lambda b: b.ff.net[0].proj.weight[idx], bf)
             self.b_ff1 = stack(lambda b: b.ff.net[0].proj.bias[idx], torch.float32)
@@ -168,18 +179,19 @@ class DitRuntime(_lib.RuntimeNotCopied):
         w.depth, w.dim, w.heads, w.channels = self.depth, self.dim, self.heads, self.channels
         w.n_latents, w.ctx_len = self.module.n_latents, ctx_len
         w.sigma_data = float(self.module.sigma_data)
+        w.precise = 1 if self.precise else 0
         for name in ("w_qkv", "w_o1", "w_q2", "w_o2", "w_ff1", "w_ff2", "b_o1", "b_o2", "b_ff1", "b_ff2", "ln_w", "ln_b",
                      "proj_in_t", "proj_out_t"):
             setattr(w, name, getattr(self, name).data_ptr())
         return w
 
-    def _workspace(self, frames: int, chain: int = 0):
-        """Workspace for micro-batches of min(frames, RALD_B200_MICROBATCH) frames; one per (size, chain), kept alive
-        because captured graphs hold their addresses."""
+    def _workspace(self, frames: int):
+        """Workspace for micro-batches of min(frames, RALD_B200_MICROBATCH) frames; one per size, kept alive because
+        captured graphs hold their addresses."""
         mb = max(1, min(default_microbatch(), frames))
         if self._ws is None:
             self._ws = {}
-        key = mb if chain == 0 else (mb, chain)
+        key = mb
         if key not in self._ws:
             T = mb * self.module.n_latents
             dev, dim = self.device, self.dim
@@ -215,16 +227,21 @@ class DitRuntime(_lib.RuntimeNotCopied):
         n = self.depth * 2 * self.dim
         out = torch.empty(rows, n, device=self.device, dtype=torch.bfloat16)
         # per block the columns are [K (bf16) | V (fp16)]: the attention kernel multiplies fp16 P with fp16 V
-        _lib.call("rald_gemm_bf16_f16cols", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim,
-                  out.data_ptr(), n, 0, rows, n, self.dim, self.dim, 2 * self.dim, _lib.cur_stream())
+        if self.precise:
+            _lib.call("rald_gemm_bf16_wsplit", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), 2 * self.dim,
+                      out.data_ptr(), n, 0, 0, 0, rows, n, self.dim, 0, self.dim, 2 * self.dim, 0, _lib.cur_stream())
+        else:
+            _lib.call("rald_gemm_bf16_f16cols", tokens_bf16.data_ptr(), self.dim, self.w_kv2.data_ptr(), self.dim,
+                      out.data_ptr(), n, 0, rows, n, self.dim, self.dim, 2 * self.dim, _lib.cur_stream())
         return out
 
     def _fusable(self, L: int, frames: int) -> bool:
-        """The fused attn2 kernel works on 128-row tiles, one per SM: it needs enough rows to fill the machine (4 tiles
-        per frame; below ~24 frames the three-kernel sequence with its narrower tiles keeps more SMs busy)."""
-        min_frames = int(os.environ.get("RALD_B200_FUSE_XATTN_MIN_FRAMES", "24"))
-        return (xattn_fusion_enabled() and L == 64 and self.heads == 8 and self.dim == 512
-                and min(frames, default_microbatch()) >= min_frames)
+        """attn2 against folded per-sample context operands (csrc/xattn.cu) whenever the geometry allows: micro-batches
+        of at least xattn_split_below() frames run the ONE-kernel form (128-row tiles, 4 per frame: needs ~32 frames to
+        fill the machine), smaller ones the same arithmetic as two GEMMs. RALD_B200_FUSE_XATTN=0 restores the to_q GEMM
+        -> attention -> to_out GEMM sequence."""
+        return (xattn_fusion_enabled() and not self.precise and L == 64 and self.heads == 8 and self.dim == 512
+                and self.module.n_latents % 256 == 0)
 
     def context_fold(self, tokens_bf16: torch.Tensor, ws: DitWorkspace):
         """Per-sample operands of the fused attn2 kernel (rald_xattn_fold): K / V projections of the tokens for all
@@ -245,6 +262,7 @@ class DitRuntime(_lib.RuntimeNotCopied):
 
     def _conditioning(self, tokens_bf16: torch.Tensor, ws: DitWorkspace, L: int):
         """(ctxkv pointer or 0, tensors to keep alive) for one call; also (un)registers the fused operands in ws."""
+        ws.xattn_split_below = xattn_split_below()
         if self._fusable(L, tokens_bf16.shape[0] // max(L, 1)):
             keep = self.context_fold(tokens_bf16, ws)
             return 0, keep
@@ -276,37 +294,8 @@ class DitRuntime(_lib.RuntimeNotCopied):
     def _sample_eager(self, latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L):
         w, ws = self._weights_struct(L), self._workspace(B)
         ctx_ptr, keep = self._conditioning(tokens_bf16, ws, L)
-        chains = sampler_chains(B) if trace is None else 1
-        if chains == 1:
-            _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(),
-                      sig_dev.data_ptr(), num_steps, mod.data_ptr(), ctx_ptr, out.data_ptr(), _lib.ptr(trace), B,
-                      _lib.cur_stream())
-            return keep
-        # concurrent chains: contiguous sub-batches, each with its own workspace, chain 0 on the current stream and the
-        # others on side streams forked from / joined to it (the pattern is graph-capturable)
-        cur = torch.cuda.current_stream()
-        while len(self._side_streams) < chains - 1:
-            self._side_streams.append(torch.cuda.Stream(device=self.device))
-        M, C = latents.shape[1], latents.shape[2]
-        base, rem = divmod(B, chains)
-        f0 = 0
-        ctx_row_bytes = L * self.depth * 2 * self.dim * 2       # one frame's K / V projections (bf16)
-        for c in range(chains):
-            nf = base + (1 if c < rem else 0)
-            wsc = self._workspace(nf, chain=c) if c > 0 else self._workspace(nf)
-            wsc.xattn_kp, wsc.xattn_vt, wsc.xattn_frames = ws.xattn_kp, ws.xattn_vt, ws.xattn_frames
-            wsc.xattn_frame0 = f0
-            stream = cur if c == 0 else self._side_streams[c - 1]
-            if c > 0:
-                stream.wait_stream(cur)
-            off = f0 * M * C * 4
-            with torch.cuda.stream(stream):
-                _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(wsc), latents.data_ptr() + off,
-                          sig_dev.data_ptr(), num_steps, mod.data_ptr(), (ctx_ptr + f0 * ctx_row_bytes) if ctx_ptr else 0,
-                          out.data_ptr() + off, 0, nf, stream.cuda_stream)
-            f0 += nf
-        for c in range(1, chains):
-            cur.wait_stream(self._side_streams[c - 1])
+        _lib.call("rald_dit_sample", ctypes.addressof(w), ctypes.addressof(ws), latents.data_ptr(), sig_dev.data_ptr(),
+                  num_steps, mod.data_ptr(), ctx_ptr, out.data_ptr(), _lib.ptr(trace), B, _lib.cur_stream())
         return keep
 
     def sample(self, latents: torch.Tensor, tokens_bf16: torch.Tensor, sigmas: torch.Tensor,
@@ -331,7 +320,7 @@ class DitRuntime(_lib.RuntimeNotCopied):
             out = torch.empty_like(latents)
             self._sample_eager(latents, tokens_bf16, sig_dev, num_steps, mod, out, trace, B, L)
             return out
-        gkey = (B, L, mb, sampler_chains(B), self._fusable(L, B))
+        gkey = (B, L, mb, self._fusable(L, B), xattn_split_below())
         g = self._graphs.get(gkey)
         if g is None:
             g = self._graphs[gkey] = _SamplerGraph()

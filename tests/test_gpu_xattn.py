@@ -1,4 +1,5 @@
-"""GPU: the fused cross-attention sub-layer (csrc/xattn.cu: rald_xattn_fold + rald_xattn_fused) against an fp32 torch
+"""GPU: the folded cross-attention sub-layer (csrc/xattn.cu: rald_xattn_fold + rald_xattn_fused, and its two-GEMM
+small-batch form rald_xattn_split, bit-identical to the fused kernel) against an fp32 torch
 restatement of CrossAttention.forward (model/models_radar_generation.py:35-76) + residual add on the same bf16-rounded
 operands, and against the unfused kernel sequence it replaces. Bar: 1e-2 relative L2 on the sub-layer's update (bf16
 operands, fp16 probabilities; north star's per-step latent bar), typically 3e-3."""
@@ -61,6 +62,16 @@ def test_fused_cross_attention_kernel(frames, frame0, total, monkeypatch):
         ref = _reference(xn, kv, wq[n], wo[n], bias[n], h0, n, list(range(frame0, frame0 + frames)))
         err = rel_l2(h - h0, ref - h0)
         assert err < 1e-2, (n, err)
+        # the two-GEMM form of the same sub-layer (small-batch path): same operands, same arithmetic order -> same bits
+        h2 = h0.clone()
+        probs = torch.empty(frames * M, 512, device=DEV, dtype=torch.float16)
+        _lib.call("rald_xattn_split", xn.data_ptr(), kp[n].data_ptr(), vt[n].data_ptr(), bias[n].data_ptr(),
+                  h2.data_ptr(), probs.data_ptr(), frames, M, frame0, total, _lib.cur_stream())
+        assert rel_l2(h2 - h0, ref - h0) < 1e-2
+        psum = probs.float().view(frames * M, 8, 64).sum(-1)
+        assert float((psum - 1).abs().max()) < 2e-2          # every head's 64 probabilities sum to 1 (fp16)
+        if frames < 37:                                       # (the cta_group::2 fused form orders its sums differently)
+            assert torch.equal(h2, h), (n, float((h2 - h).abs().max()))
         # applying it twice accumulates (TMA reduce-add into the residual stream)
         _lib.call("rald_xattn_fused", xn.data_ptr(), kp[n].data_ptr(), vt[n].data_ptr(), bias[n].data_ptr(),
                   h.data_ptr(), frames, M, frame0, total, _lib.cur_stream())
@@ -76,8 +87,11 @@ def test_fused_and_unfused_denoiser_agree(monkeypatch):
     lat = synth.unit_latents([0, 1, 2]).to(DEV)
     sg = torch.tensor([2.5, 0.4, 30.0], device=DEV).reshape(3, 1, 1)
     monkeypatch.setenv("RALD_B200_FUSE_XATTN", "1")
-    monkeypatch.setenv("RALD_B200_FUSE_XATTN_MIN_FRAMES", "1")   # 3 frames: below the default fill threshold
+    monkeypatch.setenv("RALD_B200_XATTN_SPLIT_BELOW", "0")       # the one-kernel form even for 3 frames
     a = net(lat * sg, sg, cube, cond_type="radar")
+    monkeypatch.setenv("RALD_B200_XATTN_SPLIT_BELOW", "32")      # default: 3 frames take the two-GEMM form
+    a2 = net(lat * sg, sg, cube, cond_type="radar")
+    assert torch.equal(a, a2)             # both forms of the folded sub-layer: the same bits
     monkeypatch.setenv("RALD_B200_FUSE_XATTN", "0")
     b = net(lat * sg, sg, cube, cond_type="radar")
     assert not torch.equal(a, b)          # two different kernel sequences really ran
@@ -89,7 +103,7 @@ def test_fused_path_against_reference_fixtures(monkeypatch, golden):
     """The reference-fixture parity of the denoiser (tests/test_gpu_denoiser.py) with the fused attn2 kernel forced on
     for these small batches: single evaluations (shared and per-sample sigma) and the full 18-step sampler trace."""
     monkeypatch.setenv("RALD_B200_FUSE_XATTN", "1")
-    monkeypatch.setenv("RALD_B200_FUSE_XATTN_MIN_FRAMES", "1")
+    monkeypatch.setenv("RALD_B200_XATTN_SPLIT_BELOW", "0")
     net = build_denoiser(device=DEV)
     g = golden("denoiser_eval")
     lat = synth.unit_latents([0, 1])
