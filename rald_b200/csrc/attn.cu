@@ -232,28 +232,26 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int slot = p.nbuf == 2 ? (qn & 1) : 0;
         const uint32_t use = p.nbuf == 2 ? (uint32_t)(qn >> 1) : (uint32_t)qn;
         const int passes = p.parts >> 1;
-        float m_part[2], l_part[2];
         ATT_STAMP(0);
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-        if (pass >= passes) break;
+#pragma unroll 1
+        for (int pass = 0; pass < passes; ++pass) {
         const int part = 2 * pass + g;
         const uint32_t t_mine = tmem_base + (slot * p.parts + part) * p.region + lane_off;
         mbar_wait(&s_full[slot * p.parts + part], use & 1);
         tc_fence_after();
         if (pass == 0) ATT_STAMP(1);
-        // ---- ONE sweep over this half of S (TMEM -> registers is the scarce resource: 64 B/clk per SM) ----
-        // The shift m of exp2(s*c - m) starts as the exact max of the first 32 columns and is only raised when a later
-        // chunk exceeds it by more than 2^8 (lazy rescale): then the already written P columns and the running sum are
-        // multiplied by the (exact) power-of-two-like factor exp2(m_old - m_new). Any shift gives the same softmax; this
-        // one keeps every term <= 2^8 without a separate max pass.
+        // ---- two sweeps over this part of S: exact row maximum, then probabilities ----
+        // TMEM -> register reads are cheap (tools/micro/tmem_rate.cu: ~960 B/clk per SM with 8 warps, i.e. a 128 x 512
+        // fp32 score tile in ~270 clocks — round 1 assumed 64 B/clk and built a single-sweep, lazily-raised shift around
+        // that: an fp16-overflow vote after every 32 columns, a rescale path and a redo path, all inlined twice per pass.
+        // The ncu source page of that form showed the softmax warps stalled on instruction fetch (stall_no_inst: a
+        // 7 000-instruction kernel) and on the per-chunk vote chain, not on MUFU or TMEM). With the exact maximum first,
+        // every probability is <= 1: no overflow, no vote, no rescale, and the hot loop is ~130 instructions.
         float m_scaled;
         float sum;
         {
-          float s0 = 0.f;
           uint32_t va[32], vb[32];
-          // first shift: exact max of the first 32 columns (one extra pass over registers, not over TMEM)
-          auto chunk_max = [&](const uint32_t (&v)[32]) {
+          auto max32 = [&](const uint32_t (&v)[32]) {
             float c0 = __uint_as_float(v[0]), c1 = __uint_as_float(v[1]), c2 = __uint_as_float(v[2]),
                   c3 = __uint_as_float(v[3]);
 #pragma unroll
@@ -261,55 +259,47 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               c0 = fmaxf(c0, __uint_as_float(v[j])); c1 = fmaxf(c1, __uint_as_float(v[j + 1]));
               c2 = fmaxf(c2, __uint_as_float(v[j + 2])); c3 = fmaxf(c3, __uint_as_float(v[j + 3]));
             }
-            return fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2;
+            return fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
           };
-          // P is fp16 (11-bit mantissa) and so is V (kind::f16 needs both operands of one MMA in the same format; the
-          // V projection GEMM writes fp16). Per pair of scores: two FFMA (x = s*c - m), one f16x2 pack, ONE packed
-          // MUFU exp2 whose result already is the packed MMA operand, and one packed add into the chunk sum (a 16-leaf
-          // fp16 tree, widened to fp32 once per 32 columns). No per-element max: a shift that is too low shows up as
-          // an fp16 overflow (+inf) of the chunk sum, and only then is the shift raised to the chunk's exact maximum,
-          // the earlier P columns and the running sum rescaled, and the chunk redone.
-          auto chunk_probs = [&](const uint32_t (&v)[32], uint32_t (&ps)[16]) {
+          // sweep 1: exact maximum (scale > 0, so max(s) * c = max(s * c))
+          float mx = -INFINITY;
+          tmem_ld32(t_mine, va);
+#pragma unroll 1
+          for (int c = 0; c < half; c += 64) {
+            tmem_ld_wait();
+            if (c + 32 < half) tmem_ld32(t_mine + c + 32, vb);
+            mx = fmaxf(mx, max32(va));
+            if (c + 32 < half) {
+              tmem_ld_wait();
+              if (c + 64 < half) tmem_ld32(t_mine + c + 64, va);
+              mx = fmaxf(mx, max32(vb));
+            }
+          }
+          m_scaled = mx * p.scale_log2;
+          // sweep 2: p = 2^(s c - m) <= 1 as packed fp16 pairs (= the MMA operand of P V), written back over S columns
+          // that have been consumed; row sum through a 16-leaf fp16 tree per 32 columns, widened to fp32.
+          // Per pair of scores: two FFMA, two fp32 MUFU exp2, one cvt.rn.f16x2 pack (24 elements / clk / SM; the packed
+          // ex2.approx.f16x2 round 1 used runs at a quarter of the fp32 instruction's rate: tools/micro/exp_rate.cu).
+          float s0 = 0.f;
+          auto emit = [&](const uint32_t (&v)[32], int c) {
+            uint32_t ps[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              ps[j] = ex2_f16x2(pack_f16x2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled),
-                                           fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled)));
+              ps[j] = pack_f16x2(ex2_f32(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_scaled)),
+                                 ex2_f32(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_scaled)));
             uint32_t t[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) t[j] = add_f16x2(ps[2 * j], ps[2 * j + 1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) t[j] = add_f16x2(t[2 * j], t[2 * j + 1]);
             const float2 a = unpack_f16x2(add_f16x2(t[0], t[1])), b = unpack_f16x2(add_f16x2(t[2], t[3]));
-            return (a.x + a.y) + (b.x + b.y);
-          };
-          auto emit = [&](const uint32_t (&v)[32], int c) {
-            uint32_t ps[16];
-            float cs = chunk_probs(v, ps);
-            const bool raise = !(cs < 3.0e38f);  // +inf (or NaN): some probability left the fp16 range
-            if (__any_sync(0xffffffffu, raise)) {
-              const float m_new = raise ? chunk_max(v) : m_scaled;
-              const float f = ex2_approx(m_scaled - m_new);  // 1 for the lanes that keep their shift
-              const uint32_t f2 = pack_f16x2(f, f);
-              for (int pc = 0; pc < (c >> 1); pc += 16) {
-                uint32_t pk[16];
-                tmem_ld16(t_mine + pc, pk);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = mul_f16x2(pk[j], f2);
-                tmem_st16(t_mine + pc, pk);
-              }
-              s0 *= f;
-              m_scaled = m_new;
-              cs = chunk_probs(v, ps);
-            }
-            s0 += cs;
+            s0 += (a.x + a.y) + (b.x + b.y);
             tmem_st16(t_mine + (c >> 1), ps);  // columns [c/2, c/2+16): below every column still to be read
           };
           tmem_ld32(t_mine, va);
-          tmem_ld_wait();
-          m_scaled = chunk_max(va);
+#pragma unroll 1
           for (int c = 0; c < half; c += 64) {
-            if (c != 0) tmem_ld_wait();
+            tmem_ld_wait();
             if (c + 32 < half) tmem_ld32(t_mine + c + 32, vb);
             emit(va, c);
             if (c + 32 < half) {
@@ -324,20 +314,15 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[slot * p.parts + part]);
-        m_part[pass] = m_scaled;
-        l_part[pass] = sum;
+        // (shift, sum) of this key part -> shared memory. The previous tile's readers of this slot are past their
+        // named barrier 3, which every softmax warp crosses after its last read.
+        s_stat[slot * (2 * 2 * ATT_BM) + (part * 2 + 0) * ATT_BM + row_in_tile] = m_scaled;
+        s_stat[slot * (2 * 2 * ATT_BM) + (part * 2 + 1) * ATT_BM + row_in_tile] = sum;
         }  // pass
         ATT_STAMP(2);
 
         // ---- exchange (max, sum) of every key part ----
         float* st = s_stat + slot * (2 * 2 * ATT_BM);   // [part][m, l][128]; parts = 4 only occurs with one slot
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          if (pass < passes) {
-            st[((2 * pass + g) * 2 + 0) * ATT_BM + row_in_tile] = m_part[pass];
-            st[((2 * pass + g) * 2 + 1) * ATT_BM + row_in_tile] = l_part[pass];
-          }
-        }
         // (the thread that issues the output TMA stores first makes sure the previous tile's store has read the staging
         // tile: everybody may overwrite it after the barrier)
         if (threadIdx.x == 64) bulk_wait_group_read<0>();

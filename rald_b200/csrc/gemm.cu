@@ -455,8 +455,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              o[j] = ex2_f16x2(pack_f16x2(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
-              o[16 + j] = ex2_f16x2(pack_f16x2(__uint_as_float(w[2 * j]) - mx, __uint_as_float(w[2 * j + 1]) - mx));
+              o[j] = pack_f16x2(ex2_f32(__uint_as_float(v[2 * j]) - mx), ex2_f32(__uint_as_float(v[2 * j + 1]) - mx));
+              o[16 + j] = pack_f16x2(ex2_f32(__uint_as_float(w[2 * j]) - mx), ex2_f32(__uint_as_float(w[2 * j + 1]) - mx));
               const float2 a = unpack_f16x2(o[j]), b = unpack_f16x2(o[16 + j]);
               s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
             }

@@ -417,6 +417,15 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// 2^x, fp32 (MUFU.EX2: 32 results per clock per SM on B200). Measured with tools/micro/exp_rate.cu: the packed half
+// form below, ex2.approx.f16x2, issues at a QUARTER of this instruction's rate (17.3 vs 4.3 clocks per warp instruction
+// per scheduler), i.e. it delivers HALF as many exponentials per clock — a softmax is faster computing fp32 exponentials
+// and packing them with one cvt.rn.f16x2.f32 per pair (29.6 vs 14.8 elements per clock per SM incl. the scale FFMAs).
+__device__ __forceinline__ float ex2_f32(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
   uint32_t r;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));

@@ -277,8 +277,13 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tc_fence_after();
       if (warp == 2 && lane == 0) XA_STAMP(8);
       const uint32_t t_set = tmem_base + lane_off + 256u * hs;   // S columns of this head set; P goes to its start
-      // one head (64 score columns) at a time; the TMEM loads of the next head are in flight during the arithmetic
-      auto head_probs = [&](const uint32_t (&v)[32], const uint32_t (&w)[32], int g) {
+      // One head (64 score columns) at a time. The next head's columns are fetched while this one is processed, in two
+      // halves (the second half is only issued once this head's first 32 scores are dead), which keeps the peak at ~130
+      // live registers: the 168 available with 10 warps per CTA then hold the kernel without spills (round 1 prefetched
+      // the whole next head up front and spilled 350 - 540 bytes per thread).
+      auto head_probs = [&](const uint32_t (&v)[32], const uint32_t (&w)[32], uint32_t (&nv)[32], uint32_t (&nw)[32],
+                            int g, bool more) {
+        if (more) tmem_ld32(t_set + 64 * (g + 1), nv);
         float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(w[0]),
               m3 = __uint_as_float(w[1]);
 #pragma unroll
@@ -292,38 +297,36 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          lo[j] = ex2_f16x2(pack_f16x2(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
-          hi[j] = ex2_f16x2(pack_f16x2(__uint_as_float(w[2 * j]) - mx, __uint_as_float(w[2 * j + 1]) - mx));
-          const float2 a = unpack_f16x2(lo[j]), b = unpack_f16x2(hi[j]);
-          s0 += a.x; s1 += a.y; s2 += b.x; s3 += b.y;
+          lo[j] = pack_f16x2(ex2_f32(__uint_as_float(v[2 * j]) - mx), ex2_f32(__uint_as_float(v[2 * j + 1]) - mx));
+          const float2 a = unpack_f16x2(lo[j]);
+          s0 += a.x; s1 += a.y;
+        }
+        if (more) tmem_ld32(t_set + 64 * (g + 1) + 32, nw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          hi[j] = pack_f16x2(ex2_f32(__uint_as_float(w[2 * j]) - mx), ex2_f32(__uint_as_float(w[2 * j + 1]) - mx));
+          const float2 b = unpack_f16x2(hi[j]);
+          s2 += b.x; s3 += b.y;
         }
         const float inv = 1.0f / ((s0 + s1) + (s2 + s3));   // sum >= 1 (the maximum contributes 2^0)
         const uint32_t inv2 = pack_f16x2(inv, inv);
 #pragma unroll
         for (int j = 0; j < 16; ++j) { lo[j] = mul_f16x2(lo[j], inv2); hi[j] = mul_f16x2(hi[j], inv2); }
-        // P of local head g -> columns [32 g, 32 g + 32) of the set's region: inside S columns this warp has consumed
-        // (heads g and g + 1 are both in registers before the first store that could touch them is issued)
+        // P of local head g -> columns [32 g, 32 g + 32) of the set's region: S columns of head g / 2, which this warp
+        // consumed (loaded AND waited for) before; the loads in flight address head g + 1 = columns >= 64 (g + 1)
         tmem_st16(t_set + 32 * g, lo);
         tmem_st16(t_set + 32 * g + 16, hi);
+        if (more) tmem_ld_wait();
       };
       {
         uint32_t va[32], wa[32], vb[32], wb[32];
         tmem_ld32(t_set, va);
         tmem_ld32(t_set + 32, wa);
         tmem_ld_wait();
-        tmem_ld32(t_set + 64, vb);
-        tmem_ld32(t_set + 96, wb);
-        head_probs(va, wa, 0);          // writes columns [0, 32): head 0, in registers
-        tmem_ld_wait();                 // head 1 in registers
-        tmem_ld32(t_set + 128, va);
-        tmem_ld32(t_set + 160, wa);
-        head_probs(vb, wb, 1);          // writes [32, 64): head 0's columns
-        tmem_ld_wait();                 // head 2 in registers
-        tmem_ld32(t_set + 192, vb);
-        tmem_ld32(t_set + 224, wb);
-        head_probs(va, wa, 2);          // writes [64, 96): head 1's columns
-        tmem_ld_wait();                 // head 3 in registers
-        head_probs(vb, wb, 3);          // writes [96, 128)
+        head_probs(va, wa, vb, wb, 0, true);
+        head_probs(vb, wb, va, wa, 1, true);
+        head_probs(va, wa, vb, wb, 2, true);
+        head_probs(vb, wb, va, wa, 3, false);
       }
       tmem_st_wait();
       tc_fence_before();

@@ -5,6 +5,7 @@
 //   cvt     cvt.rn.f16x2.f32 alone          ex2h    ex2.approx.f16x2 alone
 //   poly    Cody-Waite + degree-3 polynomial on the FMA pipe (no MUFU), result packed to f16x2
 //   mix     half the pairs through f16x2 MUFU, half through the polynomial
+//   f32+cvt two FFMA, two fp32 MUFU exp2, one cvt.rn.f16x2.f32 pack per pair
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I rald_b200/csrc tools/micro/exp_rate.cu -o tools/micro/_bin/exp_rate
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, float* sink, int ite
       else if (MODE == 2) { acc ^= cvt_v(a, b); }
       else if (MODE == 3) { acc ^= ex2h_v(__float_as_uint(a) + j); }
       else if (MODE == 4) { acc ^= cvt_v(exp2_poly(fmaf(a, c, -m)), exp2_poly(fmaf(b, c, -m))); }
+      else if (MODE == 6) { acc ^= cvt_v(ex2f(fmaf(a, c, -m)), ex2f(fmaf(b, c, -m))); }     // attn_d64's round-2 recipe
       else if (MODE == 5) {
         if (j & 1) acc ^= cvt_v(exp2_poly(fmaf(a, c, -m)), exp2_poly(fmaf(b, c, -m)));
         else acc ^= ex2h_v(cvt_v(fmaf(a, c, -m), fmaf(b, c, -m)));
@@ -76,9 +78,9 @@ void run(const char* name, int threads) {
 int main() {
   for (int threads : {256, 512}) {
     if (threads == 256) {
-      run<0>("f32", 256); run<1>("f16x2", 256); run<2>("cvt", 256); run<3>("ex2h", 256); run<4>("poly", 256); run<5>("mix", 256);
+      run<0>("f32", 256); run<1>("f16x2", 256); run<2>("cvt", 256); run<3>("ex2h", 256); run<4>("poly", 256); run<5>("mix", 256); run<6>("f32+cvt", 256);
     } else {
-      run<0>("f32", 512); run<1>("f16x2", 512); run<2>("cvt", 512); run<3>("ex2h", 512); run<4>("poly", 512); run<5>("mix", 512);
+      run<0>("f32", 512); run<1>("f16x2", 512); run<2>("cvt", 512); run<3>("ex2h", 512); run<4>("poly", 512); run<5>("mix", 512); run<6>("f32+cvt", 512);
     }
   }
   return 0;
