@@ -81,9 +81,10 @@ def parse(argv=None):
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the secondary weak-scaling figure")
     ap.add_argument("--no-sharding-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the sampler")
-    ap.add_argument("--ref-evals", type=int, default=NET_EVALS,
-                    help="CPU arm: network evaluations actually timed per frame (default: all 35 = nothing extrapolated "
-                         "inside the frame; fewer = the first ones of the Heun schedule, scaled linearly and flagged)")
+    ap.add_argument("--ref-budget", type=float, default=150.0,
+                    help="CPU arm: seconds the K timed steps may take in all (each step = one bounded sample of a frame)")
+    ap.add_argument("--ref-evals", type=int, default=0,
+                    help="CPU arm: cap on the network evaluations per step (tests; 0 = sized from --ref-budget)")
     return ap.parse_args(argv)
 
 
@@ -202,65 +203,100 @@ def workload_config(args, world, scaling, global_frames, spans):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's PyTorch modules on the host cores
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_frame(queries_total: int, query_chunk: int = 65536, evals_timed: int = NET_EVALS):
-    """ONE WHOLE frame on the host cores as the reference runs it (fp32, torch CPU): the 18-step Heun loop with the
-    radar encoder + tokens inside EVERY network evaluation (models_radar_generation.py:412-430, 235-275), then
-    KLAutoEncoder.decode of all `queries_total` queries (models_ae.py:408-424; the query set is walked in chunks so the
-    [Q, 512] fp32 temporaries stay bounded — same arithmetic). Nothing is extrapolated inside the frame."""
-    from oracle import rald_oracle as orc
-    from rald_b200 import synth
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    net, vae = build_models("cpu")
-    sd = {k: v.detach().float() for k, v in net.state_dict().items()}
-    sd_ae = {k: v.detach().float() for k, v in vae.state_dict().items()}
-    cube = frame_cubes(0, 1)
-    lat = synth.unit_latents([0])
-    q = synth.query_points(1, queries_total)
-    t = orc.karras_sigmas()
+class CpuReference:
+    """The reference's fp32 CPU path for ONE frame (oracle port of its PyTorch modules, all host threads): the 18-step
+    Heun loop with the radar encoder + tokens inside EVERY network evaluation (models_radar_generation.py:412-430,
+    235-275), then KLAutoEncoder.decode (models_ae.py:408-424; queries walked in chunks of 65 536 so the [Q, 512] fp32
+    temporaries stay bounded — same arithmetic). `step(evals, queries)` runs a bounded SAMPLE of the frame — the first
+    `evals` of the 35 evaluations of the real Heun schedule, the latent stack, `queries` of the Q decoder queries — and
+    returns its measured parts; evals = 35 and queries = Q is the whole frame, nothing extrapolated."""
 
-    def net_eval(x, sigma):
-        tok = orc.process_radar_cond(sd, cube)          # inside every evaluation, as the reference
-        return orc.edm_precond(sd, x, sigma, tok)
+    def __init__(self, queries_total: int):
+        from oracle import rald_oracle as orc
+        from rald_b200 import synth
+        self.orc = orc
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        net, vae = build_models("cpu")
+        self.sd = {k: v.detach().float() for k, v in net.state_dict().items()}
+        self.sd_ae = {k: v.detach().float() for k, v in vae.state_dict().items()}
+        self.cube = frame_cubes(0, 1)
+        self.lat = synth.unit_latents([0])
+        self.Q = queries_total
+        self.q = synth.query_points(1, queries_total)
+        self.t = orc.karras_sigmas()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            self.net_eval(self.lat * self.t[0], self.t[0])      # warm-up (oneDNN primitive creation)
+            t1 = time.perf_counter()
+            self.net_eval(self.lat * self.t[0], self.t[0])
+            self.t_eval_est = time.perf_counter() - t1
+            x = orc.ae_latent_stack(self.sd_ae, self.lat)
+            t2 = time.perf_counter()
+            orc.ae_query(self.sd_ae, x, self.q[:, :16384])
+            self.t_query_est = (time.perf_counter() - t2) / 16384
+            self.warmup_s = time.perf_counter() - t0
 
-    with torch.no_grad():
-        net_eval(lat * t[0], t[0])                      # warm-up (oneDNN primitive creation), not timed
+    def net_eval(self, x, sigma):
+        tok = self.orc.process_radar_cond(self.sd, self.cube)          # inside every evaluation, as the reference
+        return self.orc.edm_precond(self.sd, x, sigma, tok)
+
+    def frame_estimate_s(self) -> float:
+        return NET_EVALS * self.t_eval_est + self.Q * self.t_query_est
+
+    @torch.no_grad()
+    def step(self, evals: int = NET_EVALS, queries: int = 0, chunk: int = 65536):
+        orc, t = self.orc, self.t
+        evals = max(1, min(int(evals), NET_EVALS))
+        queries = self.Q if queries <= 0 else max(1, min(int(queries), self.Q))
         t0 = time.perf_counter()
-        x = lat * t[0]
-        evals = 0
-        evals_timed = max(1, min(int(evals_timed), NET_EVALS))
+        x = self.lat * t[0]
+        n = 0
         for i in range(18):
-            if evals >= evals_timed:
+            if n >= evals:
                 break
-            d = (x - net_eval(x, t[i])) / t[i]
+            d = (x - self.net_eval(x, t[i])) / t[i]
             x_e = x + (t[i + 1] - t[i]) * d
-            evals += 1
-            if i < 17 and evals < evals_timed:
-                d2 = (x_e - net_eval(x_e, t[i + 1])) / t[i + 1]
+            n += 1
+            if i < 17 and n < evals:
+                d2 = (x_e - self.net_eval(x_e, t[i + 1])) / t[i + 1]
                 x = x + (t[i + 1] - t[i]) * (0.5 * d + 0.5 * d2)
-                evals += 1
+                n += 1
             else:
                 x = x_e
-        t_sample = (time.perf_counter() - t0) * (NET_EVALS / evals)     # == measured when all 35 were run
-        t_scaled = t_sample * (1.0 - evals / NET_EVALS)                  # part of t_sample that was NOT measured
         t1 = time.perf_counter()
-        ctx = orc.ae_latent_stack(sd_ae, x)
-        t_stack = time.perf_counter() - t1
+        ctx = orc.ae_latent_stack(self.sd_ae, x)
         t2 = time.perf_counter()
-        for c0 in range(0, queries_total, query_chunk):
-            orc.ae_query(sd_ae, ctx, q[:, c0:c0 + query_chunk])
-        t_q = time.perf_counter() - t2
-        t_frame = time.perf_counter() - t0 + t_scaled
-        t3 = time.perf_counter(); orc.process_radar_cond(sd, cube); t_enc = time.perf_counter() - t3
-    whole = evals == NET_EVALS
-    return {"value": 1.0 / t_frame, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": ((f"1 whole frame: {NET_EVALS} network evaluations" if whole else
-                        f"1 frame, {evals} of {NET_EVALS} network evaluations timed and scaled linearly (--ref-evals),")
-                       + f" as the reference runs them (radar encoder inside "
-                       f"each; {t_sample:.1f} s) + decoder latent stack ({t_stack:.2f} s) + all {queries_total} decoder "
-                       f"queries ({t_q:.1f} s); oracle port of the reference's fp32 PyTorch CPU path, {threads} threads"),
-            "whole_frame": whole, "s_per_frame": t_frame, "s_per_net_eval": t_sample / NET_EVALS,
-            "hoisted_value": 1.0 / (t_frame - (NET_EVALS - 1) * t_enc)}
+        for c0 in range(0, queries, chunk):
+            orc.ae_query(self.sd_ae, ctx, self.q[:, c0:min(c0 + chunk, queries)])
+        t3 = time.perf_counter()
+        t_evals, t_stack, t_q = t1 - t0, t2 - t1, t3 - t2
+        # the frame this sample stands for (== the measured time when evals = 35 and queries = Q)
+        t_frame = t_evals * (NET_EVALS / n) + t_stack + t_q * (self.Q / queries)
+        return {"step_s": t3 - t0, "frame_s": t_frame, "evals": n, "queries": queries, "t_evals": t_evals,
+                "t_stack": t_stack, "t_q": t_q, "whole_frame": n == NET_EVALS and queries == self.Q}
+
+    def describe(self, r) -> str:
+        what = ("1 whole frame: all 35 network evaluations" if r["evals"] == NET_EVALS else
+                f"bounded sample of 1 frame: the first {r['evals']} of 35 network evaluations (scaled linearly)")
+        qs = (f"all {self.Q} decoder queries" if r["queries"] == self.Q else
+              f"{r['queries']} of {self.Q} decoder queries (scaled linearly)")
+        return (f"{what} as the reference runs them (radar encoder inside each; {r['t_evals']:.1f} s) + decoder latent "
+                f"stack ({r['t_stack']:.2f} s) + {qs} ({r['t_q']:.1f} s); oracle port of the reference's fp32 PyTorch "
+                f"CPU path, {self.threads} threads")
+
+
+def cpu_reference_frame(queries_total: int):
+    """cpu_baseline of our arm: ONE WHOLE frame, nothing extrapolated inside it."""
+    ref = CpuReference(queries_total)
+    r = ref.step()
+    t3 = time.perf_counter()
+    with torch.no_grad():
+        ref.orc.process_radar_cond(ref.sd, ref.cube)
+    t_enc = time.perf_counter() - t3
+    return {"value": 1.0 / r["frame_s"], "unit": UNIT, "cores": ref.threads, "kind": "port", "sample": ref.describe(r),
+            "whole_frame": r["whole_frame"], "s_per_frame": r["frame_s"], "s_per_net_eval": r["t_evals"] / r["evals"],
+            "hoisted_value": 1.0 / (r["frame_s"] - (NET_EVALS - 1) * t_enc)}
 
 
 def cpu_ae_frame():
@@ -288,32 +324,48 @@ def cpu_ae_frame():
 
 
 def run_reference(args, rank, world=1):
-    """The reference arm: the CPU path alone. Rank 0 only; the figure does not depend on --gpus (one host)."""
+    """The reference arm: the CPU path alone. Rank 0 only; the figure does not depend on --gpus (one host).
+
+    W untimed + K timed steps, each step ONE bounded sample of one frame of the workload (CpuReference.step) sized so
+    that the K steps take about --ref-budget seconds in all: whole frames when K x (time per frame) fits (the default
+    K = 5 on a 16-core host: 13 s per frame), otherwise the first n of the 35 evaluations and a proportional share of
+    the decoder queries, scaled linearly to the frame. `ms_per_step` is the MEASURED mean duration of those steps (so
+    steps x ms_per_step is time really spent); `value` = frames per second of the frame each step stands for."""
     if rank != 0:
         return
     t_all = time.perf_counter()
     scaling, G, spans = plan(args, world)
-    res, vals = None, []
-    for _ in range(max(1, min(args.steps, 2))):          # each sample is one whole frame (10 - 30 s of CPU work)
-        res = cpu_reference_frame(args.queries, evals_timed=args.ref_evals)
-        vals.append(res["value"])
-    value = statistics.median(vals)
-    timed_s = sum(1.0 / v for v in vals)
+    ref = CpuReference(args.queries)
+    K = max(1, args.steps)
+    frac = min(1.0, args.ref_budget / (K * max(ref.frame_estimate_s(), 1e-3)))
+    evals = NET_EVALS if frac >= 1.0 else max(1, int(round(NET_EVALS * frac)))
+    if args.ref_evals:
+        evals = max(1, min(args.ref_evals, NET_EVALS))
+        frac = min(frac, evals / NET_EVALS)
+    queries = args.queries if frac >= 1.0 else max(4096, int(args.queries * frac))
+    for _ in range(min(args.warmup, 1)):                 # the constructor already ran warm-up evaluations / queries
+        ref.step(1, 4096)
+    runs = [ref.step(evals, queries) for _ in range(K)]
+    frame_s = statistics.median(r["frame_s"] for r in runs)
+    step_ms = 1000.0 * sum(r["step_s"] for r in runs) / K
+    value = 1.0 / frame_s
+    whole = all(r["whole_frame"] for r in runs)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * G / value,   # one step = the job's global_frames frames, as in our arm
-            "extrapolated": (f"frames are independent and walked one at a time: {len(vals)} "
-                             f"{'whole ' if res['whole_frame'] else 'PARTIAL (--ref-evals) '}frame(s) timed "
-                             f"({timed_s:.1f} s per-frame total), ms_per_step = {G} x the per-frame time"),
-            "timed_s": timed_s, "frames_timed": len(vals),
+            "steps": K, "warmup": args.warmup, "ms_per_step": step_ms,
+            "step_definition": ("one step = " + ("ONE WHOLE frame" if whole else "a bounded sample of ONE frame") +
+                                " on the host cores (our arm's step is the job's " + str(G) + " frames on the GPUs); "
+                                "value = 1 / (seconds per frame)"),
+            "extrapolated": not whole, "sample_fraction_of_frame": frac if not whole else 1.0,
+            "timed_s": sum(r["step_s"] for r in runs), "frames_timed": K if whole else 0,
+            "ms_per_global_step_extrapolated": 1000.0 * G * frame_s,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world, scaling, G, spans),
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.threads, "kind": "port",
+                             "sample": ref.describe(runs[-1])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": None,
             "note": "CPU arm: one host process on all host cores; its value is the same whatever --gpus says, so a "
                     "ratio of the N-GPU line to this line is N GPUs against ONE host, not a scaling figure"}
-    line["cpu_baseline"]["value"] = value
     line["wall_s"] = time.perf_counter() - t_all
     print(json.dumps(line), flush=True)
 
