@@ -547,6 +547,93 @@ def leg_ae_frame(dev, peaks):
     return out
 
 
+def leg_train_step(dev, peaks, batches=(8, 64)):
+    """one training step of the denoiser (EDMLoss forward + backward over every denoiser parameter,
+    radar encoder frozen = the reference's frozen-encoder option) at the reference's batch size (train.batch_size: 8)
+    and at 64 frames, tokens precomputed; and the reference's formulation under torch autograd on the same GPU (the
+    oracle port of its modules: eager fp32, and eager with torch.autocast(bf16) + SDPA) as library-kernel anchors.
+    Algorithmic work: 3 x 130.494 GFLOP per frame (forward + twice that backward); the step here EXECUTES 4 x (the
+    forward is recomputed block by block, as the reference's checkpoint=True does)."""
+    import torch.nn.functional as Fn
+    from oracle import rald_oracle as orc
+    from rald_b200 import synth
+    from rald_b200.models_radar_generation import EDMLoss
+    net, _ = build_models(dev)
+    net.train()
+    net.radar_enc.requires_grad_(False)
+    crit = EDMLoss()
+    out = {"workload": "EDMLoss forward + backward, default denoiser (24 blocks), radar encoder frozen, tokens resident",
+           "gflop_per_frame_algorithmic": 3 * GFLOP_PER_EVAL}
+    for B in batches:
+        with torch.no_grad():
+            tok = net.process_radar_cond(frame_cubes(0, B).to(dev))
+        y = (synth.unit_latents(range(B)) * 0.7).to(dev)
+
+        def step():
+            for p in net.parameters():
+                p.grad = None
+            loss = crit(net, y, tok, "radar")
+            loss.backward()
+            return loss
+        ms = cuda_time(step, 3, warm=2)
+        tf = B * 3 * GFLOP_PER_EVAL / ms
+        out[f"batch{B}"] = {"ms_per_step": ms, "frames_per_s": B / (ms * 1e-3), "tflops_algorithmic": tf,
+                            "frac_of_sustained_bf16": tf / peaks["bf16_tflops_sustained"],
+                            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del net
+    torch.cuda.empty_cache()
+    # ---- anchors: the reference's modules (oracle port) under torch autograd, batch 8 ----
+    try:
+        B = batches[0]
+        net_c, _ = build_models("cpu")
+        sd = {k: v.detach().float().to(dev) for k, v in net_c.state_dict().items()}
+        del net_c
+        for k, v in sd.items():
+            if not k.startswith("radar_enc."):
+                v.requires_grad_(True)
+        with torch.no_grad():
+            tok = orc.process_radar_cond(sd, frame_cubes(0, B).to(dev))
+        y = (synth.unit_latents(range(B)) * 0.7).to(dev)
+
+        def eager_step():
+            for v in sd.values():
+                v.grad = None
+            rnd = torch.randn([B, 1, 1], device=dev)
+            sigma = (rnd * 1.2 - 1.2).exp()
+            weight = (sigma ** 2 + 1) / sigma ** 2
+            n = torch.randn_like(y) * sigma
+            D = orc.edm_precond(sd, y + n, sigma, tok)
+            loss = (weight * (D.float() - y) ** 2).mean()
+            loss.backward()
+            return loss
+        ms32 = cuda_time(eager_step, 2, warm=1)
+        saved = orc._heads_attention
+
+        def sdpa_heads(qq, kk, vv, heads):
+            Bq, Sq, Dm = qq.shape
+            dh = Dm // heads
+            qh = qq.view(Bq, Sq, heads, dh).transpose(1, 2)
+            kh = kk.view(Bq, -1, heads, dh).transpose(1, 2)
+            vh = vv.view(Bq, -1, heads, dh).transpose(1, 2)
+            return Fn.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(Bq, Sq, Dm)
+        orc._heads_attention = sdpa_heads
+        try:
+            def eager_bf16():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return eager_step()
+            ms16 = cuda_time(eager_bf16, 2, warm=1)
+        finally:
+            orc._heads_attention = saved
+        out["torch_eager_anchor"] = {"batch": B, "fp32_ms_per_step": ms32, "bf16_autocast_sdpa_ms_per_step": ms16,
+                                     "note": "oracle port of the reference modules under torch autograd (no activation "
+                                             "checkpointing), same GPU; reported baselines, not on the product path"}
+        del sd
+    except Exception as e:  # noqa: BLE001
+        out["torch_eager_anchor"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def leg_query_sweep(vae, dev, peaks):
     """configs[3]: decoder queries at Q = 2^16 ... 2^20 per frame against ONE latent set (stack timed separately).
     The executed (folded) formulation is tensor-bound: 0.5775 MFLOP and 16 B of mandatory HBM traffic per query."""
@@ -827,6 +914,11 @@ def run_ours(args, rank, world, local_rank):
                 line["latency_b1"] = leg_latency_b1(net, vae, dev, Q, cap, peaks)
             line["query_sweep"] = leg_query_sweep(vae, dev, peaks)
             line["ae_frame"] = leg_ae_frame(dev, peaks)
+            try:
+                line["train_step"] = leg_train_step(dev, peaks)
+            except Exception as e:  # noqa: BLE001  (a failure here only drops the key)
+                line["train_step"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+                torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not args.quick and not args.no_gpu_eager_baseline:
             # after the timed regions; a failure here (e.g. out of memory next to the resident models) only drops the key

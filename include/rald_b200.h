@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RALD_ABI_VERSION 3
+#define RALD_ABI_VERSION 4
 
 int rald_abi_version(void);
 const char* rald_last_error(void);
@@ -480,6 +480,69 @@ int rald_ema_chunk_elems(void);
  * reference then averages over the batch); ws: int32 [3 * B] scratch. */
 int rald_occupancy_iou(const float* logits, const float* labels, int B, int64_t Q, float threshold, float* out,
                        int32_t* ws, void* stream);
+
+/* ---- the backward pass of the denoiser (EDMLoss under autograd,
+ * model/models_radar_generation.py:277-295 called at engine_generation.py:89-110). The matrix products of the
+ * backward pass are calls of rald_gemm_bf16: dgrad = dY W with a transposed bf16 copy of the weight as the W operand,
+ * wgrad = dY^T X over K = rows with transposed activations and out_mode 1 / resid = out (fp32 accumulation by the
+ * TMA reduce-add epilogue). The entry points below are what surrounds them. ---- */
+
+/* rald_attn_d64 that also writes the softmax statistics stats f32 [frames*Sq][heads][2] = (row maximum m in log2
+ * units with the scale folded in, row sum l of 2^(s - m)): what rald_attn_d64_bwd recomputes the probabilities from. */
+int rald_attn_d64_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                        int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, float* stats, void* stream);
+
+/* Backward of rald_attn_d64 (autograd through the einsum / softmax / einsum of CrossAttention.forward,
+ * model/models_radar_generation.py:66-75): given Q, K, V (bf16; v_f16 must be 0 — tcgen05 kind::f16 rejects products of
+ * an fp16 with a bf16 operand, so the fp16 V of the forward is re-encoded with rald_cast_f16_bf16), the forward output O
+ * (bf16), its statistics and dO (bf16), writes dQ [frames*Sq][..], dK and dV
+ * [frames*Skv][..] as bf16 into columns [h*64, h*64+64) of rows of pitch lddq / lddk / lddv. Sq % 128 == 0; Skv = 64
+ * or a multiple of 128; heads <= 8. Scratch: lse2_ws, dsum_ws f32 [frames*heads*Sq] each. Deterministic. */
+int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int v_f16,
+                      const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* stats, float* lse2_ws,
+                      float* dsum_ws, void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, int frames,
+                      int heads, int Sq, int Skv, float scale, void* stream);
+
+/* in [R, C] (f32 when in_f32, else bf16; pitch ld_in) -> out_bf16 [R, C] (optional) and out_t_bf16 [C, R] (optional,
+ * pitch ld_t >= R): the bf16 / transposed operands of the dgrad and wgrad GEMMs. */
+int rald_cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t C, void* out_bf16, int64_t ld_out,
+                        void* out_t_bf16, int64_t ld_t, void* stream);
+
+/* out_bf16 [R, C] = bf16(in_f16 [R, C]) (pitches in elements): the V columns rald_attn_d64 consumed as fp16, re-encoded
+ * for rald_attn_d64_bwd. */
+int rald_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int64_t R, int64_t C,
+                       void* stream);
+
+/* out[c] (+)= sum over rows of in[r][c] (bias gradients); two deterministic stages through partial_ws
+ * (f32, >= min(512, ceil(R/256)) * C elements). */
+int rald_colsum(const void* in, int in_f32, int64_t ld, int64_t R, int64_t C, float* partial_ws, int64_t ws_elems,
+                float* out, int accumulate, void* stream);
+
+/* Backward of rald_ln_rows (AdaLayerNorm.forward :127-131 / nn.LayerNorm): x f32 [rows][512] (the forward input),
+ * dy bf16 [rows][512], gamma as for rald_ln_rows. dh f32 [rows][512] (+)= dx. dparam[g][0][:] (+)= sum dy * xhat,
+ * dparam[g][1][:] (+)= sum dy over the rows of group g (= frame when rows_per_frame > 0, else all rows), group pitch
+ * dparam_group_stride and second-vector offset dparam_which_stride (in floats). rows and rows_per_frame multiples
+ * of 64. partial_ws: f32 scratch of rows / 64 * 1024 elements. */
+int rald_ln_bwd(const float* x, const void* dy_bf16, const float* gamma, int64_t mod_frame_stride, int rows_per_frame,
+                int gamma_plus_one, float* dh, int accumulate_dh, float* partial_ws, int64_t ws_elems, float* dparam,
+                int64_t dparam_group_stride, int64_t dparam_which_stride, int accumulate_dparam, int64_t rows, int D,
+                float eps, void* stream);
+
+/* GEGLU (:88-95) on a materialised projection u bf16 [T][2*inner] (value columns, then gate columns), erf GELU:
+ * g bf16 [T][inner] = value * gelu(gate); backward: du = [dg * gelu(gate) | dg * value * gelu'(gate)]. */
+int rald_geglu_fwd(const void* u_bf16, int64_t T, int inner, void* g_bf16, void* stream);
+int rald_geglu_bwd(const void* u_bf16, const void* dg_bf16, int64_t T, int inner, void* du_bf16, void* stream);
+
+/* C[M, N] = alpha * op(A) op(B) + beta * C, fp32 row-major, op = transpose when trans_* != 0 (small operands only:
+ * the timestep-embedding MLP :217-219 and its gradients). */
+int rald_sgemm_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, float beta, float* C, int64_t ldc, void* stream);
+
+/* Gradients of the token projection and position embeddings of process_radar_cond (:390-405) from dtok f32
+ * [B*nr*na*ne][dim] and the encoder features feat f32 [B*nr*na*ne][cz]: dw [dim][cz], db [dim], dr_emb [nr][dim],
+ * da_emb [na][dim], de_emb [ne][dim] (rows of the embedding tables beyond nr / na / ne receive no gradient). */
+int rald_radar_tokens_bwd(const float* dtok, const float* feat, int B, int nr, int na, int ne, int cz, int dim, float* dw,
+                          float* db, float* dr_emb, float* da_emb, float* de_emb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,22 @@ _SIGNATURES = {
     "rald_ema_update": [c_void_p, c_int, c_i64, c_i64, c_f32, c_f32, c_void_p],
     "rald_ema_chunk_elems": [],
     "rald_occupancy_iou": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_void_p, c_void_p],
+    "rald_attn_d64_stats": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int,
+                            c_int, c_f32, c_void_p, c_void_p],
+    "rald_attn_d64_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int,
+                          c_int, c_int, c_f32, c_void_p],
+    "rald_cast_transpose": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p],
+    "rald_cast_f16_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+    "rald_colsum": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_int, c_void_p],
+    "rald_ln_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,
+                    c_i64, c_int, c_i64, c_int, c_f32, c_void_p],
+    "rald_geglu_fwd": [c_void_p, c_i64, c_int, c_void_p, c_void_p],
+    "rald_geglu_bwd": [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p],
+    "rald_sgemm_f32": [c_int, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_i64, c_void_p, c_i64, c_f32, c_void_p,
+                       c_i64, c_void_p],
+    "rald_radar_tokens_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
              "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64, "rald_chamfer_ws_elems": c_i64}

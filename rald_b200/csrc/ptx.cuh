@@ -266,7 +266,8 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
 //   bits [4,6) c_format (1 = f32); [7,10) a_format; [10,13) b_format (0 f16, 1 bf16, 2 tf32);
 //   bit 15 a_major, bit 16 b_major (0 = K-major, 1 = MN-major); [17,23) N>>3; [24,29) M>>4.
 enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
-// A and B element formats may differ inside kind::f16 (separate descriptor fields): fp16 A with bf16 B.
+// Separate A / B format fields. NB (measured on B200, tools/gpu_check_attn_bwd.py): inside kind::f16 the two formats must
+// be EQUAL — an fp16 x bf16 product raises cudaErrorIllegalInstruction although the descriptor has room for it.
 __host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N,
                                                      uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |

@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _lib
 from .models_radar_encoder import Encoder as RadarEncoder
 from .runtime_dit import DitRuntime
+from .runtime_dit_train import DitTrainFunction, DitTrainRuntime, RadarTokensFunction
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -171,29 +172,24 @@ def edm_sampler(net, latents, class_labels=None, cond_type=None, randn_like=torc
 
 class EDMLoss:
     """EDM denoising loss of the reference (:277-295): per-sample log-normal sigma, weight (s^2 + sd^2) / (s sd)^2,
-    mean of weight * (D(y + n; sigma) - y)^2. The network forward of this package is inference-only, so the loss can
-    be EVALUATED (validation loss: call it under ``torch.no_grad()`` or with an ``.eval()`` network; the per-sample
-    sigma path of ``rald_dit_forward`` is used) but not differentiated — training is SURVEY.md §8f #3. The RNG calls
-    (``randn([B,1,1])``, then ``randn_like(y)``, both on the input's device) are the reference's, in its order."""
+    mean of weight * (D(y + n; sigma) - y)^2. The RNG calls (``randn([B,1,1])``, then ``randn_like(y)``, both on the
+    input's device) are the reference's, in its order. With a ``.train()`` network whose parameters require gradients
+    (and gradients enabled) the network evaluation is the differentiable training forward of
+    ``runtime_dit_train`` and ``loss.backward()`` fills the ``.grad`` of every denoiser parameter
+    (engine_generation.py:89-110); otherwise the inference kernels evaluate it (validation loss)."""
 
     def __init__(self, P_mean=-1.2, P_std=1.2, sigma_data=1):
         self.P_mean, self.P_std, self.sigma_data = P_mean, P_std, sigma_data
 
     def __call__(self, net, inputs, labels=None, cond_type=None, augment_pipe=None):
-        if torch.is_grad_enabled() and getattr(net, "training", False) and any(
-                p.requires_grad for p in net.parameters()):
-            raise NotImplementedError("rald_b200: EDMLoss can be evaluated but not differentiated — the training "
-                                      "forward/backward is not built (SURVEY.md §8f #3); call it under "
-                                      "torch.no_grad() or with net.eval()")
-        with torch.no_grad():
-            rnd_normal = torch.randn([inputs.shape[0], 1, 1], device=inputs.device)
-            sigma = (rnd_normal * self.P_std + self.P_mean).exp()
-            weight = (sigma ** 2 + self.sigma_data ** 2) / (sigma * self.sigma_data) ** 2
-            y, _ = augment_pipe(inputs) if augment_pipe is not None else (inputs, None)
-            n = torch.randn_like(y) * sigma
-            D_yn = net(y + n, sigma, labels, cond_type)
-            loss = weight * ((D_yn - y) ** 2)
-            return loss.mean()
+        rnd_normal = torch.randn([inputs.shape[0], 1, 1], device=inputs.device)
+        sigma = (rnd_normal * self.P_std + self.P_mean).exp()
+        weight = (sigma ** 2 + self.sigma_data ** 2) / (sigma * self.sigma_data) ** 2
+        y, _ = augment_pipe(inputs) if augment_pipe is not None else (inputs, None)
+        n = torch.randn_like(y) * sigma
+        D_yn = net(y + n, sigma, labels, cond_type)
+        loss = weight * ((D_yn - y) ** 2)
+        return loss.mean()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -221,6 +217,7 @@ class EDMPrecond(nn.Module):
             self.radar_e_emb = nn.Embedding(self.configs[pre + "_e_dim"], tc)
             self.radar_token_project = nn.Linear(self.configs.enc_radar_ch if self.configs.use_radar_enc else 1, tc)
         self.__dict__["_rt"] = None
+        self.__dict__["_trt"] = None
 
     # ---- runtime plumbing -------------------------------------------------------------------------
     def _runtime(self) -> DitRuntime:
@@ -272,12 +269,62 @@ class EDMPrecond(nn.Module):
     def process_radar_cond(self, radar_cube):
         return self._tokens(radar_cube, want_f32=True, want_bf16=False)[0]
 
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+
+    def _train_runtime(self) -> DitTrainRuntime:
+        if self.__dict__.get("_trt") is None:
+            self.__dict__["_trt"] = DitTrainRuntime(self)
+        return self.__dict__["_trt"]
+
+    def _tokens_train(self, label_tokens, cond_type) -> torch.Tensor:
+        """fp32 conditioning tokens [B, L, dim] for the training forward, differentiable in radar_token_project and
+        the r / a / e embeddings. The radar encoder runs on the inference kernels as a frozen feature extractor (the
+        reference's `radar_enc._encode` under no_grad, engine_generation.py:86-87): its backward is not built."""
+        if cond_type != "radar":
+            raise ValueError(f"cond_type={cond_type!r}: only 'radar' conditioning exists in the reference forward")
+        if label_tokens.dim() == 3:  # already tokens
+            return label_tokens.to(torch.float32)
+        if label_tokens.device.type != "cuda":
+            raise _lib.RaldError("rald_b200 runs on CUDA devices only (no CPU fallback)")
+        feat = label_tokens[..., 0:1].contiguous().float()
+        if self.configs.get("unfreeze_radar_enc", False):
+            if any(p.requires_grad for p in self.radar_enc.parameters()):
+                raise NotImplementedError(
+                    "rald_b200: the backward pass of the radar Conv3d encoder is not built (SURVEY.md §8f #3 covers the "
+                    "denoiser); freeze it for training with net.radar_enc.requires_grad_(False)")
+            with torch.no_grad():
+                feat = self.radar_enc.forward_channels_last(feat)
+        p = self.radar_token_project
+        if feat.shape[-1] != p.in_features:
+            raise ValueError(f"radar_token_project expects {p.in_features} input channels, the conditioning has "
+                             f"{feat.shape[-1]}")
+        return RadarTokensFunction.apply(feat, p.weight, p.bias, self.radar_r_emb.weight, self.radar_a_emb.weight,
+                                         self.radar_e_emb.weight)
+
+    def _forward_train(self, x, sigma, label_tokens, cond_type):
+        """The reference's forward (:412-430) with the network evaluation as ONE autograd node on the sm_100a
+        kernels (runtime_dit_train.DitTrainFunction); the preconditioning arithmetic around it is the reference's."""
+        tokens = self._tokens_train(label_tokens, cond_type)
+        x = x.to(torch.float32)
+        sigma = torch.as_tensor(sigma, dtype=torch.float32, device=x.device).reshape(-1, 1, 1)
+        if sigma.shape[0] == 1 and x.shape[0] > 1:
+            sigma = sigma.expand(x.shape[0], 1, 1)
+        sd = self.sigma_data
+        c_skip = sd ** 2 / (sigma ** 2 + sd ** 2)
+        c_out = sigma * sd / (sigma ** 2 + sd ** 2).sqrt()
+        c_in = 1 / (sd ** 2 + sigma ** 2).sqrt()
+        named = [(n, p) for n, p in self.model.named_parameters()]
+        F_x = DitTrainFunction.apply(self._train_runtime(), [n for n, _ in named], (c_in * x).contiguous(),
+                                     sigma.flatten().contiguous(), tokens, *[p for _, p in named])
+        return c_skip * x + c_out * F_x
+
     def forward(self, x, sigma, label_tokens=None, cond_type=None, force_fp32=False, **model_kwargs):
         """D_x = c_skip x + c_out F(c_in x, ln(sigma)/4, cond) (reference :412-430), fp32 in / fp32 out.
-        sigma: 0-d, [B] or [B,1,1]. Inference only: gradients are not propagated."""
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("rald_b200: training forward/backward is not built (SURVEY.md §8f #3); "
-                                      "call under torch.no_grad() / .eval()")
+        sigma: 0-d, [B] or [B,1,1]. In .train() mode with gradients enabled and trainable parameters this is the
+        differentiable training forward; otherwise the inference kernels run and nothing is recorded."""
+        if self._wants_grad():
+            return self._forward_train(x, sigma, label_tokens, cond_type)
         with torch.no_grad():
             tokens = self._condition(label_tokens, cond_type)
             sigma = torch.as_tensor(sigma, dtype=torch.float32, device=x.device)

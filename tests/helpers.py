@@ -37,3 +37,12 @@ def cpu_state_dict(module):
 def rel_l2(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def grad_sample_index(name: str, numel: int, sample: int = 2048):
+    """Indices of the gradient entries tests/golden/train_grads.npz keeps for a large parameter (seeded by its name)."""
+    h = 0
+    for ch in name:
+        h = (h * 131 + ord(ch)) % 1000000007
+    g = torch.Generator("cpu").manual_seed(h % (1 << 31))
+    return torch.randint(0, numel, (sample,), generator=g).numpy()

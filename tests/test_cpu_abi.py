@@ -26,7 +26,7 @@ def declared_functions():
 def test_library_builds_and_loads():
     path = build.build()
     assert path.exists()
-    assert _lib.lib().rald_abi_version() == 3
+    assert _lib.lib().rald_abi_version() == 4
 
 
 def test_every_declared_symbol_is_exported_and_bound():
