@@ -493,25 +493,26 @@ int rald_attn_d64_stats(const void* Q, int64_t ldq, const void* K, int64_t ldk, 
                         int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, float* stats, void* stream);
 
 /* Backward of rald_attn_d64 (autograd through the einsum / softmax / einsum of CrossAttention.forward,
- * model/models_radar_generation.py:66-75): given Q, K, V (bf16; v_f16 must be 0 — tcgen05 kind::f16 rejects products of
- * an fp16 with a bf16 operand, so the fp16 V of the forward is re-encoded with rald_cast_f16_bf16), the forward output O
- * (bf16), its statistics and dO (bf16), writes dQ [frames*Sq][..], dK and dV
- * [frames*Skv][..] as bf16 into columns [h*64, h*64+64) of rows of pitch lddq / lddk / lddv. Sq % 128 == 0; Skv = 64
- * or a multiple of 128; heads <= 8. Scratch: lse2_ws, dsum_ws f32 [frames*heads*Sq] each. Deterministic. */
-int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int v_f16,
-                      const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* stats, float* lse2_ws,
-                      float* dsum_ws, void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, int frames,
-                      int heads, int Sq, int Skv, float scale, void* stream);
+ * model/models_radar_generation.py:66-75): given Q, K (bf16), V_centred (bf16: the forward's V minus its mean over the
+ * keys of each frame, per column — rald_center_cast_f16_bf16; dS is invariant under that shift and the products of the
+ * backward pass are far better conditioned with it, see csrc/attn_bwd.cu), the forward's statistics and dO (bf16), writes
+ * dQ [frames*Sq][..], dK and dV [frames*Skv][..] as bf16 into columns [h*64, h*64+64) of rows of pitch lddq / lddk /
+ * lddv. Sq % 128 == 0; Skv = 64 or a multiple of 128; heads <= 8. Scratch: lse2_ws, dsum_ws f32 [frames*heads*Sq] each.
+ * Deterministic (no atomics). */
+int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V_centred, int64_t ldv,
+                      const void* dO, int64_t lddo, const float* stats, float* lse2_ws, float* dsum_ws, void* dQ,
+                      int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, int frames, int heads, int Sq, int Skv,
+                      float scale, void* stream);
 
 /* in [R, C] (f32 when in_f32, else bf16; pitch ld_in) -> out_bf16 [R, C] (optional) and out_t_bf16 [C, R] (optional,
  * pitch ld_t >= R): the bf16 / transposed operands of the dgrad and wgrad GEMMs. */
 int rald_cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t C, void* out_bf16, int64_t ld_out,
                         void* out_t_bf16, int64_t ld_t, void* stream);
 
-/* out_bf16 [R, C] = bf16(in_f16 [R, C]) (pitches in elements): the V columns rald_attn_d64 consumed as fp16, re-encoded
- * for rald_attn_d64_bwd. */
-int rald_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int64_t R, int64_t C,
-                       void* stream);
+/* out_bf16[f][j][c] = bf16(in_f16[f][j][c] - mean_j in_f16[f][j][c]) over frames x rows_per_frame rows of C columns
+ * (pitches in elements): the fp16 V columns rald_attn_d64 consumed, centred and re-encoded for rald_attn_d64_bwd. */
+int rald_center_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int frames,
+                              int rows_per_frame, int64_t C, void* stream);
 
 /* out[c] (+)= sum over rows of in[r][c] (bias gradients); two deterministic stages through partial_ws
  * (f32, >= min(512, ceil(R/256)) * C elements). */

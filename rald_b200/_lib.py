@@ -89,11 +89,11 @@ _SIGNATURES = {
     "rald_occupancy_iou": [c_void_p, c_void_p, c_int, c_i64, c_f32, c_void_p, c_void_p, c_void_p],
     "rald_attn_d64_stats": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int,
                             c_int, c_f32, c_void_p, c_void_p],
-    "rald_attn_d64_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_i64,
+    "rald_attn_d64_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int,
                           c_int, c_int, c_f32, c_void_p],
     "rald_cast_transpose": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p],
-    "rald_cast_f16_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+    "rald_center_cast_f16_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_i64, c_void_p],
     "rald_colsum": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_int, c_void_p],
     "rald_ln_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,
                     c_i64, c_int, c_i64, c_int, c_f32, c_void_p],

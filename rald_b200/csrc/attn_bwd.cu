@@ -6,15 +6,26 @@
 // P is never stored by the forward pass: it is recomputed from Q, K and the forward's row statistics
 // lse2_i = m_i + log2(l_i) (log2 units, scale folded in), p_ij = 2^(s_ij scale log2e - lse2_i).
 //
-// Two launches of ONE kernel template, each deterministic (no atomics):
+// Conditioning (measured, tools/probe_train_precision.py): dP_ij and D_i both contain dO_i . vbar, vbar = the component
+// all values of a (frame, head) have in common, and only their DIFFERENCE enters dS. With V rounded to bf16 and
+// D = rowsum(dO o O) taken from the bf16 forward output (the usual flash-attention form) the two copies of that term
+// carry independent rounding errors of size 2^-9 |dO| |vbar|: on a randomly initialised deep network (nearly collinear
+// tokens, |vbar| >> spread of V) that put 5 - 15 % of noise on the to_q / to_k weight gradients of the last blocks.
+// Hence (a) the caller passes V CENTRED per (frame, head) — V - mean_j V_j, rounded to bf16 afterwards
+// (rald_center_cast_f16_bf16): dS is invariant under a shift of all values, dV does not read V — and (b) D_i is not
+// taken from O but computed as sum_j p_ij dP_ij from the very dP and P the kernel uses (first pass of MODE_DQ), so that
+// every row of dS sums to zero to fp32 accuracy. With both, those gradients are within 1e-3 of fp32 autograd in the probe.
+//
+// Launches of ONE kernel template, each deterministic (no atomics):
 //   MODE_DKV  CTA = (frame, head, 128-key tile): K_j, V_j resident in shared memory, the query tiles (Q_i, dO_i) stream
 //             through a 2-stage TMA ring. Per query tile:  S^T = K_j Q_i^T and dP^T = V_j dO_i^T into TMEM (keys on the
 //             TMEM lanes), four warps (thread <-> key row) turn them into P^T and dS^T (bf16, written back to TMEM as
 //             A operands), then dV += P^T dO_i and dK += dS^T Q_i with the SAME shared-memory tiles of dO_i / Q_i read
 //             as MN-major B operands. The per-query statistics are per COLUMN here and come from shared memory.
-//   MODE_DQ   CTA = (frame, head, 128-query tile): Q_i, dO_i resident, (K_j, V_j) stream. S = Q_i K_j^T, dP = dO_i V_j^T,
-//             dS (bf16 in TMEM), dQ += dS K_j (K_j as MN-major B operand). Statistics are per lane (registers).
-// S and dP are recomputed in both launches (7 tile products instead of the minimal 5): the alternative is a dQ
+//   MODE_DQ   (runs first) CTA = (frame, head, 128-query tile): Q_i, dO_i resident, (K_j, V_j) stream TWICE. Pass 1:
+//             S = Q_i K_j^T, dP = dO_i V_j^T, D_i = sum_j p_ij dP_ij (per lane, written to global for MODE_DKV). Pass 2:
+//             S, dP again, dS (bf16 pair in TMEM), dQ += dS K_j (K_j as MN-major B operand).
+// S and dP are recomputed in every pass (9 tile products instead of the minimal 5): the alternative is a dQ
 // accumulated across CTAs with atomics or a TMA reduce-add, whose summation order would vary from run to run.
 // dS is handed to the tensor cores as a SPLIT pair dS = hi + lo of bf16 values (16 mantissa bits, two products per
 // accumulator): every row of dS sums to zero, so dQ_i = sum_j dS_ij K_j cancels whatever the keys have in common, and
@@ -42,7 +53,7 @@ struct AttnBwdParams {
   int x_rows;            // rows per streamed tile (128, or 64 for the 64-token context in MODE_DQ)
   float scale_log2, scale;
   const float* lse2;     // [frames][heads][Sq]
-  const float* dsum;     // [frames][heads][Sq]
+  float* dsum;           // [frames][heads][Sq]: D_i, written by MODE_DQ (pass 1), read by MODE_DKV
   uint16_t* out1;        // DQ: dQ ; DKV: dV
   int64_t ld1;
   uint16_t* out2;        // DKV: dK
@@ -104,6 +115,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const int rt = item - fh * p.r_tiles;
   const int frame = fh / p.heads, head = fh - frame * p.heads;
   const int nx = p.x_tiles;
+  const int iters = MODE == AB_MODE_DQ ? 2 * nx : nx;   // MODE_DQ streams the keys twice (D pass, then dS / dQ pass)
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_P = 0, COL_DS = 128, COL_LO = 256, COL_A1 = 384, COL_A2 = 448;
 
   if (warp == 0) {
@@ -114,9 +126,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       tma_load_2d(sR1, &tmR1, r_full, head * 64, r_row);
       tma_load_2d(sR2, &tmR2, r_full, head * 64, r_row);
       const uint32_t x_bytes = 2u * (uint32_t)p.x_rows * 128u;
-      for (int s = 0; s < nx; ++s) {
-        const int st = s & 1;
-        mbar_wait(&x_empty[st], ((s >> 1) & 1) ^ 1);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it & 1;
+        const int s = it >= nx ? it - nx : it;
+        mbar_wait(&x_empty[st], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&x_full[st], x_bytes);
         const int x_row = frame * p.x_frame_rows + s * p.x_rows;
         tma_load_2d(sX1 + st * AB_TILE, &tmX1, &x_full[st], head * 64, x_row);
@@ -131,9 +144,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       const uint64_t r1_desc = make_sdesc_sw128(smem_u32(sR1), 16, 1024);
       const uint64_t r2_desc = make_sdesc_sw128(smem_u32(sR2), 16, 1024);
       const int acc_k = (MODE == AB_MODE_DQ ? p.x_rows : 128) / 16;   // 16-deep steps of the accumulating products
-      for (int s = 0; s < nx; ++s) {
-        const int st = s & 1;
-        mbar_wait(&x_full[st], (s >> 1) & 1);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it & 1;
+        const int s = it >= nx ? it - nx : it;
+        const bool acc_pass = MODE != AB_MODE_DQ || it >= nx;
+        mbar_wait(&x_full[st], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t x1 = smem_u32(sX1 + st * AB_TILE), x2 = smem_u32(sX2 + st * AB_TILE);
         const uint64_t x1_desc = make_sdesc_sw128(x1, 16, 1024), x2_desc = make_sdesc_sw128(x2, 16, 1024);
@@ -142,8 +157,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_f16_ss(tmem_base + COL_DP, r2_desc + 2 * k, x2_desc + 2 * k, p.idesc_dp, k != 0);
         tc_commit(s_full);
-        mbar_wait(p_ready, s & 1);
+        mbar_wait(p_ready, it & 1);
         tc_fence_after();
+        if (!acc_pass) {           // D pass: nothing to accumulate, the tiles are free once S and dP have been read
+          tc_commit(&x_empty[st]);
+          continue;
+        }
         // the streamed tiles again, as MN-major B operands ([k index][64 values of d]): 8-row groups 1024 B apart
         const uint64_t x1_mn = make_sdesc_sw128(x1, 1024, 1024), x2_mn = make_sdesc_sw128(x2, 1024, 1024);
         if (MODE == AB_MODE_DKV) {
@@ -170,21 +189,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const uint32_t t_mine = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int64_t stat_base = ((int64_t)frame * p.heads + head) * p.Sq;
     float lse_r = 0.f, ds_r = 0.f;
-    if (MODE == AB_MODE_DQ) {
-      lse_r = p.lse2[stat_base + rt * 128 + row];
-      ds_r = p.dsum[stat_base + rt * 128 + row];
-    }
+    if (MODE == AB_MODE_DQ) lse_r = p.lse2[stat_base + rt * 128 + row];
     const int ncols = MODE == AB_MODE_DQ ? p.x_rows : 128;
-    for (int s = 0; s < nx; ++s) {
+    for (int it = 0; it < iters; ++it) {
+      const int s = it >= nx ? it - nx : it;
       const float* lse_c = s_lse + (s & 1) * 128;
       const float* ds_c = s_ds + (s & 1) * 128;
+      if (MODE == AB_MODE_DQ && it < nx) {
+        // ---- pass 1: D_i = sum_j p_ij dP_ij over all keys (four independent chains per 32 columns) ----
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 32) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(t_mine + COL_S + c, sv);
+          tmem_ld32(t_mine + COL_DP + c, dv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 = fmaf(ex2_f32(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse_r)), __uint_as_float(dv[j]), a0);
+            a1 = fmaf(ex2_f32(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -lse_r)), __uint_as_float(dv[j + 1]), a1);
+            a2 = fmaf(ex2_f32(fmaf(__uint_as_float(sv[j + 2]), p.scale_log2, -lse_r)), __uint_as_float(dv[j + 2]), a2);
+            a3 = fmaf(ex2_f32(fmaf(__uint_as_float(sv[j + 3]), p.scale_log2, -lse_r)), __uint_as_float(dv[j + 3]), a3);
+          }
+        }
+        ds_r += (a0 + a1) + (a2 + a3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        if (it == nx - 1) p.dsum[stat_base + rt * 128 + row] = ds_r;
+        continue;
+      }
       if (MODE == AB_MODE_DKV) {
         // statistics of the 128 queries of this tile = the COLUMNS of S^T: staged in shared memory, read as broadcasts
         s_lse[(s & 1) * 128 + row] = p.lse2[stat_base + s * 128 + row];
         s_ds[(s & 1) * 128 + row] = p.dsum[stat_base + s * 128 + row];
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      mbar_wait(s_full, s & 1);
+      mbar_wait(s_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < ncols; c += 32) {
@@ -255,60 +298,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   }
 }
 
-// lse2[f][h][r] = m + log2(l) from the forward's statistics [frames*Sq][heads][2]; dsum[f][h][r] = sum_d dO O over the
-// head's 64 columns. One warp per row of 512 = 8 heads x 64 columns (lane: 16 columns, 4 lanes per head).
+// lse2[f][h][r] = m + log2(l) from the forward's statistics [frames*Sq][heads][2]
 __global__ void __launch_bounds__(256)
-attn_bwd_prep_kernel(const float* __restrict__ stats, const uint16_t* __restrict__ O, int64_t ldo,
-                     const uint16_t* __restrict__ dO, int64_t lddo, int64_t rows, int Sq, int heads,
-                     float* __restrict__ lse2, float* __restrict__ dsum) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-  if (row >= rows) return;
+attn_bwd_prep_kernel(const float* __restrict__ stats, int64_t rows, int Sq, int heads, float* __restrict__ lse2) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * heads) return;
+  const int64_t row = i / heads;
+  const int head = (int)(i - row * heads);
   const int64_t frame = row / Sq;
   const int r = (int)(row - frame * Sq);
-  float acc = 0.f;
-  if (lane * 16 < heads * 64) {
-    const uint4* o4 = reinterpret_cast<const uint4*>(O + row * ldo + lane * 16);
-    const uint4* d4 = reinterpret_cast<const uint4*>(dO + row * lddo + lane * 16);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint4 a = o4[j], b = d4[j];
-      const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc = fmaf(__uint_as_float(au[k] << 16), __uint_as_float(bu[k] << 16), acc);
-        acc = fmaf(__uint_as_float(au[k] & 0xffff0000u), __uint_as_float(bu[k] & 0xffff0000u), acc);
-      }
-    }
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  const int head = lane >> 2;
-  if ((lane & 3) == 0 && head < heads) dsum[(frame * heads + head) * Sq + r] = acc;
-  if (lane < heads) {
-    const float* sp = stats + (row * heads + lane) * 2;
-    lse2[(frame * heads + lane) * Sq + r] = sp[0] + log2f(sp[1]);
-  }
+  lse2[(frame * heads + head) * Sq + r] = stats[i * 2] + log2f(stats[i * 2 + 1]);
 }
 
-int attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int v_f16,
-                 const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* stats, float* lse2, float* dsum,
+int attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                 const void* dO, int64_t lddo, const float* stats, float* lse2, float* dsum,
                  void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, int frames, int heads, int Sq,
                  int Skv, float scale, cudaStream_t stream) {
   RALD_REQUIRE(frames > 0 && heads > 0 && heads <= 8, "attn_bwd: bad sizes (heads <= 8)");
-  // measured on B200: a kind::f16 tcgen05.mma whose A and B formats differ (fp16 x bf16) raises "illegal instruction"
-  RALD_REQUIRE(!v_f16, "attn_bwd: V must be bf16 (re-encode the forward's fp16 V with rald_cast_f16_bf16)");
   RALD_REQUIRE(Sq % 128 == 0, "attn_bwd: Sq=%d must be a multiple of 128", Sq);
   RALD_REQUIRE(Skv == 64 || Skv % 128 == 0, "attn_bwd: Skv=%d must be 64 or a multiple of 128", Skv);
-  RALD_REQUIRE(lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0,
+  RALD_REQUIRE(lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && lddo % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0,
                "attn_bwd: row pitches must be multiples of 8 elements");
   const int64_t rows = (int64_t)frames * Sq;
-  attn_bwd_prep_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(
-      stats, reinterpret_cast<const uint16_t*>(O), ldo, reinterpret_cast<const uint16_t*>(dO), lddo, rows, Sq, heads,
-      lse2, dsum);
+  attn_bwd_prep_kernel<<<(unsigned)((rows * heads + 255) / 256), 256, 0, stream>>>(stats, rows, Sq, heads, lse2);
   RALD_LAUNCHED();
 
-  const uint32_t vfmt = v_f16 ? FMT_F16 : FMT_BF16;
   const int q_tiles = Sq / 128;
   const int kv_tiles = (Skv + 127) / 128;
   const int nk = Skv < 128 ? Skv : 128;
@@ -333,6 +347,20 @@ int attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const v
   p.dsum = dsum;
   p.idesc_acc = make_idesc(FMT_BF16, 128, 64, 0, 1);
   {
+    // ---- D and dQ: queries resident, keys streamed twice in tiles of nk rows ----
+    RALD_TRY(make_tmap_2d_bf16(&tmK, K, (uint64_t)frames * Skv, cols, (uint64_t)ldk, (uint32_t)nk));
+    RALD_TRY(make_tmap_2d_bf16(&tmV, V, (uint64_t)frames * Skv, cols, (uint64_t)ldv, (uint32_t)nk));
+    p.r_tiles = q_tiles; p.x_tiles = kv_tiles;
+    p.r_frame_rows = Sq; p.x_frame_rows = Skv; p.x_rows = nk;
+    p.out1 = reinterpret_cast<uint16_t*>(dQ); p.ld1 = lddq;
+    p.out2 = nullptr; p.ld2 = 0;
+    p.idesc_s = make_idesc(FMT_BF16, 128, (uint32_t)nk, 0, 0);
+    p.idesc_dp = make_idesc(FMT_BF16, 128, (uint32_t)nk, 0, 0);
+    ProfScope prof(FAM_ATTN, stream, 10.0 * frames * heads * Sq * (double)Skv * 64);
+    attn_bwd_kernel<AB_MODE_DQ><<<frames * heads * q_tiles, AB_THREADS, smem_bytes, stream>>>(tmQ, tmdO, tmK, tmV, p);
+    RALD_LAUNCHED();
+  }
+  {
     // ---- dK, dV: keys resident (128-row boxes: rows past a 64-key context belong to the next frame or are zero-filled;
     // they only reach TMEM lanes whose results are not stored) ----
     RALD_TRY(make_tmap_2d_bf16(&tmK, K, (uint64_t)frames * Skv, cols, (uint64_t)ldk, 128));
@@ -342,23 +370,9 @@ int attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const v
     p.out1 = reinterpret_cast<uint16_t*>(dV); p.ld1 = lddv;
     p.out2 = reinterpret_cast<uint16_t*>(dK); p.ld2 = lddk;
     p.idesc_s = make_idesc(FMT_BF16, 128, 128, 0, 0);
-    p.idesc_dp = make_idesc_ab(vfmt, FMT_BF16, 128, 128, 0, 0);
+    p.idesc_dp = make_idesc(FMT_BF16, 128, 128, 0, 0);
     ProfScope prof(FAM_ATTN, stream, 8.0 * frames * heads * Sq * (double)(kv_tiles * 128) * 64);
     attn_bwd_kernel<AB_MODE_DKV><<<frames * heads * kv_tiles, AB_THREADS, smem_bytes, stream>>>(tmK, tmV, tmQ, tmdO, p);
-    RALD_LAUNCHED();
-  }
-  {
-    // ---- dQ: queries resident, keys streamed in tiles of nk rows ----
-    RALD_TRY(make_tmap_2d_bf16(&tmK, K, (uint64_t)frames * Skv, cols, (uint64_t)ldk, (uint32_t)nk));
-    RALD_TRY(make_tmap_2d_bf16(&tmV, V, (uint64_t)frames * Skv, cols, (uint64_t)ldv, (uint32_t)nk));
-    p.r_tiles = q_tiles; p.x_tiles = kv_tiles;
-    p.r_frame_rows = Sq; p.x_frame_rows = Skv; p.x_rows = nk;
-    p.out1 = reinterpret_cast<uint16_t*>(dQ); p.ld1 = lddq;
-    p.out2 = nullptr; p.ld2 = 0;
-    p.idesc_s = make_idesc(FMT_BF16, 128, (uint32_t)nk, 0, 0);
-    p.idesc_dp = make_idesc_ab(FMT_BF16, vfmt, 128, (uint32_t)nk, 0, 0);
-    ProfScope prof(FAM_ATTN, stream, 6.0 * frames * heads * Sq * (double)Skv * 64);
-    attn_bwd_kernel<AB_MODE_DQ><<<frames * heads * q_tiles, AB_THREADS, smem_bytes, stream>>>(tmQ, tmdO, tmK, tmV, p);
     RALD_LAUNCHED();
   }
   return 0;
@@ -373,10 +387,10 @@ extern "C" int rald_attn_d64_stats(const void* Q, int64_t ldq, const void* K, in
                               static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
-                                 int v_f16, const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* stats,
-                                 float* lse2_ws, float* dsum_ws, void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV,
-                                 int64_t lddv, int frames, int heads, int Sq, int Skv, float scale, void* stream) {
-  return rald::attn_d64_bwd(Q, ldq, K, ldk, V, ldv, v_f16, O, ldo, dO, lddo, stats, lse2_ws, dsum_ws, dQ, lddq, dK, lddk,
-                            dV, lddv, frames, heads, Sq, Skv, scale, static_cast<cudaStream_t>(stream));
+extern "C" int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V_centred, int64_t ldv,
+                                 const void* dO, int64_t lddo, const float* stats, float* lse2_ws, float* dsum_ws, void* dQ,
+                                 int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, int frames, int heads, int Sq,
+                                 int Skv, float scale, void* stream) {
+  return rald::attn_d64_bwd(Q, ldq, K, ldk, V_centred, ldv, dO, lddo, stats, lse2_ws, dsum_ws, dQ, lddq, dK, lddk, dV, lddv,
+                            frames, heads, Sq, Skv, scale, static_cast<cudaStream_t>(stream));
 }

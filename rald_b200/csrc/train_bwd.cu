@@ -73,27 +73,33 @@ int cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t
 }
 
 
-// fp16 -> bf16 over a [R, C] window (the V columns the forward attention consumed as fp16, re-encoded for the backward
-// attention kernel, whose tcgen05 products take bf16 on both sides)
+// out[f][j][c] = bf16(in[f][j][c] - mean_j in[f][j][c]) for fp16 in: the V columns the forward attention consumed as
+// fp16, centred per (frame, column) and re-encoded for the backward attention kernel (attn_bwd.cu explains why).
+// One CTA per (frame, 64 columns): 4 row lanes x 64 columns, mean in fp32 with a fixed summation order.
 __global__ void __launch_bounds__(256)
-cast_f16_bf16_kernel(const __half* __restrict__ in, int64_t ld_in, uint16_t* __restrict__ out, int64_t ld_out, int64_t R,
-                     int64_t C) {
-  const int64_t n = R * (C / 2);
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int64_t r = i / (C / 2), c = (i - r * (C / 2)) * 2;
-    const __half2 h = *reinterpret_cast<const __half2*>(in + r * ld_in + c);
-    const float2 f = __half22float2(h);
-    *reinterpret_cast<uint32_t*>(out + r * ld_out + c) = pack_bf16x2(f.x, f.y);
-  }
+center_cast_f16_bf16_kernel(const __half* __restrict__ in, int64_t ld_in, uint16_t* __restrict__ out, int64_t ld_out,
+                            int rows_per_frame, int64_t C) {
+  __shared__ float part[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int64_t c = (int64_t)blockIdx.x * 64 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_frame;
+  float a = 0.f;
+  if (c < C)
+    for (int j = ty; j < rows_per_frame; j += 4) a += __half2float(in[(r0 + j) * ld_in + c]);
+  part[ty][tx] = a;
+  __syncthreads();
+  const float mean = ((part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx])) / (float)rows_per_frame;
+  if (c < C)
+    for (int j = ty; j < rows_per_frame; j += 4)
+      out[(r0 + j) * ld_out + c] = f32_to_bf16_bits(__half2float(in[(r0 + j) * ld_in + c]) - mean);
 }
 
-int cast_f16_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int64_t R, int64_t C, cudaStream_t stream) {
-  RALD_REQUIRE(R > 0 && C > 0 && C % 2 == 0 && ld_in % 2 == 0 && ld_out % 2 == 0, "cast_f16_bf16: bad shape");
-  int64_t blocks = (R * (C / 2) + 255) / 256;
-  const int64_t cap = (int64_t)device_sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  cast_f16_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(in), ld_in,
-                                                             reinterpret_cast<uint16_t*>(out), ld_out, R, C);
+int center_cast_f16_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int frames, int rows_per_frame,
+                         int64_t C, cudaStream_t stream) {
+  RALD_REQUIRE(frames > 0 && rows_per_frame > 0 && C > 0 && frames < 65536, "center_cast_f16_bf16: bad shape");
+  dim3 grid((unsigned)((C + 63) / 64), (unsigned)frames);
+  center_cast_f16_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(in), ld_in,
+                                                        reinterpret_cast<uint16_t*>(out), ld_out, rows_per_frame, C);
   RALD_LAUNCHED();
   return 0;
 }
@@ -483,9 +489,10 @@ int rald_cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, in
                               static_cast<cudaStream_t>(stream));
 }
 
-int rald_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int64_t R, int64_t C,
-                       void* stream) {
-  return rald::cast_f16_bf16(in_f16, ld_in, out_bf16, ld_out, R, C, static_cast<cudaStream_t>(stream));
+int rald_center_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int frames,
+                              int rows_per_frame, int64_t C, void* stream) {
+  return rald::center_cast_f16_bf16(in_f16, ld_in, out_bf16, ld_out, frames, rows_per_frame, C,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 int rald_colsum(const void* in, int in_f32, int64_t ld, int64_t R, int64_t C, float* partial_ws, int64_t ws_elems,

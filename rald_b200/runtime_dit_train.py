@@ -202,9 +202,9 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
                    bias=self.b_o1[n], resid=h, ldr=dim)
         h1 = h.clone() if keep is not None else None
         vb1 = vb2 = None
-        if keep is not None:   # bf16 re-encoding of the fp16 V columns for the backward attention kernel
+        if keep is not None:   # fp16 V columns, centred per frame and re-encoded as bf16 for the backward attention kernel
             vb1 = torch.empty(T, dim, device=dev, dtype=BF)
-            _lib.call("rald_cast_f16_bf16", qkv.data_ptr() + 2 * dim * 2, 3 * dim, vb1.data_ptr(), dim, T, dim,
+            _lib.call("rald_center_cast_f16_bf16", qkv.data_ptr() + 2 * dim * 2, 3 * dim, vb1.data_ptr(), dim, B, M, dim,
                       _lib.cur_stream())
         # ---- attn2 ----
         xn2 = torch.empty(T, dim, device=dev, dtype=BF)
@@ -224,7 +224,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
         h2 = h.clone() if keep is not None else None
         if keep is not None:
             vb2 = torch.empty(B * L, dim, device=dev, dtype=BF)
-            _lib.call("rald_cast_f16_bf16", kv2.data_ptr() + dim * 2, 2 * dim, vb2.data_ptr(), dim, B * L, dim,
+            _lib.call("rald_center_cast_f16_bf16", kv2.data_ptr() + dim * 2, 2 * dim, vb2.data_ptr(), dim, B, L, dim,
                       _lib.cur_stream())
         # ---- feed-forward ----
         xn3 = torch.empty(T, dim, device=dev, dtype=BF)
@@ -366,7 +366,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
             dkv2 = torch.empty(B * L, 2 * dim, device=dev, dtype=BF)
             kv2 = k["kv2"]
             _lib.call("rald_attn_d64_bwd", k["q2"].data_ptr(), dim, kv2.data_ptr(), 2 * dim, k["vb2"].data_ptr(),
-                      dim, 0, k["a2"].data_ptr(), dim, da.data_ptr(), dim, k["st2"].data_ptr(), lse_ws.data_ptr(),
+                      dim, da.data_ptr(), dim, k["st2"].data_ptr(), lse_ws.data_ptr(),
                       ds_ws.data_ptr(), dq2.data_ptr(), dim, dkv2.data_ptr(), 2 * dim, dkv2.data_ptr() + dim * 2, 2 * dim,
                       B, heads, M, L, scale, stream())
             _, dq2T = self._transpose(dq2)
@@ -389,7 +389,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
             dqkv = torch.empty(T, 3 * dim, device=dev, dtype=BF)
             qkv = k["qkv"]
             _lib.call("rald_attn_d64_bwd", qkv.data_ptr(), 3 * dim, qkv.data_ptr() + dim * 2, 3 * dim,
-                      k["vb1"].data_ptr(), dim, 0, k["a1"].data_ptr(), dim, da.data_ptr(), dim,
+                      k["vb1"].data_ptr(), dim, da.data_ptr(), dim,
                       k["st1"].data_ptr(), lse_ws.data_ptr(), ds_ws.data_ptr(), dqkv.data_ptr(), 3 * dim,
                       dqkv.data_ptr() + dim * 2, 3 * dim, dqkv.data_ptr() + 2 * dim * 2, 3 * dim, B, heads, M, M, scale,
                       stream())

@@ -148,12 +148,13 @@ def test_radar_tokens_backward():
 
 
 # ---------------------------------------------------------------------------------------------------- attention
-def _attention_case(frames, Sq, Skv, seed):
+def _attention_case(frames, Sq, Skv, seed, common=0.0):
     heads, d = 8, 64
     g = torch.Generator().manual_seed(seed)
     q = torch.randn(frames * Sq, heads * d, generator=g).to(DEV).to(BF)
     k = torch.randn(frames * Skv, heads * d, generator=g).to(DEV).to(BF)
-    v16 = torch.randn(frames * Skv, heads * d, generator=g).to(DEV).to(torch.float16)
+    v16 = (torch.randn(frames * Skv, heads * d, generator=g)
+           + common * torch.randn(1, heads * d, generator=g)).to(DEV).to(torch.float16)
     do = torch.randn(frames * Sq, heads * d, generator=g).to(DEV).to(BF)
     scale = d ** -0.5
     o = torch.empty(frames * Sq, heads * d, device=DEV, dtype=BF)
@@ -162,14 +163,15 @@ def _attention_case(frames, Sq, Skv, seed):
     _lib.call("rald_attn_d64_stats", q.data_ptr(), W, k.data_ptr(), W, v16.data_ptr(), W, o.data_ptr(), W, frames, heads,
               Sq, Skv, scale, stats.data_ptr(), _s())
     vb = torch.empty(frames * Skv, W, device=DEV, dtype=BF)
-    _lib.call("rald_cast_f16_bf16", v16.data_ptr(), W, vb.data_ptr(), W, frames * Skv, W, _s())
-    assert torch.equal(vb, v16.to(BF))
+    _lib.call("rald_center_cast_f16_bf16", v16.data_ptr(), W, vb.data_ptr(), W, frames, Skv, W, _s())
+    vc = v16.float().view(frames, Skv, W)
+    assert rel_l2(vb.view(frames, Skv, W), vc - vc.mean(1, keepdim=True)) <= 4e-3
     dq = torch.zeros_like(q)
     dk = torch.zeros_like(k)
     dv = torch.zeros_like(k)
     lse = torch.empty(frames * heads * Sq, device=DEV)
     ds = torch.empty(frames * heads * Sq, device=DEV)
-    _lib.call("rald_attn_d64_bwd", q.data_ptr(), W, k.data_ptr(), W, vb.data_ptr(), W, 0, o.data_ptr(), W, do.data_ptr(),
+    _lib.call("rald_attn_d64_bwd", q.data_ptr(), W, k.data_ptr(), W, vb.data_ptr(), W, do.data_ptr(),
               W, stats.data_ptr(), lse.data_ptr(), ds.data_ptr(), dq.data_ptr(), W, dk.data_ptr(), W, dv.data_ptr(), W,
               frames, heads, Sq, Skv, scale, _s())
     torch.cuda.synchronize()
@@ -194,6 +196,16 @@ def test_attention_backward(frames, Sq, Skv):
     assert errs["dq"] <= 1e-2 and errs["dk"] <= 1e-2 and errs["dv"] <= 1e-2
 
 
+def test_attention_backward_with_collinear_values():
+    """Values with a component shared by all keys 30x larger than their spread (what the deep blocks of a randomly
+    initialised network produce): the centred V / in-kernel D form keeps dQ and dK at the 1e-2 level, where
+    D = rowsum(dO o O) from the bf16 forward output loses them (csrc/attn_bwd.cu, tools/probe_train_precision.py)."""
+    (o, o_ref), (dq, dq_ref), (dk, dk_ref), (dv, dv_ref) = _attention_case(2, 512, 512, seed=77, common=30.0)
+    errs = dict(dq=rel_l2(dq, dq_ref), dk=rel_l2(dk, dk_ref), dv=rel_l2(dv, dv_ref))
+    print("attention backward, collinear values", errs)
+    assert errs["dq"] <= 1e-2 and errs["dk"] <= 1e-2 and errs["dv"] <= 1e-2
+
+
 def test_attention_backward_is_deterministic():
     a = _attention_case(2, 512, 512, seed=3)
     b = _attention_case(2, 512, 512, seed=3)
@@ -202,11 +214,7 @@ def test_attention_backward_is_deterministic():
 
 
 # ---------------------------------------------------------------------------------------------------- whole step
-GRAD_TOL_MEDIAN, GRAD_TOL_WORST, GRAD_TOL_QK, GRAD_TOL_NORM = 1e-2, 5e-2, 0.2, 1e-2
-
-
-def _is_attn1_qk(name: str) -> bool:
-    return name.endswith("attn1.to_q.weight") or name.endswith("attn1.to_k.weight")
+GRAD_TOL_MEDIAN, GRAD_TOL_WORST, GRAD_TOL_NORM = 1e-2, 2e-2, 1e-2
 
 
 def _fixture():
@@ -214,16 +222,13 @@ def _fixture():
 
 
 def test_training_step_matches_reference_gradients():
-    """One EDMLoss step on the default denoiser (.train(), radar encoder frozen) with the fixture's sigma / noise:
-    loss within 1e-2 (measured 3e-4), D within 1e-2 rel-L2 (1.3e-3), and for EVERY trainable parameter the gradient norm
-    within 1e-2 (worst 5.6e-3) and the stored gradient entries (whole vectors / small matrices, a 2048-element sample of
-    the large ones) within 5e-2 rel-L2, median over the 493 tensors within 1e-2 (6.7e-3), of the unmodified reference's
-    fp32 autograd. Exception, bounded at 0.2 (measured 0.04 - 0.15 in blocks 16-23, < 0.04 elsewhere): the self-attention
-    to_q / to_k weights. At random init the deep blocks' tokens are nearly collinear, the logits q.k carry a large
-    component common to all keys, and rounding q and k to bf16 (the tensor-core operand format, in the forward pass as
-    well) perturbs the logits by an amount that does not cancel in the softmax; the attention OUTPUT is insensitive to
-    it (near-uniform probabilities) but the gradient w.r.t. q and k is exactly the deviation from uniform
-    (tools/probe_train_precision.py reproduces the effect on the CPU oracle by rounding only q and k)."""
+    """One EDMLoss step on the default denoiser (.train(), radar encoder frozen) with the fixture's sigma / noise against
+    the UNMODIFIED reference's fp32 autograd: loss within 1e-2 (measured 3e-4), D within 1e-2 rel-L2 (1.3e-3), and for
+    EVERY one of the 493 trainable tensors the gradient norm within 1e-2 (worst 4.3e-3) and the stored gradient entries
+    (whole vectors / small matrices, a 2048-element sample of the large ones) within 2e-2 rel-L2 (worst 9.4e-3, median
+    6.8e-3) — bf16 operands with fp32 accumulation here. (The first version of the attention backward, with the usual
+    D = rowsum(dO o O) and an uncentred V, was at 4 - 15 % on the self-attention to_q / to_k weights of blocks 16-23:
+    csrc/attn_bwd.cu, tools/probe_train_precision.py.)"""
     fx = _fixture()
     net = build_denoiser(device=DEV).train()
     net.radar_enc.requires_grad_(False)
@@ -263,11 +268,8 @@ def test_training_step_matches_reference_gradients():
     for e_v, e_n, name in rows[:12]:
         print(f"   {name}: rel-L2 {e_v:.3e}, norm deviation {e_n:.3e}")
     assert med <= GRAD_TOL_MEDIAN
-    others = [r for r in rows if not _is_attn1_qk(r[2])]
-    print(f"   worst outside attn1.to_q / to_k: {others[0][2]} rel-L2 {others[0][0]:.3e}")
     for e_v, e_n, name in rows:
-        assert e_n <= GRAD_TOL_NORM, (name, e_n)
-        assert e_v <= (GRAD_TOL_QK if _is_attn1_qk(name) else GRAD_TOL_WORST), (name, e_v)
+        assert e_n <= GRAD_TOL_NORM and e_v <= GRAD_TOL_WORST, (name, e_n, e_v)
     assert all(p.grad is None for p in net.radar_enc.parameters())
 
 
