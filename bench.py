@@ -547,7 +547,7 @@ def leg_ae_frame(dev, peaks):
     return out
 
 
-def leg_train_step(dev, peaks, batches=(8, 64)):
+def leg_train_step(dev, peaks, batches=(8, 64), anchors=True, reps=3):
     """one training step of the denoiser (EDMLoss forward + backward over every denoiser parameter,
     radar encoder frozen = the reference's frozen-encoder option) at the reference's batch size (train.batch_size: 8)
     and at 64 frames, tokens precomputed; and the reference's formulation under torch autograd on the same GPU (the
@@ -575,13 +575,15 @@ def leg_train_step(dev, peaks, batches=(8, 64)):
             loss = crit(net, y, tok, "radar")
             loss.backward()
             return loss
-        ms = cuda_time(step, 3, warm=2)
+        ms = cuda_time(step, reps, warm=2 if reps > 1 else 1)
         tf = B * 3 * GFLOP_PER_EVAL / ms
         out[f"batch{B}"] = {"ms_per_step": ms, "frames_per_s": B / (ms * 1e-3), "tflops_algorithmic": tf,
                             "frac_of_sustained_bf16": tf / peaks["bf16_tflops_sustained"],
                             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
     del net
     torch.cuda.empty_cache()
+    if not anchors:
+        return out
     # ---- anchors: the reference's modules (oracle port) under torch autograd, batch 8 ----
     try:
         B = batches[0]
