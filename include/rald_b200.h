@@ -68,6 +68,13 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    const float* bias, const float* resid, int64_t ldr, int M, int N, int K, int out_mode,
                    int bn_hint, void* stream);
 
+/* out (f32 [M,N], pitch ldo) += A[M,K] @ W[N,K]^T for GEMMs with few output tiles and a long K (the weight gradients
+ * dW = dY^T X of the training step, K = rows of the batch): the K extent of every tile is split over up to 16 CTAs that
+ * add into `out` through the TMA reduce-add epilogue. `out` must hold the value to accumulate onto (zeros for a fresh
+ * gradient). The order of the fp32 additions across splits is not fixed: results reproduce to ~1e-7 relative. */
+int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
+                         int K, void* stream);
+
 /* rald_gemm_bf16 with out_mode 0 whose output columns with (col % f16_period) >= f16_start are written as IEEE fp16
  * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
@@ -505,9 +512,12 @@ int rald_attn_d64_bwd(const void* Q, int64_t ldq, const void* K, int64_t ldk, co
                       float scale, void* stream);
 
 /* in [R, C] (f32 when in_f32, else bf16; pitch ld_in) -> out_bf16 [R, C] (optional) and out_t_bf16 [C, R] (optional,
- * pitch ld_t >= R): the bf16 / transposed operands of the dgrad and wgrad GEMMs. */
+ * pitch ld_t >= R): the bf16 / transposed operands of the dgrad and wgrad GEMMs. colsum_partial (optional; needs R and
+ * C multiples of 64 and 16-byte aligned rows): f32 [R/64][C], the column sums of every 64-row tile of the INPUT —
+ * finished by rald_colsum_finish(partial, R/64, C, out, accumulate) into the bias gradient, fixed summation order. */
 int rald_cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t C, void* out_bf16, int64_t ld_out,
-                        void* out_t_bf16, int64_t ld_t, void* stream);
+                        void* out_t_bf16, int64_t ld_t, float* colsum_partial, void* stream);
+int rald_colsum_finish(const float* partial, int chunks, int64_t C, float* out, int accumulate, void* stream);
 
 /* out_bf16[f][j][c] = bf16(in_f16[f][j][c] - mean_j in_f16[f][j][c]) over frames x rows_per_frame rows of C columns
  * (pitches in elements): the fp16 V columns rald_attn_d64 consumed, centred and re-encoded for rald_attn_d64_bwd. */

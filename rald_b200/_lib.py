@@ -30,6 +30,7 @@ _SIGNATURES = {
     "rald_prof_dump": [c_int, c_void_p, c_void_p, c_i64],
     "rald_gemm_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
                        c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rald_gemm_bf16_accum": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p],
     "rald_gemm_bf16_f16cols": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_void_p],
     "rald_gemm_bf16_wsplit": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,
@@ -92,7 +93,8 @@ _SIGNATURES = {
     "rald_attn_d64_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int,
                           c_int, c_int, c_f32, c_void_p],
-    "rald_cast_transpose": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p],
+    "rald_cast_transpose": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p],
+    "rald_colsum_finish": [c_void_p, c_int, c_i64, c_void_p, c_int, c_void_p],
     "rald_center_cast_f16_bf16": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_i64, c_void_p],
     "rald_colsum": [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_int, c_void_p],
     "rald_ln_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_void_p, c_i64, c_void_p, c_i64,

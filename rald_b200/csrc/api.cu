@@ -17,6 +17,11 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                          static_cast<cudaStream_t>(stream));
 }
 
+int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
+                         int K, void* stream) {
+  return rald::gemm_bf16_accum_splitk(A, lda, W, ldw, out, ldo, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                            const float* bias, int M, int N, int K, int f16_start, int f16_period, void* stream) {
   return rald::gemm_bf16_f16cols(A, lda, W, ldw, out, ldo, bias, M, N, K, f16_start, f16_period,

@@ -78,6 +78,10 @@ struct GemmParams {
   //             tile rows kb * N + n_blk * BN at columns f * 64
   int b_mode, grp_rows, grp_frame0, grp_total;
   int ab_f16;                 // A and W are IEEE fp16 (kind::f16 with fp16 operands) instead of bf16
+  int k_splits;               // > 1 (fp32 reduce-add epilogue, no bias): every output tile is computed by k_splits work items,
+  int kb_per_split;           // each over kb_per_split k-blocks, all adding into `out` — the weight-gradient GEMMs of the
+                              // training step (few output tiles, K = rows of the batch). Summation order across the splits
+                              // is not fixed (fp32 adds in L2): results reproduce to ~1e-7 relative, not bit for bit
   unsigned long long* dbg;  // optional [gridDim.x][8] %globaltimer stamps of the first tile (tools/gemm_phases.py)
 };
 
@@ -191,8 +195,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blks * p.num_n_blks;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_tiles = p.num_m_blks * p.num_n_blks * p.k_splits;
+  const int num_kb_all = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = p.k_splits > 1 ? p.kb_per_split : num_kb_all;   // k-blocks per work item
+  // work item -> (row block, column block, first k-block); k_splits == 1: a work item is an output tile
+  auto decode = [&](int tile, int& m_blk, int& n_blk, int& kb0) {
+    const int t2 = tile / p.k_splits;
+    kb0 = (tile - t2 * p.k_splits) * num_kb;
+    m_blk = t2 / p.num_n_blks;
+    n_blk = t2 - m_blk * p.num_n_blks;
+  };
   // tile walk of this unit: tiles unit, unit + num_units, ...
   const int t_begin = unit, t_end = num_tiles, t_step = num_units;
   // A column of k-block kb (split weights: the A tiles are re-read for the second half of K)
@@ -254,8 +266,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // static weights: the W tiles of this CTA's first SLOTS ring slots do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
     while (w_pre < SLOTS && tile < t_end) {
-      const int m_blk = tile / p.num_n_blks;
-      const int n_blk = tile - m_blk * p.num_n_blks;
+      int m_blk, n_blk, kb0;
+      decode(tile, m_blk, n_blk, kb0);   // (k_splits == 1 here: w_static is off for split-K launches)
       mbar_arrive_expect_tx(&full_bar[w_pre], SLOT_BYTES);
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -276,9 +288,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int tile = t_begin; tile < t_end; tile += t_step) {
-        const int m_blk = tile / p.num_n_blks;
-        const int n_blk = tile - m_blk * p.num_n_blks;
-        for (int kb = 0; kb < num_kb; kb += G) {
+        int m_blk, n_blk, kb0;
+        decode(tile, m_blk, n_blk, kb0);
+        for (int kb = kb0; kb < kb0 + num_kb; kb += G) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* slot = smem + s * SLOT_BYTES;
           if (CG == 2) {
@@ -365,8 +377,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;  // 0..255 among the epilogue threads
     int it = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
-      const int m_blk = tile / p.num_n_blks;
-      const int n_blk = tile - m_blk * p.num_n_blks;
+      int m_blk, n_blk, kb0_unused;
+      decode(tile, m_blk, n_blk, kb0_unused);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       float* bias_s = s_bias + acc * BN;
@@ -545,7 +557,7 @@ static int launch_gemm_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int num_tiles = p.num_m_blks * p.num_n_blks;       // tiles of (128 * CG) x BN
+  const int num_tiles = p.num_m_blks * p.num_n_blks * p.k_splits;       // work items: tiles of (128 * CG) x BN (x K splits)
   const int max_units = max_ctas / CG;
   const int units = num_tiles < max_units ? num_tiles : max_units;
   ProfScope prof(FAM_GEMM, stream, 2.0 * p.M * p.N * p.K);
@@ -579,7 +591,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   constexpr int GMAX = EPI == EPI_GENERIC ? 1
                        : (Cfg::STAGES >= 8 && Cfg::STAGES % 4 == 0) ? 4
                        : (Cfg::STAGES >= 4 && Cfg::STAGES % 2 == 0) ? 2 : 1;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = p.k_splits > 1 ? p.kb_per_split : (p.K + GEMM_BK - 1) / GEMM_BK;
   if (GMAX > 1 && gemm_env().group && num_kb % GMAX == 0)
     return launch_gemm_g<BN, OUT_MODE, EPI, CG, GMAX>(tmA, tmB, tmO, p, max_ctas, stream);
   return launch_gemm_g<BN, OUT_MODE, EPI, CG, 1>(tmA, tmB, tmO, p, max_ctas, stream);
@@ -595,6 +607,7 @@ struct GemmOpts {
   int gelu_exact = 0;
   int b_mode = 0, grp_rows = 0, grp_frame0 = 0, grp_total = 0;   // folded cross-attention operands (GemmParams)
   int ab_f16 = 0;
+  int split_k = 0;      // allow K splits (fp32 accumulate-into-out GEMMs without bias: weight gradients)
 };
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -613,6 +626,13 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   GemmOpts o;
   o.resid_mod = resid_mod;
   return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, bn_hint, o, stream);
+}
+
+int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
+                           int K, cudaStream_t stream) {
+  GemmOpts o;
+  o.split_k = 1;
+  return gemm_impl(A, lda, W, ldw, out, ldo, nullptr, out, ldo, M, N, K, 1, 0, o, stream);
 }
 
 int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -700,6 +720,21 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     }
     if (bn == 0) bn = N % 64 == 0 ? 64 : 32;
   }
+  // ---- K splits (weight gradients: K = rows of the batch, few output tiles) ----
+  int k_splits = 1, kb_per_split = 0;
+  if (o.split_k) {
+    RALD_REQUIRE(out_mode == 1 && bias == nullptr && resid == out && ldr == ldo && o.resid_mod == 0 && o.b_mode == 0 &&
+                 !o.w_split, "gemm: K splits need the fp32 accumulate-into-out form without bias");
+    if (bn_hint == 0) bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));   // widest tile: least re-reads
+    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const long tiles = (long)m_blks * ((N + bn - 1) / bn);
+    int want = (int)(sms / (tiles > 0 ? tiles : 1));
+    if (want > 16) want = 16;
+    // largest split count <= want that divides the k-blocks into equal groups of a multiple of 4 (ring-slot grouping)
+    for (int ks = want; ks >= 2; --ks) {
+      if (num_kb % ks == 0 && (num_kb / ks) % 4 == 0) { k_splits = ks; kb_per_split = num_kb / ks; break; }
+    }
+  }
   RALD_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: BN=%d unsupported", bn);
 
   int epi = EPI_GENERIC;
@@ -717,7 +752,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   // CTA pairs: 256 x 256 tiles when the problem still fills the machine with them (large-batch regime)
   const int m_blks2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   const bool pair = gemm_env().pair && bn_hint >= 0 && bn == 256 && epi != EPI_GENERIC && N % 256 == 0 &&
-                    (long)m_blks2 * (N / 256) >= sms / 2;
+                    (long)m_blks2 * (N / 256) >= sms / 2 && k_splits == 1;
 
   GemmParams p;
   p.out = out;
@@ -741,7 +776,9 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.grp_frame0 = o.grp_frame0;
   p.grp_total = o.grp_total;
   p.ab_f16 = o.ab_f16;
-  p.w_static = (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
+  p.k_splits = k_splits;
+  p.kb_per_split = kb_per_split;
+  p.w_static = k_splits > 1 ? 0 : (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
   RALD_REQUIRE(o.f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;

@@ -56,22 +56,95 @@ cast_transpose_kernel(const void* __restrict__ in, int64_t ld_in, int64_t R, int
   }
 }
 
+// Fast path for full, aligned 64 x 64 tiles: 128-bit global accesses on both sides (8 elements per thread per access)
+// and, optionally, the per-tile column sums of the fp32 INPUT (bias gradients: the same pass that produces the wgrad
+// operands, instead of another sweep over dY): colpart[blockIdx.y][c] = sum of the tile's 64 rows of column c.
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+cast_transpose_vec_kernel(const void* __restrict__ in, int64_t ld_in, int64_t R, int64_t C, uint16_t* __restrict__ out,
+                          int64_t ld_out, uint16_t* __restrict__ out_t, int64_t ld_t, float* __restrict__ colpart) {
+  __shared__ uint16_t tile[64][72];          // 144-byte rows: 16-byte aligned vector stores
+  __shared__ float csum[32][64];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+  const int cv = threadIdx.x & 7, rr = threadIdx.x >> 3;     // 8 column octets x 32 rows, two passes
+  float cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = rr + 32 * i;
+    uint4 packed;
+    if (IN_F32) {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + (r0 + row) * ld_in + c0 + cv * 8);
+      const float4 a = src[0], b = src[1];
+      cs[0] += a.x; cs[1] += a.y; cs[2] += a.z; cs[3] += a.w;
+      cs[4] += b.x; cs[5] += b.y; cs[6] += b.z; cs[7] += b.w;
+      packed = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    } else {
+      packed = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(in) + (r0 + row) * ld_in + c0 + cv * 8);
+      if (colpart != nullptr) {
+        const uint32_t u[4] = {packed.x, packed.y, packed.z, packed.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cs[2 * k] += __uint_as_float(u[k] << 16);
+          cs[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+        }
+      }
+    }
+    if (out != nullptr) *reinterpret_cast<uint4*>(out + (r0 + row) * ld_out + c0 + cv * 8) = packed;
+    *reinterpret_cast<uint4*>(&tile[row][cv * 8]) = packed;
+  }
+  if (colpart != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) csum[rr][cv * 8 + k] = cs[k];
+  }
+  __syncthreads();
+  if (colpart != nullptr && threadIdx.x < 64) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a += csum[k][threadIdx.x];
+    colpart[(int64_t)blockIdx.y * C + c0 + threadIdx.x] = a;
+  }
+  if (out_t == nullptr) return;
+  // transposed side: 8 threads write the 128 contiguous bytes (64 rows) of one output row = input column
+  const int rv = threadIdx.x & 7, cc = threadIdx.x >> 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int col = cc + 32 * i;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      w[k] = (uint32_t)tile[rv * 8 + 2 * k][col] | ((uint32_t)tile[rv * 8 + 2 * k + 1][col] << 16);
+    *reinterpret_cast<uint4*>(out_t + (c0 + col) * ld_t + r0 + rv * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 int cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t C, void* out, int64_t ld_out,
-                   void* out_t, int64_t ld_t, cudaStream_t stream) {
+                   void* out_t, int64_t ld_t, float* colpart, cudaStream_t stream) {
   RALD_REQUIRE(R > 0 && C > 0, "cast_transpose: bad shape");
-  RALD_REQUIRE(out != nullptr || out_t != nullptr, "cast_transpose: no output");
+  RALD_REQUIRE(out != nullptr || out_t != nullptr || colpart != nullptr, "cast_transpose: no output");
   dim3 grid((unsigned)((C + 63) / 64), (unsigned)((R + 63) / 64));
   RALD_REQUIRE(grid.y < 65536, "cast_transpose: too many rows (%lld)", (long long)R);
-  if (in_f32)
-    cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, ld_in, R, C, reinterpret_cast<uint16_t*>(out), ld_out,
-                                                           reinterpret_cast<uint16_t*>(out_t), ld_t);
-  else
-    cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, ld_in, R, C, reinterpret_cast<uint16_t*>(out), ld_out,
-                                                            reinterpret_cast<uint16_t*>(out_t), ld_t);
+  const int esz = in_f32 ? 4 : 2;
+  const bool vec = R % 64 == 0 && C % 64 == 0 && (ld_in * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                   (out == nullptr || (ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)) &&
+                   (out_t == nullptr || (ld_t % 8 == 0 && (reinterpret_cast<uintptr_t>(out_t) & 15) == 0));
+  RALD_REQUIRE(colpart == nullptr || vec, "cast_transpose: column sums need the aligned 64 x 64-tile form");
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  uint16_t* ot = reinterpret_cast<uint16_t*>(out_t);
+  if (vec) {
+    if (in_f32) cast_transpose_vec_kernel<true><<<grid, 256, 0, stream>>>(in, ld_in, R, C, o, ld_out, ot, ld_t, colpart);
+    else cast_transpose_vec_kernel<false><<<grid, 256, 0, stream>>>(in, ld_in, R, C, o, ld_out, ot, ld_t, colpart);
+  } else {
+    if (in_f32) cast_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, ld_in, R, C, o, ld_out, ot, ld_t);
+    else cast_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, ld_in, R, C, o, ld_out, ot, ld_t);
+  }
   RALD_LAUNCHED();
   return 0;
 }
 
+// out[c] (+)= sum_k partial[k][c] (fixed order): second stage of the column sums produced by cast_transpose
+int colsum_finish(const float* partial, int chunks, int64_t C, float* out, int accumulate, cudaStream_t stream);
 
 // out[f][j][c] = bf16(in[f][j][c] - mean_j in[f][j][c]) for fp16 in: the V columns the forward attention consumed as
 // fp16, centred per (frame, column) and re-encoded for the backward attention kernel (attn_bwd.cu explains why).
@@ -135,6 +208,13 @@ colsum_final_kernel(const float* __restrict__ partial, int chunks, int64_t C, fl
   float a = 0.f;
   for (int k = 0; k < chunks; ++k) a += partial[(int64_t)k * C + c];
   out[c] = accumulate ? out[c] + a : a;
+}
+
+int colsum_finish(const float* partial, int chunks, int64_t C, float* out, int accumulate, cudaStream_t stream) {
+  RALD_REQUIRE(chunks > 0 && C > 0, "colsum_finish: bad shape");
+  colsum_final_kernel<<<(unsigned)((C + 127) / 128), 128, 0, stream>>>(partial, chunks, C, out, accumulate);
+  RALD_LAUNCHED();
+  return 0;
 }
 
 int colsum(const void* in, int in_f32, int64_t ld, int64_t R, int64_t C, float* partial_ws, int64_t ws_elems, float* out,
@@ -304,56 +384,70 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// 8 outputs per thread: 128-bit loads of the value and the gate octet (inner % 8 == 0)
 __global__ void __launch_bounds__(256)
-geglu_fwd_kernel(const uint32_t* __restrict__ u, int64_t T, int inner, uint32_t* __restrict__ g) {
-  const int64_t half = inner / 2;            // bf16 pairs per half row
-  const int64_t n = T * half;
+geglu_fwd_kernel(const uint4* __restrict__ u, int64_t T, int inner, uint4* __restrict__ g) {
+  const int64_t oct = inner / 8;             // octets per half row
+  const int64_t n = T * oct;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int64_t t = i / half, c = i - t * half;
-    const uint32_t v = u[t * (2 * half) + c], gt = u[t * (2 * half) + half + c];
-    const float v0 = __uint_as_float(v << 16), v1 = __uint_as_float(v & 0xffff0000u);
-    const float g0 = __uint_as_float(gt << 16), g1 = __uint_as_float(gt & 0xffff0000u);
-    g[i] = pack_bf16x2(v0 * gelu_exact_f(g0), v1 * gelu_exact_f(g1));
+    const int64_t t = i / oct, c = i - t * oct;
+    const uint4 v = u[t * (2 * oct) + c], gt = u[t * (2 * oct) + oct + c];
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gt.x, gt.y, gt.z, gt.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_bf16x2(__uint_as_float(vv[k] << 16) * gelu_exact_f(__uint_as_float(gg[k] << 16)),
+                         __uint_as_float(vv[k] & 0xffff0000u) * gelu_exact_f(__uint_as_float(gg[k] & 0xffff0000u)));
+    g[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 __global__ void __launch_bounds__(256)
-geglu_bwd_kernel(const uint32_t* __restrict__ u, const uint32_t* __restrict__ dg, int64_t T, int inner,
-                 uint32_t* __restrict__ du) {
-  const int64_t half = inner / 2;
-  const int64_t n = T * half;
+geglu_bwd_kernel(const uint4* __restrict__ u, const uint4* __restrict__ dg, int64_t T, int inner, uint4* __restrict__ du) {
+  const int64_t oct = inner / 8;
+  const int64_t n = T * oct;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int64_t t = i / half, c = i - t * half;
-    const uint32_t v = u[t * (2 * half) + c], gt = u[t * (2 * half) + half + c], d = dg[i];
-    const float v0 = __uint_as_float(v << 16), v1 = __uint_as_float(v & 0xffff0000u);
-    const float g0 = __uint_as_float(gt << 16), g1 = __uint_as_float(gt & 0xffff0000u);
-    const float d0 = __uint_as_float(d << 16), d1 = __uint_as_float(d & 0xffff0000u);
-    du[t * (2 * half) + c] = pack_bf16x2(d0 * gelu_exact_f(g0), d1 * gelu_exact_f(g1));
-    du[t * (2 * half) + half + c] = pack_bf16x2(d0 * v0 * gelu_grad_f(g0), d1 * v1 * gelu_grad_f(g1));
+    const int64_t t = i / oct, c = i - t * oct;
+    const uint4 v = u[t * (2 * oct) + c], gt = u[t * (2 * oct) + oct + c], d = dg[i];
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gt.x, gt.y, gt.z, gt.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t ov[4], og[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v0 = __uint_as_float(vv[k] << 16), v1 = __uint_as_float(vv[k] & 0xffff0000u);
+      const float g0 = __uint_as_float(gg[k] << 16), g1 = __uint_as_float(gg[k] & 0xffff0000u);
+      const float d0 = __uint_as_float(dd[k] << 16), d1 = __uint_as_float(dd[k] & 0xffff0000u);
+      ov[k] = pack_bf16x2(d0 * gelu_exact_f(g0), d1 * gelu_exact_f(g1));
+      og[k] = pack_bf16x2(d0 * v0 * gelu_grad_f(g0), d1 * v1 * gelu_grad_f(g1));
+    }
+    du[t * (2 * oct) + c] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    du[t * (2 * oct) + oct + c] = make_uint4(og[0], og[1], og[2], og[3]);
   }
 }
 
 int geglu_fwd(const void* u, int64_t T, int inner, void* g, cudaStream_t stream) {
-  RALD_REQUIRE(T > 0 && inner > 0 && inner % 2 == 0, "geglu_fwd: bad shape");
-  const int64_t n = T * (inner / 2);
+  RALD_REQUIRE(T > 0 && inner > 0 && inner % 8 == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(g) & 15) == 0, "geglu_fwd: bad shape / alignment (inner % 8, 16-byte pointers)");
+  const int64_t n = T * (inner / 8);
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  geglu_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(u), T, inner,
-                                                         reinterpret_cast<uint32_t*>(g));
+  geglu_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), T, inner,
+                                                         reinterpret_cast<uint4*>(g));
   RALD_LAUNCHED();
   return 0;
 }
 
 int geglu_bwd(const void* u, const void* dg, int64_t T, int inner, void* du, cudaStream_t stream) {
-  RALD_REQUIRE(T > 0 && inner > 0 && inner % 2 == 0, "geglu_bwd: bad shape");
-  const int64_t n = T * (inner / 2);
+  RALD_REQUIRE(T > 0 && inner > 0 && inner % 8 == 0 && ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(dg) |
+                                                         reinterpret_cast<uintptr_t>(du)) & 15) == 0,
+               "geglu_bwd: bad shape / alignment (inner % 8, 16-byte pointers)");
+  const int64_t n = T * (inner / 8);
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = (int64_t)device_sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  geglu_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(u),
-                                                         reinterpret_cast<const uint32_t*>(dg), T, inner,
-                                                         reinterpret_cast<uint32_t*>(du));
+  geglu_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(u),
+                                                         reinterpret_cast<const uint4*>(dg), T, inner,
+                                                         reinterpret_cast<uint4*>(du));
   RALD_LAUNCHED();
   return 0;
 }
@@ -484,9 +578,13 @@ int radar_tokens_bwd(const float* dtok, const float* feat, int B, int nr, int na
 extern "C" {
 
 int rald_cast_transpose(const void* in, int in_f32, int64_t ld_in, int64_t R, int64_t C, void* out_bf16, int64_t ld_out,
-                        void* out_t_bf16, int64_t ld_t, void* stream) {
-  return rald::cast_transpose(in, in_f32, ld_in, R, C, out_bf16, ld_out, out_t_bf16, ld_t,
+                        void* out_t_bf16, int64_t ld_t, float* colsum_partial, void* stream) {
+  return rald::cast_transpose(in, in_f32, ld_in, R, C, out_bf16, ld_out, out_t_bf16, ld_t, colsum_partial,
                               static_cast<cudaStream_t>(stream));
+}
+
+int rald_colsum_finish(const float* partial, int chunks, int64_t C, float* out, int accumulate, void* stream) {
+  return rald::colsum_finish(partial, chunks, C, out, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int rald_center_cast_f16_bf16(const void* in_f16, int64_t ld_in, void* out_bf16, int64_t ld_out, int frames,

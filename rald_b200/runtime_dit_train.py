@@ -123,15 +123,22 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
         _lib.call("rald_ln_rows", x.data_ptr(), self.dim, gamma_ptr, beta_ptr, frame_stride, rows_per_frame, plus_one,
                   out.data_ptr(), self.dim, 0, rows, self.dim, 1e-5, _lib.cur_stream())
 
-    def _transpose(self, t2d: torch.Tensor, want_plain: bool = False):
-        """[R, C] fp32 / bf16 (contiguous) -> (bf16 [R, C] or None, bf16 [C, R])."""
+    def _transpose(self, t2d: torch.Tensor, want_plain: bool = False, colsum_out: Optional[torch.Tensor] = None):
+        """[R, C] fp32 / bf16 (contiguous) -> (bf16 [R, C] or None, bf16 [C, R]); with colsum_out (fp32 [C]) the same pass
+        also yields the column sums of the input (bias gradient)."""
         R, C = t2d.shape
         is_f32 = t2d.dtype == torch.float32
         plain = torch.empty(R, C, device=t2d.device, dtype=BF) if (want_plain and is_f32) else None
         Rp = (R + 7) // 8 * 8
         tt = torch.empty(C, Rp, device=t2d.device, dtype=BF) if Rp == R else torch.zeros(C, Rp, device=t2d.device, dtype=BF)
+        fused = colsum_out is not None and R % 64 == 0 and C % 64 == 0
+        part = torch.empty(R // 64, C, device=t2d.device, dtype=torch.float32) if fused else None
         _lib.call("rald_cast_transpose", t2d.data_ptr(), 1 if is_f32 else 0, C, R, C, _p(plain), C, tt.data_ptr(), Rp,
-                  _lib.cur_stream())
+                  _p(part), _lib.cur_stream())
+        if fused:
+            _lib.call("rald_colsum_finish", part.data_ptr(), R // 64, C, colsum_out.data_ptr(), 0, _lib.cur_stream())
+        elif colsum_out is not None:
+            self._colsum(t2d, colsum_out)
         return (plain if is_f32 else (t2d if want_plain else None)), tt
 
     def _colsum(self, t2d: torch.Tensor, out: torch.Tensor):
@@ -142,11 +149,12 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
                   ws.numel(), out.data_ptr(), 0, _lib.cur_stream())
 
     def _wgrad(self, dyT: torch.Tensor, xT: torch.Tensor, out: torch.Tensor):
-        """out fp32 [N_out, K_in] = dY^T X with dyT [N_out, T], xT [K_in, T] (bf16, K-major over the rows T)."""
+        """out fp32 [N_out, K_in] += dY^T X with dyT [N_out, T], xT [K_in, T] (bf16, K-major over the rows T)."""
         n_out, T = dyT.shape
         k_in = xT.shape[0]
-        self._gemm(dyT.data_ptr(), T, xT.data_ptr(), xT.shape[1], out.data_ptr(), out.shape[-1], n_out, k_in, T,
-                   out_mode=1)
+        # `out` is zero-initialised: the K extent (rows of the batch) is split over several CTAs per output tile
+        _lib.call("rald_gemm_bf16_accum", dyT.data_ptr(), T, xT.data_ptr(), xT.shape[1], out.data_ptr(), out.shape[-1],
+                  n_out, k_in, T, _lib.cur_stream())
 
     def _sgemm(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta=0.0):
         _lib.call("rald_sgemm_f32", ta, tb, M, N, K, 1.0, A.data_ptr(), lda, B.data_ptr(), ldb, beta, C.data_ptr(), ldc,
@@ -289,14 +297,14 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
         stream = _lib.cur_stream
 
         # stacked gradient buffers (views of them are returned per parameter)
-        G = dict(w_qkv=torch.empty(depth, 3 * dim, dim, device=dev, dtype=f32),
-                 w_o1=torch.empty(depth, dim, dim, device=dev, dtype=f32), b_o1=torch.empty(depth, dim, device=dev, dtype=f32),
-                 w_q2=torch.empty(depth, dim, dim, device=dev, dtype=f32),
-                 w_kv2=torch.empty(depth, 2 * dim, dim, device=dev, dtype=f32),
-                 w_o2=torch.empty(depth, dim, dim, device=dev, dtype=f32), b_o2=torch.empty(depth, dim, device=dev, dtype=f32),
-                 w_ff1=torch.empty(depth, 8 * dim, dim, device=dev, dtype=f32),
+        G = dict(w_qkv=torch.zeros(depth, 3 * dim, dim, device=dev, dtype=f32),
+                 w_o1=torch.zeros(depth, dim, dim, device=dev, dtype=f32), b_o1=torch.empty(depth, dim, device=dev, dtype=f32),
+                 w_q2=torch.zeros(depth, dim, dim, device=dev, dtype=f32),
+                 w_kv2=torch.zeros(depth, 2 * dim, dim, device=dev, dtype=f32),
+                 w_o2=torch.zeros(depth, dim, dim, device=dev, dtype=f32), b_o2=torch.empty(depth, dim, device=dev, dtype=f32),
+                 w_ff1=torch.zeros(depth, 8 * dim, dim, device=dev, dtype=f32),
                  b_ff1=torch.empty(depth, 8 * dim, device=dev, dtype=f32),
-                 w_ff2=torch.empty(depth, dim, 4 * dim, device=dev, dtype=f32),
+                 w_ff2=torch.zeros(depth, dim, 4 * dim, device=dev, dtype=f32),
                  b_ff2=torch.empty(depth, dim, device=dev, dtype=f32))
         dmod = torch.empty(B, depth, 3, 2 * dim, device=dev, dtype=f32)
         dtok = torch.zeros(B * L, dim, device=dev, dtype=f32)
@@ -315,7 +323,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
         dF32[:, :C] = dF.reshape(T, C)
         dF16, dF16T = self._transpose(dF32, want_plain=True)               # [T, 32], [32, T]
         _, ynT = self._transpose(saved["yn"])                              # [512, T]
-        g_wout = torch.empty(32, dim, device=dev, dtype=f32)
+        g_wout = torch.zeros(32, dim, device=dev, dtype=f32)
         self._wgrad(dF16T, ynT, g_wout)
         dyn = torch.empty(T, dim, device=dev, dtype=BF)
         self._gemm(dF16.data_ptr(), 32, self.w_out_t.data_ptr(), 32, dyn.data_ptr(), dim, T, dim, 32)
@@ -338,16 +346,14 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
                 return dmod.data_ptr() + ((n * 3 + i) * 2 * dim) * 4
 
             # -- feed-forward: h3 = h2 + g W2^T + b2,  g = geglu(u),  u = xn3 W1^T + b1
-            dh16, dh16T = self._transpose(dh, want_plain=True)
-            self._colsum(dh, G["b_ff2"][n])
+            dh16, dh16T = self._transpose(dh, want_plain=True, colsum_out=G["b_ff2"][n])
             _, gT = self._transpose(k["g"])
             self._wgrad(dh16T, gT, G["w_ff2"][n])
             dg = torch.empty(T, 4 * dim, device=dev, dtype=BF)
             self._gemm(dh16.data_ptr(), dim, self.w_ff2_t[n].data_ptr(), dim, dg.data_ptr(), 4 * dim, T, 4 * dim, dim)
             du = torch.empty(T, 8 * dim, device=dev, dtype=BF)
             _lib.call("rald_geglu_bwd", k["u"].data_ptr(), dg.data_ptr(), T, 4 * dim, du.data_ptr(), stream())
-            self._colsum(du, G["b_ff1"][n])
-            _, duT = self._transpose(du)
+            _, duT = self._transpose(du, colsum_out=G["b_ff1"][n])
             _, xn3T = self._transpose(k["xn3"])
             self._wgrad(duT, xn3T, G["w_ff1"][n])
             dxn = torch.empty(T, dim, device=dev, dtype=BF)
@@ -356,8 +362,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
             del gT, dg, du, duT, xn3T
 
             # -- attn2: h2 = h1 + a2 Wo2^T + bo2
-            dh16, dh16T = self._transpose(dh, want_plain=True)
-            self._colsum(dh, G["b_o2"][n])
+            dh16, dh16T = self._transpose(dh, want_plain=True, colsum_out=G["b_o2"][n])
             _, a2T = self._transpose(k["a2"])
             self._wgrad(dh16T, a2T, G["w_o2"][n])
             da = torch.empty(T, dim, device=dev, dtype=BF)
@@ -381,8 +386,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
             del a2T, dq2, dkv2, dq2T, xn2T, dkv2T
 
             # -- attn1: h1 = h0 + a1 Wo1^T + bo1
-            dh16, dh16T = self._transpose(dh, want_plain=True)
-            self._colsum(dh, G["b_o1"][n])
+            dh16, dh16T = self._transpose(dh, want_plain=True, colsum_out=G["b_o1"][n])
             _, a1T = self._transpose(k["a1"])
             self._wgrad(dh16T, a1T, G["w_o1"][n])
             self._gemm(dh16.data_ptr(), dim, self.w_o1_t[n].data_ptr(), dim, da.data_ptr(), dim, T, dim, dim)
@@ -405,7 +409,7 @@ class DitTrainRuntime(_lib.RuntimeNotCopied):
         x32 = torch.zeros(T, 32, device=dev, dtype=f32)
         x32[:, :C] = saved["x2d"]
         _, xT = self._transpose(x32)                                         # [32, T]
-        g_win = torch.empty(dim, 32, device=dev, dtype=f32)
+        g_win = torch.zeros(dim, 32, device=dev, dtype=f32)
         self._wgrad(dhT, xT, g_win)
 
         # ---- adaLN linears and the timestep-embedding MLP from dmod [B, depth*3*1024] ----

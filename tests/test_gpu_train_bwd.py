@@ -33,11 +33,37 @@ def test_cast_transpose(R, C, f32):
     Rp = (R + 7) // 8 * 8
     out = torch.empty(R, C, device=DEV, dtype=BF)
     out_t = torch.zeros(C, Rp, device=DEV, dtype=BF)
-    _lib.call("rald_cast_transpose", x.data_ptr(), 1 if f32 else 0, C, R, C, out.data_ptr(), C, out_t.data_ptr(), Rp, _s())
+    _lib.call("rald_cast_transpose", x.data_ptr(), 1 if f32 else 0, C, R, C, out.data_ptr(), C, out_t.data_ptr(), Rp, 0,
+              _s())
     want = x.to(BF)
     assert torch.equal(out, want)
     assert torch.equal(out_t[:, :R], want.t())
     assert float(out_t[:, R:].abs().sum()) == 0.0
+    if R % 64 == 0 and C % 64 == 0:      # the same pass with the fused column sums of the (un-rounded) input
+        part = torch.empty(R // 64, C, device=DEV)
+        out2 = torch.empty_like(out)
+        out_t2 = torch.empty_like(out_t)
+        _lib.call("rald_cast_transpose", x.data_ptr(), 1 if f32 else 0, C, R, C, out2.data_ptr(), C, out_t2.data_ptr(), Rp,
+                  part.data_ptr(), _s())
+        assert torch.equal(out2, want) and torch.equal(out_t2[:, :R], want.t())
+        bias = torch.full((C,), 2.0, device=DEV)
+        _lib.call("rald_colsum_finish", part.data_ptr(), R // 64, C, bias.data_ptr(), 1, _s())
+        assert rel_l2(bias, x.double().sum(0) + 2.0) <= 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 32768), (4096, 512, 4096), (32, 512, 1024), (512, 32, 8192), (1536, 512, 128),
+                                   (1024, 512, 8)])
+def test_gemm_accumulate_split_k(M, N, K):
+    """out += A W^T with the K extent split over several CTAs per output tile (the weight-gradient GEMMs) against an fp64
+    product of the same bf16 operands; accumulates onto what `out` holds."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).to(BF)
+    W = torch.randn(N, K, generator=g).to(DEV).to(BF)
+    out0 = torch.randn(M, N, generator=g).to(DEV)
+    out = out0.clone()
+    _lib.call("rald_gemm_bf16_accum", A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, _s())
+    want = out0.double() + A.double() @ W.double().t()
+    assert rel_l2(out, want) <= 1e-5
 
 
 @pytest.mark.parametrize("R,C,f32", [(4096, 512, True), (100, 33, True), (70000, 64, False)])
