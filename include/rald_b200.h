@@ -75,6 +75,13 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
 int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
                          int K, void* stream);
 
+/* rald_gemm_bf16_accum with the W operand read w_col_shift columns to the right of A: out[m][n] += sum_k A[m][k] *
+ * W[n][k + w_col_shift] (w_col_shift % 8 == 0), columns of W outside [0, K) counting as zero. One (kd, kh) tap pair of a 3x3x3 convolution's weight gradient
+ * when A = dY^T and W = X^T are laid out on the flattened zero-padded voxel grid (rald_enc_pad_transpose), where a tap is
+ * a constant index offset (autograd through nn.Conv3d, model/models_radar_encoder.py:63-72, 37-41). */
+int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_t ldw, int w_col_shift, float* out,
+                               int64_t ldo, int M, int N, int K, void* stream);
+
 /* rald_gemm_bf16 with out_mode 0 whose output columns with (col % f16_period) >= f16_start are written as IEEE fp16
  * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
@@ -554,6 +561,32 @@ int rald_sgemm_f32(int trans_a, int trans_b, int M, int N, int K, float alpha, c
  * da_emb [na][dim], de_emb [ne][dim] (rows of the embedding tables beyond nr / na / ne receive no gradient). */
 int rald_radar_tokens_bwd(const float* dtok, const float* feat, int B, int nr, int na, int ne, int cz, int dim, float* dw,
                           float* db, float* dr_emb, float* da_emb, float* de_emb, void* stream);
+
+/* ---- backward of the radar-cube encoder (training with unfreeze_radar_enc: true; autograd through
+ * model/models_radar_encoder.py). Convolution dgrad = rald_conv3d_cl on flipped / transposed weights, wgrad =
+ * rald_gemm_bf16_accum_shift per tap, 1x1 convolutions = GEMMs; the rest: ---- */
+
+/* GroupNorm(groups, eps) (+ swish when swish != 0) backward (Normalize + nonlinearity :5-12): x, dy fp32 [B, V, C], stats
+ * = rald_gn_stats of x. dx = d loss / d x (+ add when given, e.g. the identity-shortcut gradient); sums f64 [B][C][2] =
+ * {sum_v dyh * xhat, sum_v dyh} (d gamma / d beta = their sums over B). */
+int rald_gn_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, int B, int64_t V,
+                int C, int groups, float eps, int swish, double* sums, const float* add, float* dx, void* stream);
+
+/* in [B, D, H, W, C] (f32 or bf16, channels last) -> out_t bf16 [copies * copy_rows][ld]: element (c, P) of copy r at
+ * row r * copy_rows + c, column P + pos_bias - r, P = flattened index of voxel (dil*d+1, dil*h+1, dil*w+1) on the
+ * zero-padded grid [B][dil*D+2][dil*H+2][Wp] (Wp % 8 == 0, >= dil*W+2). out_t must be zero-initialised, ld >= grid + 8.
+ * dil = 2 places a stride-2 convolution's output gradient on its input grid; copies = 3 writes the three kw-shifted
+ * copies of a convolution input (TMA box origins must be 16-byte aligned: only the kd / kh part of a tap offset can be
+ * an operand shift of rald_gemm_bf16_accum_shift). */
+int rald_enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
+                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, void* stream);
+
+/* out bf16 [B, 2D, 2H, 2W, C] (zero-initialised by the caller) with out[2d+1, 2h+1, 2w+1] = in[d, h, w]: the operand of
+ * the stride-2 convolution's dgrad (Downsample :34-41) as a stride-1 convolution with flipped weights. */
+int rald_enc_stuff(const float* in, int B, int D, int H, int W, int C, void* out_bf16, void* stream);
+
+/* Backward of rald_enc_attn (AttnBlock :121-133): qkv fp32 [B*n, 3C], dO fp32 [B*n, C] -> dqkv fp32 [B*n, 3C]. */
+int rald_enc_attn_bwd(const float* qkv, const float* dO, float* dqkv, int B, int n, int C, void* stream);
 
 #ifdef __cplusplus
 }

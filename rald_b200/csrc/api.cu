@@ -19,7 +19,12 @@ int rald_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
 
 int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
                          int K, void* stream) {
-  return rald::gemm_bf16_accum_splitk(A, lda, W, ldw, out, ldo, M, N, K, static_cast<cudaStream_t>(stream));
+  return rald::gemm_bf16_accum_splitk(A, lda, W, ldw, 0, out, ldo, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
+int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_t ldw, int w_col_shift, float* out,
+                               int64_t ldo, int M, int N, int K, void* stream) {
+  return rald::gemm_bf16_accum_splitk(A, lda, W, ldw, w_col_shift, out, ldo, M, N, K, static_cast<cudaStream_t>(stream));
 }
 
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,

@@ -78,6 +78,9 @@ struct GemmParams {
   //             tile rows kb * N + n_blk * BN at columns f * 64
   int b_mode, grp_rows, grp_frame0, grp_total;
   int ab_f16;                 // A and W are IEEE fp16 (kind::f16 with fp16 operands) instead of bf16
+  int w_k_off;                // added to the K coordinate of every W tile (A unaffected): W is read `w_k_off` columns to
+                              // the right of A (negative: left; columns outside [0, K) read zeros) — a tap of the
+                              // convolution weight gradient on the flattened padded voxel grid (enc_bwd.cu)
   int k_splits;               // > 1 (fp32 reduce-add epilogue, no bias): every output tile is computed by k_splits work items,
   int kb_per_split;           // each over kb_per_split k-blocks, all adding into `out` — the weight-gradient GEMMs of the
                               // training step (few output tiles, K = rows of the batch). Summation order across the splits
@@ -216,7 +219,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else tma_load_2d(dst, &tmB, bar, x, y);
     };
     if (p.b_mode == 0) {
-      ld(sb, kb * GEMM_BK, n_blk * BN + (int)cta_rank * (BN / CG));
+      ld(sb, kb * GEMM_BK + p.w_k_off, n_blk * BN + (int)cta_rank * (BN / CG));
     } else {
       const int f = p.grp_frame0 + (m_blk * TILE_M) / p.grp_rows;
       if (p.b_mode == 1) {
@@ -608,6 +611,7 @@ struct GemmOpts {
   int b_mode = 0, grp_rows = 0, grp_frame0 = 0, grp_total = 0;   // folded cross-attention operands (GemmParams)
   int ab_f16 = 0;
   int split_k = 0;      // allow K splits (fp32 accumulate-into-out GEMMs without bias: weight gradients)
+  int w_k_off = 0;      // column shift of the W operand (GemmParams::w_k_off)
 };
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -628,10 +632,11 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
   return gemm_impl(A, lda, W, ldw, out, ldo, bias, resid, ldr, M, N, K, out_mode, bn_hint, o, stream);
 }
 
-int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
-                           int K, cudaStream_t stream) {
+int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int w_k_off, float* out, int64_t ldo,
+                           int M, int N, int K, cudaStream_t stream) {
   GemmOpts o;
   o.split_k = 1;
+  o.w_k_off = w_k_off;
   return gemm_impl(A, lda, W, ldw, out, ldo, nullptr, out, ldo, M, N, K, 1, 0, o, stream);
 }
 
@@ -699,6 +704,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(o.f16_period == 0 || (o.f16_period % 64 == 0 && o.f16_start % 64 == 0 && o.f16_start < o.f16_period),
                "gemm: fp16 column window start=%d period=%d must be multiples of 64", o.f16_start, o.f16_period);
   RALD_REQUIRE(o.f16_period == 0 || N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
+  RALD_REQUIRE(o.w_k_off % 8 == 0, "gemm: W column shift %d must be a multiple of 8 (TMA box origins are 16-byte aligned)",
+               o.w_k_off);
   RALD_REQUIRE(!o.w_split || K % GEMM_BK == 0, "gemm: split weights need K=%d to be a multiple of %d", K, GEMM_BK);
   const int k_total = o.w_split ? 2 * K : K;   // k extent the main loop walks
 
@@ -729,7 +736,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const long tiles = (long)m_blks * ((N + bn - 1) / bn);
     int want = (int)(sms / (tiles > 0 ? tiles : 1));
-    if (want > 16) want = 16;
+    if (want > 64) want = 64;
     // largest split count <= want that divides the k-blocks into equal groups of a multiple of 4 (ring-slot grouping)
     for (int ks = want; ks >= 2; --ks) {
       if (num_kb % ks == 0 && (num_kb / ks) % 4 == 0) { k_splits = ks; kb_per_split = num_kb / ks; break; }
@@ -776,6 +783,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.grp_frame0 = o.grp_frame0;
   p.grp_total = o.grp_total;
   p.ab_f16 = o.ab_f16;
+  p.w_k_off = o.w_k_off;
   p.k_splits = k_splits;
   p.kb_per_split = kb_per_split;
   p.w_static = k_splits > 1 ? 0 : (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;

@@ -23,8 +23,9 @@ int gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* o
 // out (fp32 [M,N], pitch ldo) += A W^T with the K extent split over several CTAs per output tile when the tiles alone do
 // not fill the machine (TMA reduce-add epilogue; summation order across splits not fixed): the weight-gradient GEMMs of
 // the training step, K = rows of the batch.
-int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int M, int N,
-                           int K, cudaStream_t stream);
+// w_k_off: W is read that many columns to the right of A (columns outside [0, K) read zeros).
+int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int w_k_off, float* out, int64_t ldo,
+                           int M, int N, int K, cudaStream_t stream);
 
 // bf16 output in which the columns with (col % f16_period) >= f16_start are written as fp16 instead: the V
 // projections feeding attn_d64 (fp16 probabilities x fp16 values on the tensor cores).

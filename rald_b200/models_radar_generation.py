@@ -23,6 +23,7 @@ from . import _lib
 from .models_radar_encoder import Encoder as RadarEncoder
 from .runtime_dit import DitRuntime
 from .runtime_dit_train import DitTrainFunction, DitTrainRuntime, RadarTokensFunction
+from .runtime_encoder_train import EncoderTrainFunction, EncoderTrainRuntime
 
 
 def zero_module(module: nn.Module) -> nn.Module:
@@ -218,6 +219,7 @@ class EDMPrecond(nn.Module):
             self.radar_token_project = nn.Linear(self.configs.enc_radar_ch if self.configs.use_radar_enc else 1, tc)
         self.__dict__["_rt"] = None
         self.__dict__["_trt"] = None
+        self.__dict__["_ert"] = None
 
     # ---- runtime plumbing -------------------------------------------------------------------------
     def _runtime(self) -> DitRuntime:
@@ -277,10 +279,16 @@ class EDMPrecond(nn.Module):
             self.__dict__["_trt"] = DitTrainRuntime(self)
         return self.__dict__["_trt"]
 
+    def _enc_train_runtime(self) -> EncoderTrainRuntime:
+        if self.__dict__.get("_ert") is None:
+            self.__dict__["_ert"] = EncoderTrainRuntime(self.radar_enc)
+        return self.__dict__["_ert"]
+
     def _tokens_train(self, label_tokens, cond_type) -> torch.Tensor:
-        """fp32 conditioning tokens [B, L, dim] for the training forward, differentiable in radar_token_project and
-        the r / a / e embeddings. The radar encoder runs on the inference kernels as a frozen feature extractor (the
-        reference's `radar_enc._encode` under no_grad, engine_generation.py:86-87): its backward is not built."""
+        """fp32 conditioning tokens [B, L, dim] for the training forward, differentiable in radar_token_project, the
+        r / a / e embeddings and — when its parameters require gradients — the radar encoder
+        (runtime_encoder_train.EncoderTrainFunction); a frozen encoder runs on the inference kernels (the reference's
+        `radar_enc._encode` under no_grad, engine_generation.py:86-87)."""
         if cond_type != "radar":
             raise ValueError(f"cond_type={cond_type!r}: only 'radar' conditioning exists in the reference forward")
         if label_tokens.dim() == 3:  # already tokens
@@ -290,11 +298,13 @@ class EDMPrecond(nn.Module):
         feat = label_tokens[..., 0:1].contiguous().float()
         if self.configs.get("unfreeze_radar_enc", False):
             if any(p.requires_grad for p in self.radar_enc.parameters()):
-                raise NotImplementedError(
-                    "rald_b200: the backward pass of the radar Conv3d encoder is not built (SURVEY.md §8f #3 covers the "
-                    "denoiser); freeze it for training with net.radar_enc.requires_grad_(False)")
-            with torch.no_grad():
-                feat = self.radar_enc.forward_channels_last(feat)
+                # trained jointly with the denoiser (the shipped configuration): differentiable encoder
+                named = list(self.radar_enc.named_parameters())
+                feat = EncoderTrainFunction.apply(self._enc_train_runtime(), [n for n, _ in named], feat,
+                                                  *[p for _, p in named])
+            else:
+                with torch.no_grad():
+                    feat = self.radar_enc.forward_channels_last(feat)
         p = self.radar_token_project
         if feat.shape[-1] != p.in_features:
             raise ValueError(f"radar_token_project expects {p.in_features} input channels, the conditioning has "

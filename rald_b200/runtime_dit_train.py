@@ -493,8 +493,7 @@ class DitTrainFunction(torch.autograd.Function):
 
 class RadarTokensFunction(torch.autograd.Function):
     """tokens = Linear(feat) + r / a / e position embeddings (process_radar_cond :390-405), differentiable in the
-    projection and the embedding tables (the encoder features themselves are treated as constants: the encoder's
-    backward is not built)."""
+    projection, the embedding tables and the encoder features."""
 
     @staticmethod
     def forward(ctx, feat, w, b, r_emb, a_emb, e_emb):
@@ -504,13 +503,13 @@ class RadarTokensFunction(torch.autograd.Function):
         tok = torch.empty(B, nr * na * ne, dim, device=feat.device, dtype=torch.float32)
         _lib.call("rald_radar_tokens", feat.data_ptr(), B, nr, na, ne, cz, w.data_ptr(), b.data_ptr(), r_emb.data_ptr(),
                   a_emb.data_ptr(), e_emb.data_ptr(), dim, tok.data_ptr(), 0, _lib.cur_stream())
-        ctx.save_for_backward(feat)
+        ctx.save_for_backward(feat, w)
         ctx.geom = (B, nr, na, ne, cz, dim, r_emb.shape[0], a_emb.shape[0], e_emb.shape[0])
         return tok
 
     @staticmethod
     def backward(ctx, dtok):
-        (feat,) = ctx.saved_tensors
+        feat, w = ctx.saved_tensors
         B, nr, na, ne, cz, dim, tr_, ta_, te_ = ctx.geom
         dev = feat.device
         dtok = dtok.contiguous().float()
@@ -521,4 +520,11 @@ class RadarTokensFunction(torch.autograd.Function):
         de = torch.zeros(te_, dim, device=dev, dtype=torch.float32)
         _lib.call("rald_radar_tokens_bwd", dtok.data_ptr(), feat.data_ptr(), B, nr, na, ne, cz, dim, dw.data_ptr(),
                   db.data_ptr(), dr.data_ptr(), da.data_ptr(), de.data_ptr(), _lib.cur_stream())
-        return None, dw, db, dr, da, de
+        dfeat = None
+        if ctx.needs_input_grad[0]:   # d feat = d tok W: into the (trainable) radar encoder
+            wc = w.detach().float().contiguous()
+            dfeat = torch.empty(B * nr * na * ne, cz, device=dev, dtype=torch.float32)
+            _lib.call("rald_sgemm_f32", 0, 0, B * nr * na * ne, cz, dim, 1.0, dtok.data_ptr(), dim, wc.data_ptr(), cz, 0.0,
+                      dfeat.data_ptr(), cz, _lib.cur_stream())
+            dfeat = dfeat.reshape(B, nr, na, ne, cz)
+        return dfeat, dw, db, dr, da, de

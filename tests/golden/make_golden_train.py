@@ -91,6 +91,31 @@ def main():
     print(f"oracle autograd vs reference: loss {abs(loss_o.item() - loss.item()):.2e}, worst gradient rel-L2 {worst:.2e}")
     np.savez_compressed(os.path.join(HERE, "train_grads.npz"), **out)
 
+    # ---- the same step with the radar encoder TRAINABLE (unfreeze_radar_enc: true, the shipped configuration): the
+    # denoiser's gradients are unchanged (asserted), the encoder's 144 tensors are stored in train_grads_enc.npz ----
+    net.zero_grad(set_to_none=True)
+    net.radar_enc.requires_grad_(True)
+    D2 = net(y + noise * sigma, sigma, cube, "radar")
+    loss2 = (weight * (D2 - y) ** 2).mean()
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) < 1e-9
+    out2 = {"loss": np.float64(loss2.item())}
+    enc_names = []
+    for name, p in net.named_parameters():
+        gr = p.grad.detach()
+        if not name.startswith("radar_enc."):
+            assert orc.rel_l2(gr, ref_grads[name]) < 1e-6, name
+            continue
+        enc_names.append(name)
+        out2["norm/" + name] = np.float64(gr.double().norm().item())
+        if gr.numel() <= FULL_BELOW:
+            out2["full/" + name] = gr.numpy()
+        else:
+            out2["sample/" + name] = gr.reshape(-1)[torch.from_numpy(sample_index(name, gr.numel()))].numpy()
+    out2["names"] = np.array(enc_names)
+    print(f"trainable encoder: {len(enc_names)} tensors", flush=True)
+    np.savez_compressed(os.path.join(HERE, "train_grads_enc.npz"), **out2)
+
 
 if __name__ == "__main__":
     main()

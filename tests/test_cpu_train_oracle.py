@@ -43,3 +43,33 @@ def test_oracle_autograd_reproduces_reference_gradients():
         else:
             idx = torch.from_numpy(grad_sample_index(name, gr.numel()))
             assert rel_l2(gr.reshape(-1)[idx], torch.from_numpy(fx["sample/" + name])) <= 2e-4, name
+
+
+def test_oracle_autograd_reproduces_reference_encoder_gradients():
+    """The same step with the radar encoder trainable (the shipped configuration): autograd through the oracle's encoder
+    restatement reproduces the 144 encoder gradients of tests/golden/train_grads_enc.npz."""
+    fx0 = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    fx = np.load(os.path.join(GOLDEN, "train_grads_enc.npz"))
+    sd = cpu_state_dict(build_denoiser())
+    for v in sd.values():
+        v.requires_grad_(True)
+    cube = synth.radar_cube(2, seed=1024)
+    y, sigma, noise = (torch.from_numpy(fx0[k]) for k in ("y", "sigma", "noise"))
+    tok = orc.process_radar_cond(sd, cube)
+    D = orc.edm_precond(sd, y + noise * sigma, sigma, tok)
+    loss = ((sigma ** 2 + 1.0) / sigma ** 2 * (D - y) ** 2).mean()
+    loss.backward()
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * float(fx["loss"])
+    names = [str(n) for n in fx["names"]]
+    assert len(names) == 144
+    for name in names:
+        gr = sd[name].grad
+        assert gr is not None, name
+        if name.endswith(".k.bias"):       # analytically zero: rounding noise on both sides
+            continue
+        assert abs(float(gr.double().norm()) - float(fx["norm/" + name])) <= 1e-3 * float(fx["norm/" + name]), name
+        if "full/" + name in fx.files:
+            assert rel_l2(gr, torch.from_numpy(fx["full/" + name])) <= 1e-3, name
+        else:
+            idx = torch.from_numpy(grad_sample_index(name, gr.numel()))
+            assert rel_l2(gr.reshape(-1)[idx], torch.from_numpy(fx["sample/" + name])) <= 1e-3, name

@@ -320,9 +320,13 @@ def test_edm_loss_backward_and_optimizer_step():
     assert losses[2] < losses[0]
 
 
-def test_encoder_gradients_are_refused():
+def test_frozen_and_partially_frozen_encoder():
+    """requires_grad_(False) on the radar encoder (the reference's frozen-encoder option) leaves its .grad empty; the
+    denoiser still trains."""
     net = build_denoiser(device=DEV).train()
+    net.radar_enc.requires_grad_(False)
     cube = synth.radar_cube(1, seed=7).to(DEV)
     y = (synth.unit_latents([1]) * 0.7).to(DEV)
-    with pytest.raises(NotImplementedError):
-        EDMLoss()(net, y, cube, "radar")
+    EDMLoss()(net, y, cube, "radar").backward()
+    assert all(p.grad is None for p in net.radar_enc.parameters())
+    assert net.model.proj_in.weight.grad is not None and net.radar_token_project.weight.grad is not None
