@@ -580,7 +580,27 @@ def leg_train_step(dev, peaks, batches=(8, 64), anchors=True, reps=3):
         out[f"batch{B}"] = {"ms_per_step": ms, "frames_per_s": B / (ms * 1e-3), "tflops_algorithmic": tf,
                             "frac_of_sustained_bf16": tf / peaks["bf16_tflops_sustained"],
                             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
-    del net
+    # ---- the shipped configuration: radar encoder trained jointly (unfreeze_radar_enc: true), cubes as input ----
+    net.radar_enc.requires_grad_(True)
+    Bf = batches[0]
+    cubes = frame_cubes(0, Bf).to(dev)
+    yf = (synth.unit_latents(range(Bf)) * 0.7).to(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+
+    def full_step():
+        for p in net.parameters():
+            p.grad = None
+        loss = crit(net, yf, cubes, "radar")
+        loss.backward()
+        return loss
+    msf = cuda_time(full_step, reps, warm=2 if reps > 1 else 1)
+    gflop_full = 3 * (GFLOP_PER_EVAL + GFLOP_ENCODER)
+    out[f"batch{Bf}_with_encoder"] = {
+        "ms_per_step": msf, "frames_per_s": Bf / (msf * 1e-3), "gflop_per_frame_algorithmic": gflop_full,
+        "tflops_algorithmic": Bf * gflop_full / msf, "frac_of_sustained_bf16": Bf * gflop_full / msf / peaks["bf16_tflops_sustained"],
+        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        "note": "EDMLoss forward + backward through encoder + denoiser, every one of the 637 parameters trainable"}
+    del net, cubes
     torch.cuda.empty_cache()
     if not anchors:
         return out
@@ -593,9 +613,11 @@ def leg_train_step(dev, peaks, batches=(8, 64), anchors=True, reps=3):
         for k, v in sd.items():
             if not k.startswith("radar_enc."):
                 v.requires_grad_(True)
+        cube_e = frame_cubes(0, B).to(dev)
         with torch.no_grad():
-            tok = orc.process_radar_cond(sd, frame_cubes(0, B).to(dev))
+            tok_const = orc.process_radar_cond(sd, cube_e)
         y = (synth.unit_latents(range(B)) * 0.7).to(dev)
+        mode = {"enc": False}
 
         def eager_step():
             for v in sd.values():
@@ -604,6 +626,7 @@ def leg_train_step(dev, peaks, batches=(8, 64), anchors=True, reps=3):
             sigma = (rnd * 1.2 - 1.2).exp()
             weight = (sigma ** 2 + 1) / sigma ** 2
             n = torch.randn_like(y) * sigma
+            tok = orc.process_radar_cond(sd, cube_e) if mode["enc"] else tok_const
             D = orc.edm_precond(sd, y + n, sigma, tok)
             loss = (weight * (D.float() - y) ** 2).mean()
             loss.backward()
@@ -626,7 +649,19 @@ def leg_train_step(dev, peaks, batches=(8, 64), anchors=True, reps=3):
             ms16 = cuda_time(eager_bf16, 2, warm=1)
         finally:
             orc._heads_attention = saved
+        # with the encoder trained jointly
+        for v in sd.values():
+            v.requires_grad_(True)
+        mode["enc"] = True
+        ms32e = cuda_time(eager_step, 2, warm=1)
+        orc._heads_attention = sdpa_heads
+        try:
+            ms16e = cuda_time(eager_bf16, 2, warm=1)
+        finally:
+            orc._heads_attention = saved
         out["torch_eager_anchor"] = {"batch": B, "fp32_ms_per_step": ms32, "bf16_autocast_sdpa_ms_per_step": ms16,
+                                     "with_encoder_fp32_ms_per_step": ms32e,
+                                     "with_encoder_bf16_autocast_sdpa_ms_per_step": ms16e,
                                      "note": "oracle port of the reference modules under torch autograd (no activation "
                                              "checkpointing), same GPU; reported baselines, not on the product path"}
         del sd

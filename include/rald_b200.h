@@ -82,6 +82,13 @@ int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw,
 int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_t ldw, int w_col_shift, float* out,
                                int64_t ldo, int M, int N, int K, void* stream);
 
+/* n_taps (<= 9) shifted products of rald_gemm_bf16_accum_shift in ONE launch: out[m][t * w_rows + n] += sum_k A[m][k] *
+ * W[n][k + tap_shifts_host[t]] with W of w_rows rows (a multiple of 32) — all (kd, kh) taps of a convolution's weight
+ * gradient; the CTAs that work on different taps of the same K range run concurrently and share A and W in L2, so HBM
+ * sees the operands about once instead of n_taps times. tap_shifts_host: HOST array of n_taps multiples of 8. */
+int rald_gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
+                              const int* tap_shifts_host, float* out, int64_t ldo, int M, int K, void* stream);
+
 /* rald_gemm_bf16 with out_mode 0 whose output columns with (col % f16_period) >= f16_start are written as IEEE fp16
  * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,

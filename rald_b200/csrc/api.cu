@@ -27,6 +27,12 @@ int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_
   return rald::gemm_bf16_accum_splitk(A, lda, W, ldw, w_col_shift, out, ldo, M, N, K, static_cast<cudaStream_t>(stream));
 }
 
+int rald_gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
+                              const int* tap_shifts_host, float* out, int64_t ldo, int M, int K, void* stream) {
+  return rald::gemm_bf16_accum_taps(A, lda, W, ldw, w_rows, n_taps, tap_shifts_host, out, ldo, M, K,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 int rald_gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                            const float* bias, int M, int N, int K, int f16_start, int f16_period, void* stream) {
   return rald::gemm_bf16_f16cols(A, lda, W, ldw, out, ldo, bias, M, N, K, f16_start, f16_period,

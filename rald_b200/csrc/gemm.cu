@@ -81,6 +81,9 @@ struct GemmParams {
   int w_k_off;                // added to the K coordinate of every W tile (A unaffected): W is read `w_k_off` columns to
                               // the right of A (negative: left; columns outside [0, K) read zeros) — a tap of the
                               // convolution weight gradient on the flattened padded voxel grid (enc_bwd.cu)
+  int tap_n;                  // > 0: the N extent is n_taps blocks of tap_n columns that all read the SAME tap_n rows of W, block
+  int tap_shift[9];           // t with column shift tap_shift[t] instead of w_k_off (all taps of a convolution weight gradient
+                              // in ONE launch: the CTAs working on different taps of the same K range share A and W in L2)
   int k_splits;               // > 1 (fp32 reduce-add epilogue, no bias): every output tile is computed by k_splits work items,
   int kb_per_split;           // each over kb_per_split k-blocks, all adding into `out` — the weight-gradient GEMMs of the
                               // training step (few output tiles, K = rows of the batch). Summation order across the splits
@@ -219,7 +222,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else tma_load_2d(dst, &tmB, bar, x, y);
     };
     if (p.b_mode == 0) {
-      ld(sb, kb * GEMM_BK + p.w_k_off, n_blk * BN + (int)cta_rank * (BN / CG));
+      int row = n_blk * BN + (int)cta_rank * (BN / CG), shift = p.w_k_off;
+      if (p.tap_n > 0) {
+        const int tap = row / p.tap_n;
+        shift = p.tap_shift[tap];
+        row -= tap * p.tap_n;
+      }
+      ld(sb, kb * GEMM_BK + shift, row);
     } else {
       const int f = p.grp_frame0 + (m_blk * TILE_M) / p.grp_rows;
       if (p.b_mode == 1) {
@@ -612,6 +621,8 @@ struct GemmOpts {
   int ab_f16 = 0;
   int split_k = 0;      // allow K splits (fp32 accumulate-into-out GEMMs without bias: weight gradients)
   int w_k_off = 0;      // column shift of the W operand (GemmParams::w_k_off)
+  int tap_n = 0, n_taps = 0;   // N = n_taps * tap_n, W has tap_n rows, tap t is shifted by tap_shift[t]
+  int tap_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -638,6 +649,17 @@ int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ld
   o.split_k = 1;
   o.w_k_off = w_k_off;
   return gemm_impl(A, lda, W, ldw, out, ldo, nullptr, out, ldo, M, N, K, 1, 0, o, stream);
+}
+
+int gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
+                         const int* tap_shifts, float* out, int64_t ldo, int M, int K, cudaStream_t stream) {
+  RALD_REQUIRE(n_taps >= 1 && n_taps <= 9 && tap_shifts != nullptr, "gemm taps: 1..9 taps");
+  GemmOpts o;
+  o.split_k = 1;
+  o.tap_n = w_rows;
+  o.n_taps = n_taps;
+  for (int t = 0; t < n_taps; ++t) o.tap_shift[t] = tap_shifts[t];
+  return gemm_impl(A, lda, W, ldw, out, ldo, nullptr, out, ldo, M, n_taps * w_rows, K, 1, 0, o, stream);
 }
 
 int gemm_bf16_f16cols(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -706,6 +728,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(o.f16_period == 0 || N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
   RALD_REQUIRE(o.w_k_off % 8 == 0, "gemm: W column shift %d must be a multiple of 8 (TMA box origins are 16-byte aligned)",
                o.w_k_off);
+  RALD_REQUIRE(o.tap_n == 0 || (o.split_k && o.n_taps >= 1 && o.n_taps <= 9 && N == o.n_taps * o.tap_n && o.tap_n % 32 == 0),
+               "gemm: bad tap layout (%d taps of %d columns, N=%d)", o.n_taps, o.tap_n, N);
+  for (int t = 0; t < o.n_taps; ++t)
+    RALD_REQUIRE(o.tap_shift[t] % 8 == 0, "gemm: tap shift %d must be a multiple of 8", o.tap_shift[t]);
   RALD_REQUIRE(!o.w_split || K % GEMM_BK == 0, "gemm: split weights need K=%d to be a multiple of %d", K, GEMM_BK);
   const int k_total = o.w_split ? 2 * K : K;   // k extent the main loop walks
 
@@ -732,7 +758,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   if (o.split_k) {
     RALD_REQUIRE(out_mode == 1 && bias == nullptr && resid == out && ldr == ldo && o.resid_mod == 0 && o.b_mode == 0 &&
                  !o.w_split, "gemm: K splits need the fp32 accumulate-into-out form without bias");
-    if (bn_hint == 0) bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));   // widest tile: least re-reads
+    const int nn = o.tap_n > 0 ? o.tap_n : N;       // a tile must not straddle two taps
+    if (bn_hint == 0) bn = nn % 256 == 0 ? 256 : (nn % 128 == 0 ? 128 : (nn % 64 == 0 ? 64 : 32));   // widest tile: least re-reads
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const long tiles = (long)m_blks * ((N + bn - 1) / bn);
     int want = (int)(sms / (tiles > 0 ? tiles : 1));
@@ -784,6 +811,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.grp_total = o.grp_total;
   p.ab_f16 = o.ab_f16;
   p.w_k_off = o.w_k_off;
+  p.tap_n = o.tap_n;
+  for (int t = 0; t < 9; ++t) p.tap_shift[t] = o.tap_shift[t];
   p.k_splits = k_splits;
   p.kb_per_split = kb_per_split;
   p.w_static = k_splits > 1 ? 0 : (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
@@ -797,7 +826,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(K / 64) * N, (uint64_t)o.grp_total * 64, (uint64_t)ldw,
                                (uint32_t)(pair ? bn / 2 : bn)));
   } else {
-    RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)k_total, (uint64_t)ldw, (uint32_t)(pair ? bn / 2 : bn)));
+    RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(o.tap_n > 0 ? o.tap_n : N), (uint64_t)k_total, (uint64_t)ldw,
+                               (uint32_t)(pair ? bn / 2 : bn)));
   }
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1, 32u));

@@ -8,11 +8,11 @@ One ``torch.autograd.Function`` around ``Encoder.forward`` (model/models_radar_e
   inputs, GroupNorm statistics, the bf16 operands of every convolution, the attention blocks' q | k | v);
 * backward, op by op in reverse:
     3x3x3 convolution  dgrad = ``rald_conv3d_cl`` on spatially flipped, in/out-transposed weights (stride 2: on the
-                       output gradient zero-stuffed onto the input grid, ``rald_enc_stuff``); wgrad = 9 split-K GEMMs
-                       ``dW[kd, kh, :] = dY^T [X_kw0 | X_kw1 | X_kw2]`` over all voxels of the batch: dY and the three
+                       output gradient zero-stuffed onto the input grid, ``rald_enc_stuff``); wgrad = ONE split-K GEMM
+                       launch of nine shifted products ``dW[kd, kh, :] = dY^T [X_kw0 | X_kw1 | X_kw2]`` over all voxels: dY and the three
                        kw-shifted copies of X are written once, transposed, onto the zero-padded voxel grid
                        (``rald_enc_pad_transpose``) where a (kd, kh) tap is a constant, 16-byte aligned index offset
-                       (``rald_gemm_bf16_accum_shift``); bias gradient by column sums;
+                       (``rald_gemm_bf16_accum_taps``); bias gradient by column sums;
     GroupNorm(+swish)  ``rald_gn_bwd`` (two passes; adds the identity-shortcut gradient);
     1x1x1 convolutions GEMMs (dgrad against the transposed weight, wgrad over K = voxels with transposed operands);
     AttnBlock          ``rald_enc_attn_bwd`` between the GEMMs of its 1x1 convolutions.
@@ -22,6 +22,7 @@ Host-side sequencing only; no torch fallback for any convolution, normalisation,
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -234,15 +235,13 @@ class EncoderTrainRuntime(_lib.RuntimeNotCopied):
                   1, cv_cout, 0, dyT.data_ptr(), Lp, _s())
         _lib.call("rald_enc_pad_transpose", x_in.data_ptr(), 1 if x_in.dtype == F32 else 0, B, D, H, W, cin, 1, Wp, 3,
                   cin_rows, o, xT.data_ptr(), Lp, _s())
-        dW = torch.zeros(9, cv_cout, 3 * cin_rows, device=self.dev, dtype=F32)
+        # all nine (kd, kh) taps in one launch: out[cout][(kd*3+kh) * 3*cin_rows + kw*cin_rows + ci]
+        dW = torch.zeros(cv_cout, 9 * 3 * cin_rows, device=self.dev, dtype=F32)
         S1, S2 = (H + 2) * Wp, Wp
-        for kd in range(3):
-            for kh in range(3):
-                off = (kd - o) * S1 + (kh - o) * S2
-                _lib.call("rald_gemm_bf16_accum_shift", dyT.data_ptr(), Lp, xT.data_ptr(), Lp, off,
-                          dW[kd * 3 + kh].data_ptr(), 3 * cin_rows, cv_cout, 3 * cin_rows, Lp, _s())
-        # [kd*3+kh][cout][kw][cin_rows] -> [cout][cin][kd][kh][kw]
-        gw = dW.reshape(3, 3, cv_cout, 3, cin_rows)[..., :cin].permute(2, 4, 0, 1, 3).contiguous()
+        shifts = (ctypes.c_int * 9)(*[(kd - o) * S1 + (kh - o) * S2 for kd in range(3) for kh in range(3)])
+        _lib.call("rald_gemm_bf16_accum_taps", dyT.data_ptr(), Lp, xT.data_ptr(), Lp, 3 * cin_rows, 9,
+                  ctypes.addressof(shifts), dW.data_ptr(), 9 * 3 * cin_rows, cv_cout, Lp, _s())
+        gw = dW.reshape(cv_cout, 3, 3, 3, cin_rows)[..., :cin].permute(0, 4, 1, 2, 3).contiguous()
         gb = self._colsum(dy.reshape(-1, cv_cout))
         return gw, gb
 
