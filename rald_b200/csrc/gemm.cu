@@ -166,7 +166,9 @@ __device__ __forceinline__ void epilogue_direct(uint32_t (&v)[32], const GemmPar
 
 // OUT_MODE: 0 = bf16 [M,N]; 1 = fp32 [M,N]; 2 = GEGLU -> bf16 [M,N/2]; 3 = softmax over every group of 64 columns
 // (scores already in log2 units) -> fp16 probabilities [M,N] (TMA-store epilogue only)
-template <int BN, int OUT_MODE, int EPI, int CG, int G>
+// SPLITK: the weight-gradient form (K splits, W column shifts / taps). A separate instantiation so that the forward
+// kernels keep their exact instruction stream (no runtime division by k_splits, no shift logic in the producer).
+template <int BN, int OUT_MODE, int EPI, int CG, int G, bool SPLITK = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
@@ -201,13 +203,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blks * p.num_n_blks * p.k_splits;
+  const int num_tiles = p.num_m_blks * p.num_n_blks * (SPLITK ? p.k_splits : 1);
   const int num_kb_all = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_kb = p.k_splits > 1 ? p.kb_per_split : num_kb_all;   // k-blocks per work item
-  // work item -> (row block, column block, first k-block); k_splits == 1: a work item is an output tile
+  const int num_kb = (SPLITK && p.k_splits > 1) ? p.kb_per_split : num_kb_all;   // k-blocks per work item
+  // work item -> (row block, column block, first k-block); without K splits a work item is an output tile
   auto decode = [&](int tile, int& m_blk, int& n_blk, int& kb0) {
-    const int t2 = tile / p.k_splits;
-    kb0 = (tile - t2 * p.k_splits) * num_kb;
+    int t2 = tile;
+    kb0 = 0;
+    if (SPLITK) {
+      t2 = tile / p.k_splits;
+      kb0 = (tile - t2 * p.k_splits) * num_kb;
+    }
     m_blk = t2 / p.num_n_blks;
     n_blk = t2 - m_blk * p.num_n_blks;
   };
@@ -222,11 +228,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else tma_load_2d(dst, &tmB, bar, x, y);
     };
     if (p.b_mode == 0) {
-      int row = n_blk * BN + (int)cta_rank * (BN / CG), shift = p.w_k_off;
-      if (p.tap_n > 0) {
-        const int tap = row / p.tap_n;
-        shift = p.tap_shift[tap];
-        row -= tap * p.tap_n;
+      int row = n_blk * BN + (int)cta_rank * (BN / CG), shift = 0;
+      if (SPLITK) {
+        shift = p.w_k_off;
+        if (p.tap_n > 0) {
+          const int tap = row / p.tap_n;
+          shift = p.tap_shift[tap];
+          row -= tap * p.tap_n;
+        }
       }
       ld(sb, kb * GEMM_BK + shift, row);
     } else {
@@ -558,18 +567,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int OUT_MODE, int EPI, int CG, int G>
+template <int BN, int OUT_MODE, int EPI, int CG, int G, bool SPLITK = false>
 static int launch_gemm_g(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
                          int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static_assert(Cfg::STAGES >= 3, "ring too shallow");
-  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, G>;
+  auto kern = gemm_bf16_kernel<BN, OUT_MODE, EPI, CG, G, SPLITK>;
   static bool configured = false;
   if (!configured) {
     RALD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int num_tiles = p.num_m_blks * p.num_n_blks * p.k_splits;       // work items: tiles of (128 * CG) x BN (x K splits)
+  const int num_tiles = p.num_m_blks * p.num_n_blks * (SPLITK ? p.k_splits : 1);   // work items: tiles (x K splits)
   const int max_units = max_ctas / CG;
   const int units = num_tiles < max_units ? num_tiles : max_units;
   ProfScope prof(FAM_GEMM, stream, 2.0 * p.M * p.N * p.K);
@@ -604,6 +613,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        : (Cfg::STAGES >= 8 && Cfg::STAGES % 4 == 0) ? 4
                        : (Cfg::STAGES >= 4 && Cfg::STAGES % 2 == 0) ? 2 : 1;
   const int num_kb = p.k_splits > 1 ? p.kb_per_split : (p.K + GEMM_BK - 1) / GEMM_BK;
+  if constexpr (OUT_MODE == 1 && EPI == EPI_TMA_REDUCE && CG == 1) {
+    // the weight-gradient form is only reachable through the fp32 accumulate-into-out GEMMs
+    if (p.k_splits > 1 || p.tap_n > 0 || p.w_k_off != 0) {
+      if (GMAX > 1 && gemm_env().group && num_kb % GMAX == 0)
+        return launch_gemm_g<BN, OUT_MODE, EPI, CG, GMAX, true>(tmA, tmB, tmO, p, max_ctas, stream);
+      return launch_gemm_g<BN, OUT_MODE, EPI, CG, 1, true>(tmA, tmB, tmO, p, max_ctas, stream);
+    }
+  }
   if (GMAX > 1 && gemm_env().group && num_kb % GMAX == 0)
     return launch_gemm_g<BN, OUT_MODE, EPI, CG, GMAX>(tmA, tmB, tmO, p, max_ctas, stream);
   return launch_gemm_g<BN, OUT_MODE, EPI, CG, 1>(tmA, tmB, tmO, p, max_ctas, stream);
