@@ -584,9 +584,10 @@ int rald_gn_bwd(const float* x, const float* dy, const double* stats, const floa
  * zero-padded grid [B][dil*D+2][dil*H+2][Wp] (Wp % 8 == 0, >= dil*W+2). out_t must be zero-initialised, ld >= grid + 8.
  * dil = 2 places a stride-2 convolution's output gradient on its input grid; copies = 3 writes the three kw-shifted
  * copies of a convolution input (TMA box origins must be 16-byte aligned: only the kd / kh part of a tap offset can be
- * an operand shift of rald_gemm_bf16_accum_shift). */
+ * an operand shift of rald_gemm_bf16_accum_shift). colsum (optional, f64 [C], f32 input only) receives the column sums of
+ * the input over all voxels: the convolution's bias gradient from the pass that already reads dY. */
 int rald_enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, void* stream);
+                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, double* colsum, void* stream);
 
 /* out bf16 [B, 2D, 2H, 2W, C] (zero-initialised by the caller) with out[2d+1, 2h+1, 2w+1] = in[d, h, w]: the operand of
  * the stride-2 convolution's dgrad (Downsample :34-41) as a stride-1 convolution with flipped weights. */

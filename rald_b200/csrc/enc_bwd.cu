@@ -201,9 +201,12 @@ int gn_bwd(const float* x, const float* dy, const double* stats, const float* ga
 template <bool IN_F32>
 __global__ void __launch_bounds__(256)
 enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, int H, int W, int C, int dil, int Wp,
-                         int copies, int copy_rows, int pos_bias, uint16_t* __restrict__ out_t, int64_t ld) {
+                         int copies, int copy_rows, int pos_bias, uint16_t* __restrict__ out_t, int64_t ld,
+                         double* __restrict__ colsum) {
   __shared__ uint16_t tile[64][66];
   __shared__ int64_t s_p[64];
+  __shared__ float s_cs[4][64];
+  float cs = 0.f;
   const int64_t v0 = (int64_t)blockIdx.y * 64;
   const int c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -228,7 +231,9 @@ enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, 
     uint16_t val = 0;
     if (v < total_vox && c < C) {
       if (IN_F32) {
-        __nv_bfloat16 hv = __float2bfloat16_rn(reinterpret_cast<const float*>(in)[v * C + c]);
+        const float f = reinterpret_cast<const float*>(in)[v * C + c];
+        cs += f;
+        __nv_bfloat16 hv = __float2bfloat16_rn(f);
         val = *reinterpret_cast<uint16_t*>(&hv);
       } else {
         val = reinterpret_cast<const uint16_t*>(in)[v * C + c];
@@ -236,7 +241,12 @@ enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, 
     }
     tile[i][tx] = val;
   }
+  if (IN_F32 && colsum != nullptr) s_cs[ty][tx] = cs;
   __syncthreads();
+  // bias gradient: column sums of the fp32 input, one fp64 atomic per (CTA, channel) (order-dependent at 1e-16 relative)
+  if (IN_F32 && colsum != nullptr && threadIdx.x < 64 && c0 + threadIdx.x < C)
+    atomicAdd(&colsum[c0 + threadIdx.x], (double)((s_cs[0][threadIdx.x] + s_cs[1][threadIdx.x]) +
+                                                  (s_cs[2][threadIdx.x] + s_cs[3][threadIdx.x])));
   // store: consecutive threads walk the voxels of one channel row (contiguous runs of W on the padded grid)
 #pragma unroll 4
   for (int i = ty; i < 64; i += 4) {
@@ -250,7 +260,9 @@ enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, 
 }
 
 int enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                      int copy_rows, int pos_bias, void* out_t, int64_t ld, cudaStream_t stream) {
+                      int copy_rows, int pos_bias, void* out_t, int64_t ld, double* colsum, cudaStream_t stream) {
+  RALD_REQUIRE(colsum == nullptr || in_f32, "enc_pad_transpose: column sums are taken from an fp32 input");
+  if (colsum != nullptr) RALD_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * C, stream));
   RALD_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (dil == 1 || dil == 2), "enc_pad_transpose: bad geometry");
   RALD_REQUIRE(Wp >= dil * W + 2 && Wp % 8 == 0, "enc_pad_transpose: row pitch %d must be a multiple of 8 >= %d", Wp,
                dil * W + 2);
@@ -271,9 +283,9 @@ int enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, in
     const char* src = reinterpret_cast<const char*>(in) + f0 * vox_per_frame * C * esz;
     uint16_t* dst = reinterpret_cast<uint16_t*>(out_t) + f0 * padded_frame;
     if (in_f32) enc_pad_transpose_kernel<true><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows,
-                                                                       pos_bias, dst, ld);
+                                                                       pos_bias, dst, ld, colsum);
     else enc_pad_transpose_kernel<false><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias,
-                                                                 dst, ld);
+                                                                 dst, ld, nullptr);
     RALD_LAUNCHED();
   }
   return 0;
@@ -326,6 +338,7 @@ enc_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
   const float* dob = dO + (int64_t)b * n * C;
   float* outb = dqkv + (int64_t)b * n * 3 * C;
   const int quads = C >> 2;
+  // (every CTA of a frame recomputes the 64 x 64 probabilities: 2 MFLOP; the CTAs split the channels of the last phase)
   // scores and dP: thread (i, jq) handles 16 columns of row i
   {
     const int i = threadIdx.x >> 2, jq = threadIdx.x & 3;
@@ -390,9 +403,16 @@ enc_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     }
   }
   __syncthreads();
-  // dq[i] = sum_j dS[i][j] k[j];  dk[j] = sum_i dS[i][j] q[i];  dv[j] = sum_i P[i][j] dO[i]   (thread <-> channel)
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    for (int i = 0; i < n; ++i) {
+  // dq[i] = sum_j dS[i][j] k[j];  dk[j] = sum_i dS[i][j] q[i];  dv[j] = sum_i P[i][j] dO[i]
+  // thread <-> (channel of this CTA's slice, quarter of the rows)
+  const int cpb = (C + gridDim.y - 1) / gridDim.y;           // channels per CTA
+  const int rows_q = (n + 3) / 4;
+  for (int cc = threadIdx.x & 63; cc < cpb; cc += 64) {
+    const int c = blockIdx.y * cpb + cc;
+    if (c >= C) break;
+    const int i0 = (threadIdx.x >> 6) * rows_q;
+    const int i1 = (i0 + rows_q) < n ? (i0 + rows_q) : n;
+    for (int i = i0; i < i1; ++i) {
       float aq = 0.f, ak = 0.f, av = 0.f;
       for (int j = 0; j < n; ++j) {
         aq = fmaf(s_ds[i * 65 + j], base[(int64_t)j * 3 * C + C + c], aq);
@@ -408,7 +428,7 @@ enc_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
 
 int enc_attn_bwd(const float* qkv, const float* dO, float* dqkv, int B, int n, int C, cudaStream_t stream) {
   RALD_REQUIRE(n > 0 && n <= 64 && C % 4 == 0 && C <= 256, "enc_attn_bwd: n=%d C=%d unsupported", n, C);
-  enc_attn_bwd_kernel<<<B, 256, 0, stream>>>(qkv, dO, dqkv, n, C, 1.0f / sqrtf((float)C));
+  enc_attn_bwd_kernel<<<dim3(B, 4), 256, 0, stream>>>(qkv, dO, dqkv, n, C, 1.0f / sqrtf((float)C));
   RALD_LAUNCHED();
   return 0;
 }
@@ -424,8 +444,8 @@ int rald_gn_bwd(const float* x, const float* dy, const double* stats, const floa
 }
 
 int rald_enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, void* stream) {
-  return rald::enc_pad_transpose(in, in_f32, B, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias, out_t_bf16, ld,
+                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, double* colsum, void* stream) {
+  return rald::enc_pad_transpose(in, in_f32, B, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias, out_t_bf16, ld, colsum,
                                  static_cast<cudaStream_t>(stream));
 }
 

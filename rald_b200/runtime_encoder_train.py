@@ -231,10 +231,11 @@ class EncoderTrainRuntime(_lib.RuntimeNotCopied):
         o = 1 if stride == 1 else 0
         dyT = torch.zeros(cv_cout, Lp, device=self.dev, dtype=BF)
         xT = torch.zeros(3 * cin_rows, Lp, device=self.dev, dtype=BF)     # [kw][cin_rows]: X pre-shifted by kw - o
+        bsum = torch.empty(cv_cout, device=self.dev, dtype=torch.float64)      # bias gradient, from the same pass over dY
         _lib.call("rald_enc_pad_transpose", dy.data_ptr(), 1, B, D // stride, H // stride, W // stride, cv_cout, stride, Wp,
-                  1, cv_cout, 0, dyT.data_ptr(), Lp, _s())
+                  1, cv_cout, 0, dyT.data_ptr(), Lp, bsum.data_ptr(), _s())
         _lib.call("rald_enc_pad_transpose", x_in.data_ptr(), 1 if x_in.dtype == F32 else 0, B, D, H, W, cin, 1, Wp, 3,
-                  cin_rows, o, xT.data_ptr(), Lp, _s())
+                  cin_rows, o, xT.data_ptr(), Lp, 0, _s())
         # all nine (kd, kh) taps in one launch: out[cout][(kd*3+kh) * 3*cin_rows + kw*cin_rows + ci]
         dW = torch.zeros(cv_cout, 9 * 3 * cin_rows, device=self.dev, dtype=F32)
         S1, S2 = (H + 2) * Wp, Wp
@@ -242,8 +243,7 @@ class EncoderTrainRuntime(_lib.RuntimeNotCopied):
         _lib.call("rald_gemm_bf16_accum_taps", dyT.data_ptr(), Lp, xT.data_ptr(), Lp, 3 * cin_rows, 9,
                   ctypes.addressof(shifts), dW.data_ptr(), 9 * 3 * cin_rows, cv_cout, Lp, _s())
         gw = dW.reshape(cv_cout, 3, 3, 3, cin_rows)[..., :cin].permute(0, 4, 1, 2, 3).contiguous()
-        gb = self._colsum(dy.reshape(-1, cv_cout))
-        return gw, gb
+        return gw, bsum.float()
 
     def _lin_fwd(self, a16: torch.Tensor, lin: _Lin, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
         """a16 bf16 [R, cin] -> fp32 [R, cout] = a W^T + b (+ resid)."""
