@@ -82,10 +82,11 @@ int rald_gemm_bf16_accum(const void* A, int64_t lda, const void* W, int64_t ldw,
 int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_t ldw, int w_col_shift, float* out,
                                int64_t ldo, int M, int N, int K, void* stream);
 
-/* n_taps (<= 9) shifted products of rald_gemm_bf16_accum_shift in ONE launch: out[m][t * w_rows + n] += sum_k A[m][k] *
+/* n_taps (<= 16) shifted products of rald_gemm_bf16_accum_shift in ONE launch: out[m][t * w_rows + n] += sum_k A[m][k] *
  * W[n][k + tap_shifts_host[t]] with W of w_rows rows (a multiple of 32) — all (kd, kh) taps of a convolution's weight
  * gradient; the CTAs that work on different taps of the same K range run concurrently and share A and W in L2, so HBM
- * sees the operands about once instead of n_taps times. tap_shifts_host: HOST array of n_taps multiples of 8. */
+ * sees the operands about once instead of n_taps times; with w_rows of 64 or 128 several taps share one 256-wide tile
+ * (one A tile, one MMA). tap_shifts_host: HOST array of n_taps multiples of 8. */
 int rald_gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
                               const int* tap_shifts_host, float* out, int64_t ldo, int M, int K, void* stream);
 

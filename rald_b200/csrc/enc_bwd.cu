@@ -5,11 +5,12 @@
 // The matrix work of the encoder's backward pass runs on the existing tensor-core kernels:
 //   conv dgrad  = the forward implicit-GEMM convolution (conv3d.cu) on spatially flipped, in/out-transposed weights
 //                 (stride 2: over the output gradient zero-stuffed onto the input grid, enc_stuff_kernel);
-//   conv wgrad  = for each of the 9 (kd, kh) tap pairs ONE split-K GEMM  dW = dY^T [X_kw0 | X_kw1 | X_kw2]  over K = all
-//                 voxels of the batch: dY is written once and X three times (pre-shifted by kw), transposed, onto the
-//                 zero-PADDED voxel grid (enc_pad_transpose_kernel), where a tap is a constant offset of the flattened
-//                 index — the (kd, kh) part, a multiple of 8 columns, is passed to the GEMM as a column offset of its W
-//                 operand's TMA coordinates (gemm.cu: w_k_off; out-of-range coordinates read zeros);
+//   conv wgrad  = ONE split-K GEMM launch over K = all voxels of the batch: A = the three kw-shifted copies of X, W = dY,
+//                 both written once, transposed, onto the zero-PADDED voxel grid (enc_pad_transpose_kernel), where a tap
+//                 is a constant offset of the flattened index. The nine (kd, kh) taps are nine column blocks of the
+//                 output, each reading dY^T at its own column offset (multiples of 8: TMA box origins must be 16-byte
+//                 aligned, hence the pre-shifted kw copies); four taps (Cout = 64) share one 256-wide tile and one A tile
+//                 (gemm.cu: tap_n / tap_shift; out-of-range coordinates read zeros);
 //   1x1 convs   = GEMMs as in the denoiser (train_bwd.cu helpers).
 // This file holds the rest: GroupNorm(+swish) backward in two passes, the padded / dilated transpose, the zero-stuffing
 // and the backward of the 64-voxel single-head attention.

@@ -82,8 +82,9 @@ struct GemmParams {
                               // the right of A (negative: left; columns outside [0, K) read zeros) — a tap of the
                               // convolution weight gradient on the flattened padded voxel grid (enc_bwd.cu)
   int tap_n;                  // > 0: the N extent is n_taps blocks of tap_n columns that all read the SAME tap_n rows of W, block
-  int tap_shift[9];           // t with column shift tap_shift[t] instead of w_k_off (all taps of a convolution weight gradient
-                              // in ONE launch: the CTAs working on different taps of the same K range share A and W in L2)
+  int tap_shift[16];          // t with column shift tap_shift[t] instead of w_k_off (all taps of a convolution weight gradient
+                              // in ONE launch). tap_n < BN: a W tile is BN / tap_n boxes of tap_n rows, one per tap, each with
+                              // its own shift — several taps share one A tile and one wide MMA
   int k_splits;               // > 1 (fp32 reduce-add epilogue, no bias): every output tile is computed by k_splits work items,
   int kb_per_split;           // each over kb_per_split k-blocks, all adding into `out` — the weight-gradient GEMMs of the
                               // training step (few output tiles, K = rows of the batch). Summation order across the splits
@@ -231,6 +232,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int row = n_blk * BN + (int)cta_rank * (BN / CG), shift = 0;
       if (SPLITK) {
         shift = p.w_k_off;
+        if (p.tap_n > 0 && p.tap_n < BN) {
+          // several taps per tile: one box of tap_n rows (all rows of W) per tap, stacked in the B tile
+          const int tap0 = row / p.tap_n;
+          for (int i = 0; i < BN / p.tap_n; ++i)
+            ld(sb + (size_t)i * p.tap_n * 128, kb * GEMM_BK + p.tap_shift[tap0 + i], 0);
+          return;
+        }
         if (p.tap_n > 0) {
           const int tap = row / p.tap_n;
           shift = p.tap_shift[tap];
@@ -639,7 +647,7 @@ struct GemmOpts {
   int split_k = 0;      // allow K splits (fp32 accumulate-into-out GEMMs without bias: weight gradients)
   int w_k_off = 0;      // column shift of the W operand (GemmParams::w_k_off)
   int tap_n = 0, n_taps = 0;   // N = n_taps * tap_n, W has tap_n rows, tap t is shifted by tap_shift[t]
-  int tap_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int tap_shift[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, const float* bias,
@@ -670,7 +678,7 @@ int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ld
 
 int gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
                          const int* tap_shifts, float* out, int64_t ldo, int M, int K, cudaStream_t stream) {
-  RALD_REQUIRE(n_taps >= 1 && n_taps <= 9 && tap_shifts != nullptr, "gemm taps: 1..9 taps");
+  RALD_REQUIRE(n_taps >= 1 && n_taps <= 16 && tap_shifts != nullptr, "gemm taps: 1..16 taps");
   GemmOpts o;
   o.split_k = 1;
   o.tap_n = w_rows;
@@ -745,7 +753,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(o.f16_period == 0 || N % 64 == 0, "gemm: N=%d must be a multiple of 64 for mixed fp16 / bf16 output", N);
   RALD_REQUIRE(o.w_k_off % 8 == 0, "gemm: W column shift %d must be a multiple of 8 (TMA box origins are 16-byte aligned)",
                o.w_k_off);
-  RALD_REQUIRE(o.tap_n == 0 || (o.split_k && o.n_taps >= 1 && o.n_taps <= 9 && N == o.n_taps * o.tap_n && o.tap_n % 32 == 0),
+  RALD_REQUIRE(o.tap_n == 0 || (o.split_k && o.n_taps >= 1 && o.n_taps <= 16 && N == o.n_taps * o.tap_n && o.tap_n % 32 == 0),
                "gemm: bad tap layout (%d taps of %d columns, N=%d)", o.n_taps, o.tap_n, N);
   for (int t = 0; t < o.n_taps; ++t)
     RALD_REQUIRE(o.tap_shift[t] % 8 == 0, "gemm: tap shift %d must be a multiple of 8", o.tap_shift[t]);
@@ -775,8 +783,13 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   if (o.split_k) {
     RALD_REQUIRE(out_mode == 1 && bias == nullptr && resid == out && ldr == ldo && o.resid_mod == 0 && o.b_mode == 0 &&
                  !o.w_split, "gemm: K splits need the fp32 accumulate-into-out form without bias");
-    const int nn = o.tap_n > 0 ? o.tap_n : N;       // a tile must not straddle two taps
-    if (bn_hint == 0) bn = nn % 256 == 0 ? 256 : (nn % 128 == 0 ? 128 : (nn % 64 == 0 ? 64 : 32));   // widest tile: least re-reads
+    // widest tile (least re-reads); with taps a tile holds whole taps: tap_n % bn == 0 or bn % tap_n == 0 (tap_n >= 64)
+    if (bn_hint == 0) {
+      bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
+      if (o.tap_n > 0) {
+        while (bn > 32 && !((o.tap_n % bn == 0) || (bn % o.tap_n == 0 && o.tap_n % 64 == 0))) bn >>= 1;
+      }
+    }
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const long tiles = (long)m_blks * ((N + bn - 1) / bn);
     int want = (int)(sms / (tiles > 0 ? tiles : 1));
@@ -829,7 +842,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.ab_f16 = o.ab_f16;
   p.w_k_off = o.w_k_off;
   p.tap_n = o.tap_n;
-  for (int t = 0; t < 9; ++t) p.tap_shift[t] = o.tap_shift[t];
+  for (int t = 0; t < 16; ++t) p.tap_shift[t] = o.tap_shift[t];
   p.k_splits = k_splits;
   p.kb_per_split = kb_per_split;
   p.w_static = k_splits > 1 ? 0 : (gemm_env().wpre && g_w_static > 0 && !pair && pdl_enabled()) ? 1 : 0;
@@ -844,7 +857,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
                                (uint32_t)(pair ? bn / 2 : bn)));
   } else {
     RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(o.tap_n > 0 ? o.tap_n : N), (uint64_t)k_total, (uint64_t)ldw,
-                               (uint32_t)(pair ? bn / 2 : bn)));
+                               (uint32_t)(pair ? bn / 2 : ((o.tap_n > 0 && o.tap_n < bn) ? o.tap_n : bn))));
   }
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1, 32u));

@@ -9,10 +9,11 @@ One ``torch.autograd.Function`` around ``Encoder.forward`` (model/models_radar_e
 * backward, op by op in reverse:
     3x3x3 convolution  dgrad = ``rald_conv3d_cl`` on spatially flipped, in/out-transposed weights (stride 2: on the
                        output gradient zero-stuffed onto the input grid, ``rald_enc_stuff``); wgrad = ONE split-K GEMM
-                       launch of nine shifted products ``dW[kd, kh, :] = dY^T [X_kw0 | X_kw1 | X_kw2]`` over all voxels: dY and the three
-                       kw-shifted copies of X are written once, transposed, onto the zero-padded voxel grid
-                       (``rald_enc_pad_transpose``) where a (kd, kh) tap is a constant, 16-byte aligned index offset
-                       (``rald_gemm_bf16_accum_taps``); bias gradient by column sums;
+                       launch ``dW^T[kw, ci ; tap, co] = sum_P X_kw[ci][P] dY[co][P - off(tap)]`` over all voxels: the three
+                       kw-shifted copies of X and dY are written once, transposed, onto the zero-padded voxel grid
+                       (``rald_enc_pad_transpose``) where a (kd, kh) tap is a constant, 16-byte aligned index offset of
+                       the dY^T boxes (``rald_gemm_bf16_accum_taps``, four taps per 256-wide tile);
+                       bias gradient from the same pass over dY;
     GroupNorm(+swish)  ``rald_gn_bwd`` (two passes; adds the identity-shortcut gradient);
     1x1x1 convolutions GEMMs (dgrad against the transposed weight, wgrad over K = voxels with transposed operands);
     AttnBlock          ``rald_enc_attn_bwd`` between the GEMMs of its 1x1 convolutions.
@@ -228,21 +229,29 @@ class EncoderTrainRuntime(_lib.RuntimeNotCopied):
         padded = B * (D + 2) * (H + 2) * Wp
         Lp = -(-(padded + 8) // 16384) * 16384
         cin_rows = -(-cin // 32) * 32
+        co_rows = -(-cv_cout // 64) * 64                 # a tap = one box of co_rows rows of dY^T
         o = 1 if stride == 1 else 0
-        dyT = torch.zeros(cv_cout, Lp, device=self.dev, dtype=BF)
+        dyT = torch.zeros(co_rows, Lp, device=self.dev, dtype=BF)
         xT = torch.zeros(3 * cin_rows, Lp, device=self.dev, dtype=BF)     # [kw][cin_rows]: X pre-shifted by kw - o
         bsum = torch.empty(cv_cout, device=self.dev, dtype=torch.float64)      # bias gradient, from the same pass over dY
         _lib.call("rald_enc_pad_transpose", dy.data_ptr(), 1, B, D // stride, H // stride, W // stride, cv_cout, stride, Wp,
-                  1, cv_cout, 0, dyT.data_ptr(), Lp, bsum.data_ptr(), _s())
+                  1, co_rows, 0, dyT.data_ptr(), Lp, bsum.data_ptr(), _s())
         _lib.call("rald_enc_pad_transpose", x_in.data_ptr(), 1 if x_in.dtype == F32 else 0, B, D, H, W, cin, 1, Wp, 3,
                   cin_rows, o, xT.data_ptr(), Lp, 0, _s())
-        # all nine (kd, kh) taps in one launch: out[cout][(kd*3+kh) * 3*cin_rows + kw*cin_rows + ci]
-        dW = torch.zeros(cv_cout, 9 * 3 * cin_rows, device=self.dev, dtype=F32)
+        # dW^T in ONE launch: out[kw*cin_rows + ci][tap*co_rows + co] = sum_P X_kw[ci][P] dY[co][P - off(tap)], the nine
+        # (kd, kh) taps as shifted boxes of dY^T stacked four (co_rows = 64) / two (128) to a 256-wide tile; the tap count is
+        # padded to a multiple of that with dummy taps whose output is dropped
+        per_tile = max(1, 256 // co_rows)
+        n_taps = -(-9 // per_tile) * per_tile
         S1, S2 = (H + 2) * Wp, Wp
-        shifts = (ctypes.c_int * 9)(*[(kd - o) * S1 + (kh - o) * S2 for kd in range(3) for kh in range(3)])
-        _lib.call("rald_gemm_bf16_accum_taps", dyT.data_ptr(), Lp, xT.data_ptr(), Lp, 3 * cin_rows, 9,
-                  ctypes.addressof(shifts), dW.data_ptr(), 9 * 3 * cin_rows, cv_cout, Lp, _s())
-        gw = dW.reshape(cv_cout, 3, 3, 3, cin_rows)[..., :cin].permute(0, 4, 1, 2, 3).contiguous()
+        offs = [-((kd - o) * S1 + (kh - o) * S2) for kd in range(3) for kh in range(3)] + [0] * (n_taps - 9)
+        shifts = (ctypes.c_int * n_taps)(*offs)
+        dWt = torch.zeros(3 * cin_rows, n_taps * co_rows, device=self.dev, dtype=F32)
+        _lib.call("rald_gemm_bf16_accum_taps", xT.data_ptr(), Lp, dyT.data_ptr(), Lp, co_rows, n_taps,
+                  ctypes.addressof(shifts), dWt.data_ptr(), n_taps * co_rows, 3 * cin_rows, Lp, _s())
+        # [kw][cin_rows][tap][co_rows] -> [cout][cin][kd][kh][kw]
+        gw = dWt.reshape(3, cin_rows, n_taps, co_rows)[:, :cin, :9, :cv_cout].reshape(3, cin, 3, 3, cv_cout) \
+            .permute(4, 1, 2, 3, 0).contiguous()
         return gw, bsum.float()
 
     def _lin_fwd(self, a16: torch.Tensor, lin: _Lin, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
