@@ -624,8 +624,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if constexpr (OUT_MODE == 1 && EPI == EPI_TMA_REDUCE && CG == 1) {
     // the weight-gradient form is only reachable through the fp32 accumulate-into-out GEMMs
     if (p.k_splits > 1 || p.tap_n > 0 || p.w_k_off != 0) {
-      if (GMAX > 1 && gemm_env().group && num_kb % GMAX == 0)
-        return launch_gemm_g<BN, OUT_MODE, EPI, CG, GMAX, true>(tmA, tmB, tmO, p, max_ctas, stream);
+      // one k-block per ring slot: these GEMMs stream hundreds of k-blocks per work item, and a slot that is refilled
+      // as soon as ONE k-block has been consumed keeps more loads in flight than grouped slots (measured, tools/
+      // gpu_time_wgrad.py: dW of FF2 70 -> 62 us, of the 512 x 512 projections 22.6 -> 19.2 us at K = 32 768)
       return launch_gemm_g<BN, OUT_MODE, EPI, CG, 1, true>(tmA, tmB, tmO, p, max_ctas, stream);
     }
   }
