@@ -330,3 +330,48 @@ def test_frozen_and_partially_frozen_encoder():
     EDMLoss()(net, y, cube, "radar").backward()
     assert all(p.grad is None for p in net.radar_enc.parameters())
     assert net.model.proj_in.weight.grad is not None and net.radar_token_project.weight.grad is not None
+
+
+def test_eight_channel_variant_against_oracle_autograd():
+    """kl_d512_m512_l8_edm (8 latent channels, 12 blocks): the channel padding of proj_in / proj_out in the training path;
+    gradients of a few tensors against fp32 autograd through the CPU oracle on the same inputs. Also checks that a second
+    backward pass ACCUMULATES into .grad (the reference's accum_iter > 1)."""
+    from helpers import cpu_state_dict
+    from oracle import rald_oracle as orc
+    net = build_denoiser(name="kl_d512_m512_l8_edm", device=DEV).train()
+    net.radar_enc.requires_grad_(False)
+    g = torch.Generator().manual_seed(12)
+    B = 2
+    cube = synth.radar_cube(B, seed=31)
+    y = torch.randn(B, 512, 8, generator=g) * 0.7
+    sigma = torch.tensor([0.4, 2.5]).view(B, 1, 1)
+    noise = torch.randn(B, 512, 8, generator=g)
+    weight = (sigma ** 2 + 1.0) / sigma ** 2
+
+    def run():
+        D = net((y + noise * sigma).to(DEV), sigma.to(DEV), cube.to(DEV), "radar")
+        loss = (weight.to(DEV) * (D - y.to(DEV)) ** 2).mean()
+        loss.backward()
+        return float(loss)
+    loss = run()
+    names = ["model.proj_in.weight", "model.proj_out.weight", "model.norm.weight", "model.map_layer0.weight",
+             "model.transformer_blocks.0.attn2.to_k.weight", "model.transformer_blocks.11.ff.net.0.proj.bias",
+             "model.transformer_blocks.6.norm2.linear.weight", "radar_a_emb.weight", "radar_token_project.weight"]
+    params = dict(net.named_parameters())
+    got = {n: params[n].grad.clone() for n in names}
+    run()                                                   # second pass: gradients add up
+    for n in names:
+        assert rel_l2(params[n].grad, 2 * got[n]) <= 1e-5, n
+    sd = cpu_state_dict(net)
+    for k, v in sd.items():
+        if not k.startswith("radar_enc."):
+            v.requires_grad_(True)
+    tok = orc.process_radar_cond(sd, cube)
+    D = orc.edm_precond(sd, y + noise * sigma, sigma, tok)
+    ref_loss = (weight * (D - y) ** 2).mean()
+    ref_loss.backward()
+    assert abs(loss - float(ref_loss)) <= 1e-2 * float(ref_loss)
+    for n in names:
+        e = rel_l2(got[n], sd[n].grad)
+        print(n, f"{e:.2e}")
+        assert e <= 2e-2, (n, e)
