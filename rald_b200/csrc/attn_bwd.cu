@@ -27,11 +27,13 @@
 //             S, dP again, dS (bf16 pair in TMEM), dQ += dS K_j (K_j as MN-major B operand).
 // S and dP are recomputed in every pass (9 tile products instead of the minimal 5): the alternative is a dQ
 // accumulated across CTAs with atomics or a TMA reduce-add, whose summation order would vary from run to run.
-// dS is handed to the tensor cores as a SPLIT pair dS = hi + lo of bf16 values (16 mantissa bits, two products per
-// accumulator): every row of dS sums to zero, so dQ_i = sum_j dS_ij K_j cancels whatever the keys have in common, and
-// independently rounded entries leave |mean key| x sum_j eps_ij behind (unit test: dQ / dK 3.0e-3 -> 2.4e-3 rel-L2).
-// TMEM columns: S [0,128) (P^T bf16 written back over its consumed columns [0,64)), dP [128,256) (dS_hi over [128,192)),
-// dS_lo [256,320), accumulators [384,448) and [448,512).
+// In MODE_DQ dS is handed to the tensor cores as a SPLIT pair dS = hi + lo of bf16 values (16 mantissa bits, two products
+// per accumulator): every row of dS sums to zero, so dQ_i = sum_j dS_ij K_j cancels whatever the keys have in common, and
+// independently rounded entries leave |mean key| x sum_j eps_ij behind (unit test: dQ 3.0e-3 -> 2.4e-3 rel-L2). dK has no
+// such cancellation (the columns of dS do not sum to zero) and takes the plain bf16 dS^T.
+// TMEM columns: S [0,128), dP [128,256), then MODE_DQ: dS_hi [256,320), dS_lo [320,384), dQ [384,448);
+// MODE_DKV: P^T [256,320), dS^T [320,384), dV [384,448), dK [448,512). Nothing is written over S / dP: the two compute
+// warps of a lane quarter work on different column halves at their own pace.
 #include "../../include/rald_b200.h"
 
 #include "host.cuh"
@@ -40,7 +42,9 @@
 
 namespace rald {
 
-constexpr int AB_THREADS = 192;              // warp 0: TMA, warp 1: MMA issue, warps 2..5: one TMEM lane quarter each
+constexpr int AB_THREADS = 320;              // warp 0: TMA, warp 1: MMA issue, warps 2..9: compute — two per TMEM lane
+                                             // quarter (a scheduler with ONE such warp cannot hide its ex2 / TMEM latencies),
+                                             // each taking half of the tile's columns
 constexpr int AB_TILE = 128 * 64 * 2;        // one [128 x 64] 16-bit tile, 128-byte swizzled rows
 constexpr int AB_MODE_DQ = 0, AB_MODE_DKV = 1;
 
@@ -97,7 +101,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       mbar_init(&x_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -116,7 +120,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const int frame = fh / p.heads, head = fh - frame * p.heads;
   const int nx = p.x_tiles;
   const int iters = MODE == AB_MODE_DQ ? 2 * nx : nx;   // MODE_DQ streams the keys twice (D pass, then dS / dQ pass)
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_P = 0, COL_DS = 128, COL_LO = 256, COL_A1 = 384, COL_A2 = 448;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_P = 256, COL_DS = MODE == AB_MODE_DKV ? 320 : 256, COL_LO = 320,
+                     COL_A1 = 384, COL_A2 = 448;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -168,10 +173,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         if (MODE == AB_MODE_DKV) {
           for (int k = 0; k < acc_k; ++k)   // dV += P^T dO_i
             mma_f16_ts(tmem_base + COL_A1, tmem_base + COL_P + 8 * k, x2_mn + 128 * k, p.idesc_acc, (s | k) != 0);
-          for (int k = 0; k < acc_k; ++k)   // dK += dS^T Q_i   (hi, then lo)
+          for (int k = 0; k < acc_k; ++k)   // dK += dS^T Q_i
             mma_f16_ts(tmem_base + COL_A2, tmem_base + COL_DS + 8 * k, x1_mn + 128 * k, p.idesc_acc, (s | k) != 0);
-          for (int k = 0; k < acc_k; ++k)
-            mma_f16_ts(tmem_base + COL_A2, tmem_base + COL_LO + 8 * k, x1_mn + 128 * k, p.idesc_acc, 1);
         } else {
           for (int k = 0; k < acc_k; ++k)   // dQ += dS K_j   (hi, then lo)
             mma_f16_ts(tmem_base + COL_A1, tmem_base + COL_DS + 8 * k, x1_mn + 128 * k, p.idesc_acc, (s | k) != 0);
@@ -183,14 +186,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       tc_commit(acc_done);
     }
   } else {
-    // ===================== P / dS computation + epilogue (warps 2..5) =====================
+    // ===================== P / dS computation + epilogue (warps 2..9) =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;               // column half of the tile this warp works on
     const int row = q * 32 + lane;                // tile row = TMEM lane
     const uint32_t t_mine = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int64_t stat_base = ((int64_t)frame * p.heads + head) * p.Sq;
     float lse_r = 0.f, ds_r = 0.f;
     if (MODE == AB_MODE_DQ) lse_r = p.lse2[stat_base + rt * 128 + row];
     const int ncols = MODE == AB_MODE_DQ ? p.x_rows : 128;
+    const int hc = ncols >> 1;                    // columns per warp (64, or 32 for a 64-token context in MODE_DQ)
+    const int cbeg = ch * hc;
     for (int it = 0; it < iters; ++it) {
       const int s = it >= nx ? it - nx : it;
       const float* lse_c = s_lse + (s & 1) * 128;
@@ -201,7 +207,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         tc_fence_after();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < ncols; c += 32) {
+        for (int c = cbeg; c < cbeg + hc; c += 32) {
           uint32_t sv[32], dv[32];
           tmem_ld32(t_mine + COL_S + c, sv);
           tmem_ld32(t_mine + COL_DP + c, dv);
@@ -218,19 +224,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        if (it == nx - 1) p.dsum[stat_base + rt * 128 + row] = ds_r;
+        if (it == nx - 1) {
+          // the two column halves of a row meet: D_i = half 0 + half 1 (fixed order), written once for MODE_DKV
+          s_lse[ch * 128 + row] = ds_r;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ds_r = s_lse[row] + s_lse[128 + row];
+          if (ch == 0) p.dsum[stat_base + rt * 128 + row] = ds_r;
+        }
         continue;
       }
       if (MODE == AB_MODE_DKV) {
         // statistics of the 128 queries of this tile = the COLUMNS of S^T: staged in shared memory, read as broadcasts
-        s_lse[(s & 1) * 128 + row] = p.lse2[stat_base + s * 128 + row];
-        s_ds[(s & 1) * 128 + row] = p.dsum[stat_base + s * 128 + row];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ch == 0) {
+          s_lse[(s & 1) * 128 + row] = p.lse2[stat_base + s * 128 + row];
+          s_ds[(s & 1) * 128 + row] = p.dsum[stat_base + s * 128 + row];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(s_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < ncols; c += 32) {
+      for (int c = cbeg; c < cbeg + hc; c += 32) {
         uint32_t sv[32], dv[32];
         tmem_ld32(t_mine + COL_S + c, sv);
         tmem_ld32(t_mine + COL_DP + c, dv);
@@ -251,43 +265,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           const float g1 = p1 * (__uint_as_float(dv[2 * j + 1]) - d1) * p.scale;
           pp[j] = pack_bf16x2(p0, p1);
           dd[j] = pack_bf16x2(g0, g1);
-          dl[j] = pack_bf16x2(g0 - __uint_as_float(dd[j] << 16), g1 - __uint_as_float(dd[j] & 0xffff0000u));
+          if (MODE == AB_MODE_DQ)
+            dl[j] = pack_bf16x2(g0 - __uint_as_float(dd[j] << 16), g1 - __uint_as_float(dd[j] & 0xffff0000u));
         }
-        // P^T and dS_hi go back over columns of S / dP that have been read ([c/2, c/2 + 16) lies below c + 32)
         if (MODE == AB_MODE_DKV) tmem_st16(t_mine + COL_P + (c >> 1), pp);
         tmem_st16(t_mine + COL_DS + (c >> 1), dd);
-        tmem_st16(t_mine + COL_LO + (c >> 1), dl);
+        if (MODE == AB_MODE_DQ) tmem_st16(t_mine + COL_LO + (c >> 1), dl);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- epilogue: accumulators -> bf16 rows of the gradient tensors ----
+    // ---- epilogue: accumulators -> bf16 rows of the gradient tensors (each warp: 32 of the 64 columns) ----
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int tile_row = rt * 128 + row;
     const bool valid = tile_row < p.r_frame_rows;
     const int64_t grow = (int64_t)frame * p.r_frame_rows + tile_row;
-    auto store64 = [&](uint32_t col, uint16_t* out, int64_t ld) {
+    auto store32 = [&](uint32_t col, uint16_t* out, int64_t ld) {
+      uint32_t v[32];
+      tmem_ld32(t_mine + col + 32 * ch, v);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(out + grow * ld + head * 64 + 32 * ch);
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t v[32];
-        tmem_ld32(t_mine + col + 32 * h2, v);
-        tmem_ld_wait();
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(out + grow * ld + head * 64 + 32 * h2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-        }
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
       }
     };
-    store64(COL_A1, p.out1, p.ld1);
-    if (MODE == AB_MODE_DKV) store64(COL_A2, p.out2, p.ld2);
+    store32(COL_A1, p.out1, p.ld1);
+    if (MODE == AB_MODE_DKV) store32(COL_A2, p.out2, p.ld2);
   }
 
   tc_fence_before();
