@@ -86,9 +86,14 @@ int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_
  * W[n][k + tap_shifts_host[t]] with W of w_rows rows (a multiple of 32) — all (kd, kh) taps of a convolution's weight
  * gradient; the CTAs that work on different taps of the same K range run concurrently and share A and W in L2, so HBM
  * sees the operands about once instead of n_taps times; with w_rows of 64 or 128 several taps share one 256-wide tile
- * (one A tile, one MMA). tap_shifts_host: HOST array of n_taps multiples of 8. */
+ * (one A tile, one MMA). tap_shifts_host: HOST array of n_taps multiples of 8. panel_len > 0 (a multiple of 64 that
+ * divides K; lda / ldw unused): K-PANEL-MAJOR operands, A = [K/panel_len][M][panel_len] and W = [K/panel_len][w_rows]
+ * [panel_len + 2*w_halo] where every W panel repeats w_halo columns of its neighbours on both sides (|shift| <= w_halo).
+ * With row-major operands of several MB of row pitch every row of a TMA box lies in another 2 MB page and the same
+ * product runs 3x slower (measured: 346 vs 1042 TFLOP/s); rald_enc_pad_transpose writes this layout. */
 int rald_gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
-                              const int* tap_shifts_host, float* out, int64_t ldo, int M, int K, void* stream);
+                              const int* tap_shifts_host, int panel_len, int w_halo, float* out, int64_t ldo, int M, int K,
+                              void* stream);
 
 /* rald_gemm_bf16 with out_mode 0 whose output columns with (col % f16_period) >= f16_start are written as IEEE fp16
  * instead of bf16 (start / period multiples of 64): the V projections consumed by rald_attn_d64. */
@@ -586,9 +591,11 @@ int rald_gn_bwd(const float* x, const float* dy, const double* stats, const floa
  * dil = 2 places a stride-2 convolution's output gradient on its input grid; copies = 3 writes the three kw-shifted
  * copies of a convolution input (TMA box origins must be 16-byte aligned: only the kd / kh part of a tap offset can be
  * an operand shift of rald_gemm_bf16_accum_shift). colsum (optional, f64 [C], f32 input only) receives the column sums of
- * the input over all voxels: the convolution's bias gradient from the pass that already reads dY. */
+ * the input over all voxels: the convolution's bias gradient from the pass that already reads dY. panel_len > 0: the
+ * K-panel-major layout of rald_gemm_bf16_accum_taps, [n_panels][copies*copy_rows][halo | panel_len | halo] (ld unused). */
 int rald_enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, double* colsum, void* stream);
+                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, int panel_len, int halo, int n_panels,
+                           double* colsum, void* stream);
 
 /* out bf16 [B, 2D, 2H, 2W, C] (zero-initialised by the caller) with out[2d+1, 2h+1, 2w+1] = in[d, h, w]: the operand of
  * the stride-2 convolution's dgrad (Downsample :34-41) as a stride-1 convolution with flipped weights. */

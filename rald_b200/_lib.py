@@ -35,11 +35,11 @@ _SIGNATURES = {
     "rald_gn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_f32, c_int, c_void_p,
                     c_void_p, c_void_p, c_void_p],
     "rald_enc_pad_transpose": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_void_p, c_i64, c_void_p, c_void_p],
+                               c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p],
     "rald_enc_stuff": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "rald_enc_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
-    "rald_gemm_bf16_accum_taps": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_int,
-                                  c_void_p],
+    "rald_gemm_bf16_accum_taps": [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_i64,
+                                  c_int, c_int, c_void_p],
     "rald_gemm_bf16_f16cols": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_void_p],
     "rald_gemm_bf16_wsplit": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64,

@@ -28,8 +28,9 @@ int rald_gemm_bf16_accum_shift(const void* A, int64_t lda, const void* W, int64_
 }
 
 int rald_gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
-                              const int* tap_shifts_host, float* out, int64_t ldo, int M, int K, void* stream) {
-  return rald::gemm_bf16_accum_taps(A, lda, W, ldw, w_rows, n_taps, tap_shifts_host, out, ldo, M, K,
+                              const int* tap_shifts_host, int panel_len, int w_halo, float* out, int64_t ldo, int M, int K,
+                              void* stream) {
+  return rald::gemm_bf16_accum_taps(A, lda, W, ldw, w_rows, n_taps, tap_shifts_host, panel_len, w_halo, out, ldo, M, K,
                                     static_cast<cudaStream_t>(stream));
 }
 

@@ -202,8 +202,8 @@ int gn_bwd(const float* x, const float* dy, const double* stats, const float* ga
 template <bool IN_F32>
 __global__ void __launch_bounds__(256)
 enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, int H, int W, int C, int dil, int Wp,
-                         int copies, int copy_rows, int pos_bias, uint16_t* __restrict__ out_t, int64_t ld,
-                         double* __restrict__ colsum) {
+                         int copies, int copy_rows, int64_t pos_bias, uint16_t* __restrict__ out_t, int64_t ld,
+                         int panel_len, int halo, int n_panels, double* __restrict__ colsum) {
   __shared__ uint16_t tile[64][66];
   __shared__ int64_t s_p[64];
   __shared__ float s_cs[4][64];
@@ -255,13 +255,30 @@ enc_pad_transpose_kernel(const void* __restrict__ in, int64_t total_vox, int D, 
     const int64_t P = s_p[tx];
     if (c < C && P >= 0) {
       const uint16_t val = tile[tx][i];
-      for (int r = 0; r < copies; ++r) out_t[((int64_t)r * copy_rows + c) * ld + P + pos_bias - r] = val;
+      for (int r = 0; r < copies; ++r) {
+        const int64_t pos = P + pos_bias - r;
+        const int64_t orow = (int64_t)r * copy_rows + c;
+        if (panel_len == 0) {
+          out_t[orow * ld + pos] = val;
+        } else {
+          // K-panel-major: [panel][row][halo | panel_len | halo]; a column near a panel edge is repeated in the
+          // neighbour's halo
+          const int64_t rows_total = (int64_t)copies * copy_rows, pls = panel_len + 2 * halo;
+          const int64_t pn = pos / panel_len;
+          const int col = (int)(pos - pn * panel_len);
+          out_t[(pn * rows_total + orow) * pls + col + halo] = val;
+          if (col < halo && pn > 0) out_t[((pn - 1) * rows_total + orow) * pls + col + panel_len + halo] = val;
+          if (col >= panel_len - halo && pn + 1 < n_panels)
+            out_t[((pn + 1) * rows_total + orow) * pls + col - panel_len + halo] = val;
+        }
+      }
     }
   }
 }
 
 int enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                      int copy_rows, int pos_bias, void* out_t, int64_t ld, double* colsum, cudaStream_t stream) {
+                      int copy_rows, int pos_bias, void* out_t, int64_t ld, int panel_len, int halo, int n_panels,
+                      double* colsum, cudaStream_t stream) {
   RALD_REQUIRE(colsum == nullptr || in_f32, "enc_pad_transpose: column sums are taken from an fp32 input");
   if (colsum != nullptr) RALD_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * C, stream));
   RALD_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (dil == 1 || dil == 2), "enc_pad_transpose: bad geometry");
@@ -270,7 +287,13 @@ int enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, in
   RALD_REQUIRE((copies == 1 || copies == 3) && copy_rows >= C && pos_bias >= 0 && pos_bias <= 1,
                "enc_pad_transpose: bad copy layout");
   const int64_t padded = (int64_t)B * (dil * D + 2) * (dil * H + 2) * Wp;
-  RALD_REQUIRE(ld >= padded + 8, "enc_pad_transpose: row pitch %lld < padded grid %lld", (long long)ld, (long long)padded);
+  if (panel_len == 0) {
+    RALD_REQUIRE(ld >= padded + 8, "enc_pad_transpose: row pitch %lld < padded grid %lld", (long long)ld, (long long)padded);
+  } else {
+    RALD_REQUIRE(panel_len % 64 == 0 && halo >= 0 && halo % 8 == 0 && halo < panel_len && n_panels > 0 &&
+                 (int64_t)n_panels * panel_len >= padded + 8, "enc_pad_transpose: %d panels of %d columns (halo %d) do not "
+                 "hold the padded grid of %lld", n_panels, panel_len, halo, (long long)padded);
+  }
   // frame groups whose voxel-tile count fits gridDim.y
   const int64_t vox_per_frame = (int64_t)D * H * W;
   const int64_t max_frames = (65535ll * 64) / vox_per_frame;
@@ -282,11 +305,12 @@ int enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, in
     const int64_t tv = nf * vox_per_frame;
     dim3 g2((unsigned)((C + 63) / 64), (unsigned)((tv + 63) / 64));
     const char* src = reinterpret_cast<const char*>(in) + f0 * vox_per_frame * C * esz;
-    uint16_t* dst = reinterpret_cast<uint16_t*>(out_t) + f0 * padded_frame;
-    if (in_f32) enc_pad_transpose_kernel<true><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows,
-                                                                       pos_bias, dst, ld, colsum);
-    else enc_pad_transpose_kernel<false><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias,
-                                                                 dst, ld, nullptr);
+    const int64_t bias = pos_bias + f0 * padded_frame;     // the group's frames start at this column
+    uint16_t* dst = reinterpret_cast<uint16_t*>(out_t);
+    if (in_f32) enc_pad_transpose_kernel<true><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows, bias,
+                                                                       dst, ld, panel_len, halo, n_panels, colsum);
+    else enc_pad_transpose_kernel<false><<<g2, 256, 0, stream>>>(src, tv, D, H, W, C, dil, Wp, copies, copy_rows, bias, dst,
+                                                                 ld, panel_len, halo, n_panels, nullptr);
     RALD_LAUNCHED();
   }
   return 0;
@@ -445,9 +469,10 @@ int rald_gn_bwd(const float* x, const float* dy, const double* stats, const floa
 }
 
 int rald_enc_pad_transpose(const void* in, int in_f32, int B, int D, int H, int W, int C, int dil, int Wp, int copies,
-                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, double* colsum, void* stream) {
-  return rald::enc_pad_transpose(in, in_f32, B, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias, out_t_bf16, ld, colsum,
-                                 static_cast<cudaStream_t>(stream));
+                           int copy_rows, int pos_bias, void* out_t_bf16, int64_t ld, int panel_len, int halo, int n_panels,
+                           double* colsum, void* stream) {
+  return rald::enc_pad_transpose(in, in_f32, B, D, H, W, C, dil, Wp, copies, copy_rows, pos_bias, out_t_bf16, ld, panel_len,
+                                 halo, n_panels, colsum, static_cast<cudaStream_t>(stream));
 }
 
 int rald_enc_stuff(const float* in, int B, int D, int H, int W, int C, void* out_bf16, void* stream) {

@@ -85,6 +85,10 @@ struct GemmParams {
   int tap_shift[16];          // t with column shift tap_shift[t] instead of w_k_off (all taps of a convolution weight gradient
                               // in ONE launch). tap_n < BN: a W tile is BN / tap_n boxes of tap_n rows, one per tap, each with
                               // its own shift — several taps share one A tile and one wide MMA
+  int panel_len, b_halo;      // panel_len > 0: A is [K / panel_len panels][M][panel_len] and W [panels][w rows][panel_len + 2 b_halo]
+                              // (K-panel-major: the rows of a tile lie within a few pages; with a 5.5 MB row pitch every row of
+                              // a box is in another 2 MB page and the same GEMM runs 3x slower, tools/gpu_pitch_probe.py). W
+                              // panels carry b_halo columns of their neighbours on both sides so that shifted boxes stay inside
   int k_splits;               // > 1 (fp32 reduce-add epilogue, no bias): every output tile is computed by k_splits work items,
   int kb_per_split;           // each over kb_per_split k-blocks, all adding into `out` — the weight-gradient GEMMs of the
                               // training step (few output tiles, K = rows of the batch). Summation order across the splits
@@ -222,6 +226,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int t_begin = unit, t_end = num_tiles, t_step = num_units;
   // A column of k-block kb (split weights: the A tiles are re-read for the second half of K)
   auto a_col = [&](int kb) { const int c = kb * GEMM_BK; return c >= p.a_k ? c - p.a_k : c; };
+  // the A tile of k-block kb, rows row0 ...
+  auto load_a = [&](uint8_t* sa, uint64_t* bar, int kb, int row0) {
+    if (SPLITK && p.panel_len > 0) {
+      const int c = kb * GEMM_BK, pn = c / p.panel_len;
+      tma_load_3d(sa, &tmA, bar, c - pn * p.panel_len, row0, pn);
+    } else {
+      tma_load_2d(sa, &tmA, bar, a_col(kb), row0);
+    }
+  };
   // this CTA's share of the W tile of (k-block kb, tile (m_blk, n_blk)) -> sb, credited to `bar`
   auto load_b = [&](uint8_t* sb, uint64_t* bar, int kb, int m_blk, int n_blk) {
     auto ld = [&](uint8_t* dst, int x, int y) {
@@ -232,6 +245,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int row = n_blk * BN + (int)cta_rank * (BN / CG), shift = 0;
       if (SPLITK) {
         shift = p.w_k_off;
+        if (p.panel_len > 0) {
+          // K-panel-major operands (3-D tensor maps: column in panel, row, panel)
+          const int c = kb * GEMM_BK, pn = c / p.panel_len, cc = c - pn * p.panel_len + p.b_halo;
+          if (p.tap_n > 0 && p.tap_n < BN) {
+            const int tap0 = row / p.tap_n;
+            for (int i = 0; i < BN / p.tap_n; ++i)
+              tma_load_3d(sb + (size_t)i * p.tap_n * 128, &tmB, bar, cc + p.tap_shift[tap0 + i], 0, pn);
+          } else if (p.tap_n > 0) {
+            const int tap = row / p.tap_n;
+            tma_load_3d(sb, &tmB, bar, cc + p.tap_shift[tap], row - tap * p.tap_n, pn);
+          } else {
+            tma_load_3d(sb, &tmB, bar, cc + shift, row, pn);
+          }
+          return;
+        }
         if (p.tap_n > 0 && p.tap_n < BN) {
           // several taps per tile: one box of tap_n rows (all rows of W) per tap, stacked in the B tile
           const int tap0 = row / p.tap_n;
@@ -337,13 +365,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             --w_pre;
 #pragma unroll
             for (int g = 0; g < G; ++g)
-              tma_load_2d(slot + g * Cfg::STAGE_BYTES, &tmA, &full_bar[s], a_col(kb + g), m_blk * BM);
+              load_a(slot + g * Cfg::STAGE_BYTES, &full_bar[s], kb + g, m_blk * BM);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], SLOT_BYTES);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
-              tma_load_2d(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * BM);
+              load_a(sa, &full_bar[s], kb + g, m_blk * BM);
               load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
             }
           }
@@ -623,7 +651,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int num_kb = p.k_splits > 1 ? p.kb_per_split : (p.K + GEMM_BK - 1) / GEMM_BK;
   if constexpr (OUT_MODE == 1 && EPI == EPI_TMA_REDUCE && CG == 1) {
     // the weight-gradient form is only reachable through the fp32 accumulate-into-out GEMMs
-    if (p.k_splits > 1 || p.tap_n > 0 || p.w_k_off != 0) {
+    if (p.k_splits > 1 || p.tap_n > 0 || p.w_k_off != 0 || p.panel_len > 0) {
       // one k-block per ring slot: these GEMMs stream hundreds of k-blocks per work item, and a slot that is refilled
       // as soon as ONE k-block has been consumed keeps more loads in flight than grouped slots (measured, tools/
       // gpu_time_wgrad.py: dW of FF2 70 -> 62 us, of the 512 x 512 projections 22.6 -> 19.2 us at K = 32 768)
@@ -647,6 +675,7 @@ struct GemmOpts {
   int ab_f16 = 0;
   int split_k = 0;      // allow K splits (fp32 accumulate-into-out GEMMs without bias: weight gradients)
   int w_k_off = 0;      // column shift of the W operand (GemmParams::w_k_off)
+  int panel_len = 0, b_halo = 0, n_panels = 0;   // K-panel-major operands (GemmParams::panel_len)
   int tap_n = 0, n_taps = 0;   // N = n_taps * tap_n, W has tap_n rows, tap t is shifted by tap_shift[t]
   int tap_shift[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -678,12 +707,22 @@ int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ld
 }
 
 int gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
-                         const int* tap_shifts, float* out, int64_t ldo, int M, int K, cudaStream_t stream) {
+                         const int* tap_shifts, int panel_len, int w_halo, float* out, int64_t ldo, int M, int K,
+                         cudaStream_t stream) {
   RALD_REQUIRE(n_taps >= 1 && n_taps <= 16 && tap_shifts != nullptr, "gemm taps: 1..16 taps");
   GemmOpts o;
   o.split_k = 1;
   o.tap_n = w_rows;
   o.n_taps = n_taps;
+  if (panel_len > 0) {
+    RALD_REQUIRE(K % panel_len == 0, "gemm taps: K=%d must be a multiple of the panel length %d", K, panel_len);
+    o.panel_len = panel_len;
+    o.b_halo = w_halo;
+    o.n_panels = K / panel_len;
+    for (int t = 0; t < n_taps; ++t)
+      RALD_REQUIRE(tap_shifts[t] >= -w_halo && tap_shifts[t] <= w_halo, "gemm taps: shift %d exceeds the halo %d",
+                   tap_shifts[t], w_halo);
+  }
   for (int t = 0; t < n_taps; ++t) o.tap_shift[t] = tap_shifts[t];
   return gemm_impl(A, lda, W, ldw, out, ldo, nullptr, out, ldo, M, n_taps * w_rows, K, 1, 0, o, stream);
 }
@@ -842,6 +881,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   p.grp_total = o.grp_total;
   p.ab_f16 = o.ab_f16;
   p.w_k_off = o.w_k_off;
+  p.panel_len = o.panel_len;
+  p.b_halo = o.b_halo;
   p.tap_n = o.tap_n;
   for (int t = 0; t < 16; ++t) p.tap_shift[t] = o.tap_shift[t];
   p.k_splits = k_splits;
@@ -850,6 +891,21 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   RALD_REQUIRE(o.f16_period == 0 || epi == EPI_TMA_STORE, "gemm: mixed fp16 / bf16 output needs the TMA-store epilogue");
 
   CUtensorMap tmA, tmB, tmO;
+  if (o.panel_len > 0) {
+    RALD_REQUIRE(o.split_k && o.panel_len % GEMM_BK == 0 && o.n_panels > 0 && K == o.n_panels * o.panel_len &&
+                 o.b_halo % 8 == 0 && o.b_mode == 0, "gemm: bad panel layout (%d panels of %d columns, K=%d, halo %d)",
+                 o.n_panels, o.panel_len, K, o.b_halo);
+    const int w_rows = o.tap_n > 0 ? o.tap_n : N;
+    const int w_len = o.panel_len + 2 * o.b_halo;
+    uint64_t da[3] = {(uint64_t)o.panel_len, (uint64_t)M, (uint64_t)o.n_panels};
+    uint64_t sa[2] = {(uint64_t)o.panel_len * 2, (uint64_t)M * o.panel_len * 2};
+    uint32_t ba[3] = {64, (uint32_t)GEMM_BM, 1};
+    RALD_TRY(make_tmap_nd_bf16(&tmA, A, 3, da, sa, ba, nullptr));
+    uint64_t db[3] = {(uint64_t)w_len, (uint64_t)w_rows, (uint64_t)o.n_panels};
+    uint64_t sb[2] = {(uint64_t)w_len * 2, (uint64_t)w_rows * w_len * 2};
+    uint32_t bb[3] = {64, (uint32_t)((o.tap_n > 0 && o.tap_n < bn) ? o.tap_n : bn), 1};
+    RALD_TRY(make_tmap_nd_bf16(&tmB, W, 3, db, sb, bb, nullptr));
+  } else {
   RALD_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, (uint32_t)GEMM_BM));
   if (o.b_mode == 1) {          // K' of one block: [8 heads * grp_total frames * 64 keys][K], one 64-row box per head
     RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(N / 64) * o.grp_total * 64, (uint64_t)K, (uint64_t)ldw, 64u));
@@ -859,6 +915,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
   } else {
     RALD_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)(o.tap_n > 0 ? o.tap_n : N), (uint64_t)k_total, (uint64_t)ldw,
                                (uint32_t)(pair ? bn / 2 : ((o.tap_n > 0 && o.tap_n < bn) ? o.tap_n : bn))));
+  }
   }
   if (epi != EPI_GENERIC) {
     RALD_TRY(make_tmap_out(&tmO, out, (uint64_t)M, (uint64_t)(out_mode == 2 ? N / 2 : N), (uint64_t)ldo, out_mode == 1, 32u));

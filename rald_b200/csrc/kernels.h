@@ -28,8 +28,10 @@ int gemm_bf16_accum_splitk(const void* A, int64_t lda, const void* W, int64_t ld
                            int M, int N, int K, cudaStream_t stream);
 
 // n_taps shifted products in one launch: out[m][t * w_rows + n] += sum_k A[m][k] W[n][k + tap_shifts[t]] (W: w_rows rows)
+// panel_len > 0: K-panel-major operands, A [K/panel_len][M][panel_len], W [K/panel_len][w_rows][panel_len + 2 w_halo]
 int gemm_bf16_accum_taps(const void* A, int64_t lda, const void* W, int64_t ldw, int w_rows, int n_taps,
-                         const int* tap_shifts, float* out, int64_t ldo, int M, int K, cudaStream_t stream);
+                         const int* tap_shifts, int panel_len, int w_halo, float* out, int64_t ldo, int M, int K,
+                         cudaStream_t stream);
 
 // bf16 output in which the columns with (col % f16_period) >= f16_start are written as fp16 instead: the V
 // projections feeding attn_d64 (fp16 probabilities x fp16 values on the tensor cores).

@@ -24,11 +24,15 @@ Host-side sequencing only; no torch fallback for any convolution, normalisation,
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import _lib
+
+# K-panel length of the conv weight-gradient operands (0: row-major operands with one row per channel)
+_WGRAD_PANEL = int(os.environ.get("RALD_B200_WGRAD_PANEL", "32768"))
 
 BF = torch.bfloat16
 F32 = torch.float32
@@ -227,28 +231,39 @@ class EncoderTrainRuntime(_lib.RuntimeNotCopied):
         D, H, W = dims
         Wp = -(-(W + 2) // 8) * 8                       # padded row pitch: kd / kh tap offsets become multiples of 8
         padded = B * (D + 2) * (H + 2) * Wp
-        Lp = -(-(padded + 8) // 16384) * 16384
         cin_rows = -(-cin // 32) * 32
         co_rows = -(-cv_cout // 64) * 64                 # a tap = one box of co_rows rows of dY^T
         o = 1 if stride == 1 else 0
-        dyT = torch.zeros(co_rows, Lp, device=self.dev, dtype=BF)
-        xT = torch.zeros(3 * cin_rows, Lp, device=self.dev, dtype=BF)     # [kw][cin_rows]: X pre-shifted by kw - o
-        bsum = torch.empty(cv_cout, device=self.dev, dtype=torch.float64)      # bias gradient, from the same pass over dY
-        _lib.call("rald_enc_pad_transpose", dy.data_ptr(), 1, B, D // stride, H // stride, W // stride, cv_cout, stride, Wp,
-                  1, co_rows, 0, dyT.data_ptr(), Lp, bsum.data_ptr(), _s())
-        _lib.call("rald_enc_pad_transpose", x_in.data_ptr(), 1 if x_in.dtype == F32 else 0, B, D, H, W, cin, 1, Wp, 3,
-                  cin_rows, o, xT.data_ptr(), Lp, 0, _s())
-        # dW^T in ONE launch: out[kw*cin_rows + ci][tap*co_rows + co] = sum_P X_kw[ci][P] dY[co][P - off(tap)], the nine
-        # (kd, kh) taps as shifted boxes of dY^T stacked four (co_rows = 64) / two (128) to a 256-wide tile; the tap count is
-        # padded to a multiple of that with dummy taps whose output is dropped
         per_tile = max(1, 256 // co_rows)
         n_taps = -(-9 // per_tile) * per_tile
         S1, S2 = (H + 2) * Wp, Wp
         offs = [-((kd - o) * S1 + (kh - o) * S2) for kd in range(3) for kh in range(3)] + [0] * (n_taps - 9)
+        bsum = torch.empty(cv_cout, device=self.dev, dtype=torch.float64)      # bias gradient, from the same pass over dY
         shifts = (ctypes.c_int * n_taps)(*offs)
         dWt = torch.zeros(3 * cin_rows, n_taps * co_rows, device=self.dev, dtype=F32)
-        _lib.call("rald_gemm_bf16_accum_taps", xT.data_ptr(), Lp, dyT.data_ptr(), Lp, co_rows, n_taps,
-                  ctypes.addressof(shifts), dWt.data_ptr(), n_taps * co_rows, 3 * cin_rows, Lp, _s())
+        if _WGRAD_PANEL > 0:
+            PL = _WGRAD_PANEL                           # K-panel length: a tile's rows lie within a few 2 MB pages
+            n_pan = -(-(padded + 8) // PL)
+            K = n_pan * PL
+            halo = -(-max(abs(v) for v in offs) // 8) * 8
+            # panel-major operands: X copies [n_pan][3*cin_rows][PL], dY^T [n_pan][co_rows][halo | PL | halo]
+            dyT = torch.zeros(n_pan, co_rows, PL + 2 * halo, device=self.dev, dtype=BF)
+            xT = torch.zeros(n_pan, 3 * cin_rows, PL, device=self.dev, dtype=BF)    # [kw][cin_rows]: X pre-shifted by kw - o
+            ld = 0
+        else:
+            PL = halo = n_pan = 0
+            ld = K = -(-(padded + 8) // 16384) * 16384
+            dyT = torch.zeros(co_rows, ld, device=self.dev, dtype=BF)
+            xT = torch.zeros(3 * cin_rows, ld, device=self.dev, dtype=BF)
+        _lib.call("rald_enc_pad_transpose", dy.data_ptr(), 1, B, D // stride, H // stride, W // stride, cv_cout, stride, Wp,
+                  1, co_rows, 0, dyT.data_ptr(), ld, PL, halo, n_pan, bsum.data_ptr(), _s())
+        _lib.call("rald_enc_pad_transpose", x_in.data_ptr(), 1 if x_in.dtype == F32 else 0, B, D, H, W, cin, 1, Wp, 3,
+                  cin_rows, o, xT.data_ptr(), ld, PL, 0, n_pan, 0, _s())
+        # dW^T in ONE launch: out[kw*cin_rows + ci][tap*co_rows + co] = sum_P X_kw[ci][P] dY[co][P - off(tap)], the nine
+        # (kd, kh) taps as shifted boxes of dY^T stacked four (co_rows = 64) / two (128) to a 256-wide tile; the tap count is
+        # padded to a multiple of that with dummy taps whose output is dropped
+        _lib.call("rald_gemm_bf16_accum_taps", xT.data_ptr(), ld, dyT.data_ptr(), ld, co_rows, n_taps,
+                  ctypes.addressof(shifts), PL, halo, dWt.data_ptr(), n_taps * co_rows, 3 * cin_rows, K, _s())
         # [kw][cin_rows][tap][co_rows] -> [cout][cin][kd][kh][kw]
         gw = dWt.reshape(3, cin_rows, n_taps, co_rows)[:, :cin, :9, :cv_cout].reshape(3, cin, 3, 3, cv_cout) \
             .permute(4, 1, 2, 3, 0).contiguous()
