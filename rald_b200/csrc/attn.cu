@@ -412,6 +412,8 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
                    int64_t ldo, int frames, int heads, int Sq, int Skv, int kv_frame_rows, float* stats, float scale,
                    cudaStream_t stream) {
   RALD_REQUIRE(frames > 0 && heads > 0 && Sq > 0, "attn: bad sizes");
+  if (Skv == 512 && g_attn_dbg == nullptr && attn_streams_enabled())
+    return attn_d64_streams(Q, ldq, K, ldk, V, ldv, O, ldo, frames, heads, Sq, kv_frame_rows, stats, scale, stream);
   RALD_REQUIRE(kv_frame_rows >= Skv, "attn: %d key rows per frame < Skv=%d", kv_frame_rows, Skv);
   RALD_REQUIRE(Skv >= 64 && Skv <= 512 && Skv % 64 == 0, "attn: Skv=%d must be a multiple of 64 in [64, 512]", Skv);
   RALD_REQUIRE(Sq % ATT_BM == 0, "attn: Sq=%d must be a multiple of 128", Sq);

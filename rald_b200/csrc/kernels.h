@@ -78,6 +78,11 @@ int attn_d64_chunk(const void* Q, int64_t ldq, const void* K, int64_t ldk, const
                    cudaStream_t stream);
 // Skv = chunks * 512 (1024 .. 4096): chunked attention + exact merge; o_chunks bf16 [chunks][frames*Sq][heads*64],
 // stats fp32 [chunks][frames*Sq][heads][2] are scratch
+// attn_streams.cu: the Skv = 512 case as four concurrent softmax streams per CTA (RALD_B200_ATTN_STREAMS=0: attn.cu's form)
+bool attn_streams_enabled();
+int attn_d64_streams(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                     int64_t ldo, int frames, int heads, int Sq, int kv_frame_rows, float* stats, float scale,
+                     cudaStream_t stream);
 int attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                   int64_t ldo, int frames, int heads, int Sq, int Skv, float scale, void* o_chunks, float* stats,
                   cudaStream_t stream);

@@ -10,10 +10,13 @@ L.rald_ln_rows.argtypes = [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_
 dev = "cuda"
 torch.manual_seed(0)
 
-def attn(B, H, Sq, Skv, amp=1.0, timing=False):
+def attn(B, H, Sq, Skv, amp=1.0, timing=False, ramp=0.0):
     D = H * 64
     q = (torch.randn(B * Sq, D, device=dev) * amp).bfloat16()
-    k = (torch.randn(B * Skv, D, device=dev) * amp).bfloat16()
+    k = torch.randn(B * Skv, D, device=dev) * amp
+    if ramp:   # key magnitude grows with the key index: later key chunks raise the running maximum (lazy-shift path)
+        k = (k.view(B, Skv, D) * torch.linspace(0.05, ramp, Skv, device=dev)[None, :, None]).reshape(B * Skv, D)
+    k = k.bfloat16()
     v = torch.randn(B * Skv, D, device=dev).half()   # V is fp16 (see include/rald_b200.h)
     o = torch.zeros(B * Sq, D, device=dev, dtype=torch.bfloat16)
     st = _lib.cur_stream()
@@ -26,7 +29,7 @@ def attn(B, H, Sq, Skv, amp=1.0, timing=False):
     ref = torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, -1) @ vf
     ref = ref.transpose(1, 2).reshape(B * Sq, D)
     err = ((o.float() - ref).norm() / ref.norm()).item()
-    print(f"attn B={B} H={H} Sq={Sq} Skv={Skv} amp={amp}: rel={err:.3e} {'OK' if err < 1e-2 else 'FAIL'}", flush=True)
+    print(f"attn B={B} H={H} Sq={Sq} Skv={Skv} amp={amp} ramp={ramp}: rel={err:.3e} {'OK' if err < 1e-2 else 'FAIL'}", flush=True)
     if timing:
         for _ in range(3): L.rald_attn_d64(*args)
         torch.cuda.synchronize()
@@ -69,6 +72,9 @@ ok &= attn(2, 8, 512, 64)
 ok &= attn(3, 8, 512, 512, amp=3.0)
 ok &= attn(2, 8, 512, 512, amp=5.0)
 ok &= attn(2, 8, 512, 64, amp=4.0)
+ok &= attn(2, 8, 512, 512, amp=2.0, ramp=4.0)
+ok &= attn(1, 8, 512, 512, amp=2.0, ramp=4.0)
+ok &= attn(3, 2, 256, 512, amp=1.0, ramp=8.0)
 ok &= attn(64, 8, 512, 512, timing=True)
 ok &= attn(64, 8, 512, 64, timing=True)
 ok &= attn(8, 8, 512, 512, timing=True)
