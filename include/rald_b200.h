@@ -118,6 +118,8 @@ int rald_gemm_debug_buffer(unsigned long long* dev_buf);
  * softmax groups, stamps at dev_buf[(tile*2+group)*8 + i]: 0 tile start, 1 S ready, 2 P written, 3 stats merged,
  * 4 O ready, 5 stored. */
 int rald_attn_debug_buffer(unsigned long long* dev_buf);
+/* Same for the four-stream form of the Skv = 512 case (attn_streams.cu): issuer and stream stamps of CTA 0. */
+int rald_attn_streams_debug_buffer(unsigned long long* dev_buf);
 
 /* O = softmax(Q K^T * scale) V per (frame, head), head_dim 64, Skv <= 512 (multiple of 64), scores kept in TMEM.
  * Q: [frames*Sq, >= heads*64] bf16 (ldq), K: [frames*Skv, ...] bf16, V: [frames*Skv, ...] **fp16** (the probabilities

@@ -46,6 +46,7 @@ _SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rald_gemm_debug_buffer": [c_void_p],
     "rald_attn_debug_buffer": [c_void_p],
+    "rald_attn_streams_debug_buffer": [c_void_p],
     "rald_xattn_debug_buffer": [c_void_p],
     "rald_ae_query_debug_buffer": [c_void_p],
     "rald_attn_d64": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_int,
