@@ -7,11 +7,8 @@
 // four stream regions of 128 columns = [S / P chunk: 64 columns | O accumulator: 64 columns], each owned by four warps
 // (thread <-> query row <-> TMEM lane). A stream walks over 64-key chunks:
 //     S = Q K_c^T (MMA)  ->  row max, lazily raised shift, p = 2^(s c - m) as fp16 pairs over S  ->  O += P V_c (MMA)
-// and while one stream waits for its MMAs the other three keep the exp2 unit busy. Every stream issues ITS OWN MMAs
-// (lane 0 of its first warp, behind a 128-thread named barrier): a single MMA thread serving the four streams
-// round-robin was the pace — an mbarrier probe + four MMAs cost it ~0.3 us, 0.62 us per stream step, so the streams
-// idled 75 % of the time (70 us per 64 frames; tools/attn_streams_phases.py). Row statistics are thread-local (no
-// shuffles, no shared-memory exchange inside a tile).
+// and while one stream waits for its MMAs the other three keep the exp2 unit busy; the single MMA thread serves the
+// streams round-robin. Row statistics are thread-local (no shuffles, no shared-memory exchange inside a tile).
 //   tq = 2: two query tiles of a (frame, head) in flight, two streams each (even / odd chunks)   [batches that fill the GPU]
 //   tq = 1: one query tile, four streams (chunks c = sub mod 4)                                   [small batches]
 // The streams of a tile keep their own (shift, sum, O) and are merged exactly at the end of the tile (as attn.cu merges
@@ -19,8 +16,8 @@
 // it by more than 2^8 (p <= 256 in fp16), which rescales that stream's O in TMEM (rare; exact either way).
 //   warp 0 lane 0 : TMA producer (Q tile ring of 4, K / V as eight 64-key chunks each, recycled chunk by chunk so the
 //                   next item's keys arrive while the current item finishes)
-//   warp 1        : TMEM allocation
-//   warps 2..17   : stream s = (warp - 2) / 4, TMEM lane quarter = warp % 4; lane 0 of warp 2 + 4 s issues the stream's MMAs
+//   warp 1 lane 0 : tcgen05 issuer
+//   warps 2..17   : stream s = (warp - 2) / 4, TMEM lane quarter = warp % 4
 // The output tile is staged (bf16, 128-byte swizzled rows) in the tile's own Q slot — dead once the last S product of
 // the tile has retired — and leaves through one TMA store. Reference: model/models_radar_generation.py:66-75.
 #include "host.cuh"
@@ -35,7 +32,7 @@ constexpr int AS_CK = 64;                      // keys per chunk
 constexpr int AS_SKV = 512;
 constexpr int AS_NCH = AS_SKV / AS_CK;         // 8 chunks
 constexpr int AS_STREAMS = 4;
-constexpr int AS_THREADS = 64 + AS_STREAMS * 128;
+constexpr int AS_THREADS = 64 + AS_STREAMS * 128 + 32;   // TMA warp, MMA warp A, 16 stream warps, MMA warp B
 constexpr int AS_QBYTES = AS_BM * AS_D * 2;    // 16 KB
 constexpr int AS_CBYTES = AS_CK * AS_D * 2;    // 8 KB: one K or V chunk
 constexpr int AS_QSLOTS = 4;
@@ -48,10 +45,9 @@ struct AttnStreamParams {
   int num_items;
   float scale_log2;    // scale * log2(e)
   int kv_frame_rows;   // rows per frame in the K / V tensors (>= 512; a key CHUNK of a longer context when larger)
-  int skew;            // tq = 2: chunks by which the second tile slot starts behind the first (0..2)
   float* stats;        // optional [frames*Sq][heads][2] = (shift, sum) of the keys seen by this call
-  unsigned long long* dbg;   // optional %globaltimer stamps of CTA 0 (tools/attn_phases.py): leaders [n < 32][stream][PV issued,
-                             // S issued], streams 256 + [stream][n < 32][S seen, max done, P written]
+  unsigned long long* dbg;   // optional %globaltimer stamps of CTA 0 (tools/attn_streams_phases.py): issuers [n < 32][stream]
+                             // [PV issued, S issued], streams 256 + [stream][n < 32][S seen, max done, P written]
 };
 static unsigned long long* g_attn_streams_dbg = nullptr;
 #define AS_STAMP_I(n_, s_, e_)                                                                      \
@@ -83,7 +79,9 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* kv_full = bars + 8;     // [8]
   uint64_t* kv_empty = bars + 16;   // [8]
   uint64_t* s_full = bars + 24;     // [4]
+  uint64_t* p_full = bars + 28;     // [4]
   uint64_t* o_full = bars + 32;     // [4]
+  uint64_t* o_free = bars + 36;     // [2] per tile slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
 
   const int warp = threadIdx.x >> 5;
@@ -100,12 +98,14 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     for (int i = 0; i < AS_NCH; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], TQ);   // one commit per stream that uses the chunk
+      mbar_init(&kv_empty[i], TQ);   // tq = 2: one commit per MMA warp (each serves one tile slot)
     }
     for (int i = 0; i < AS_STREAMS; ++i) {
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&o_free[i], 4 * NS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -143,9 +143,61 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // (allocates / frees TMEM; every stream issues its own MMAs)
-  } else {
+  } else if (warp == 1 || warp == 2 + 4 * AS_STREAMS) {
+    // ===================== MMA issuers: warp 1 serves streams 0, 1; the last warp streams 2, 3 =====================
+    // (one issuer for all four streams was the pace: an mbarrier probe + four MMAs cost it ~0.3 us, 0.62 us per stream
+    // step, 2.5 us per round of the four streams whose softmax takes 0.55 us: tools/attn_streams_phases.py)
+    if (lane == 0) {
+      const int s_lo = warp == 1 ? 0 : 2;
+      const uint32_t idesc_s = make_idesc(FMT_BF16, AS_BM, AS_CK, 0, 0);   // Q (smem) x K_c (smem) -> 128 x 64 fp32
+      const uint32_t idesc_o = make_idesc(FMT_F16, AS_BM, AS_D, 0, 1);     // P fp16 (TMEM) x V_c fp16 (smem, MN-major)
+      uint32_t it = 0;
+      uint32_t n = 0;    // chunks issued per stream so far (the streams advance in lock step)
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+#pragma unroll 1
+        for (int k = 0; k <= NCH; ++k) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int s = s_lo + s2;
+            const int ts = s / NS, sub = s % NS;
+            const uint32_t t_sp = tmem_base + s * 128;   // S / P chunk
+            const uint32_t t_o = t_sp + 64;              // O accumulator
+            if (k >= 1) {
+              // ---- O_s (+)= P V_c for the chunk whose probabilities the stream has just written ----
+              const int c = (k - 1) * NS + sub;
+              mbar_wait(&p_full[s], (n + k - 1) & 1);
+              if (k == 1) mbar_wait(&o_free[ts], (it & 1) ^ 1);   // the previous tile's O has been read
+              tc_fence_after();
+              // V chunk is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom
+              const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + c * AS_CBYTES), 1024, 1024);
+#pragma unroll
+              for (int j = 0; j < AS_CK / 16; ++j)   // 16 keys per MMA = 8 TMEM columns of P and 2048 B of V
+                mma_f16_ts(t_o, t_sp + 8 * j, v_desc + 128 * j, idesc_o, k > 1 || j > 0);
+              if (k == NCH) tc_commit(&o_full[s]);
+              AS_STAMP_I(n + k - 1, s, 0);
+              tc_commit(&kv_empty[c]);
+            }
+            if (k < NCH) {
+              // ---- S_s = Q K_c^T of the stream's next chunk (in order behind the P V product that read P) ----
+              const int c = k * NS + sub;
+              const uint32_t qn = it * TQ + ts;
+              const int qslot = qn & 3;
+              if (k == 0 && (sub & 1) == 0) mbar_wait(&q_full[qslot], (qn >> 2) & 1);   // once per issuer and tile
+              mbar_wait(&kv_full[c], it & 1);
+              tc_fence_after();
+              const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qslot * AS_QBYTES), 16, 1024);
+              const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + c * AS_CBYTES), 16, 1024);
+#pragma unroll
+              for (int j = 0; j < AS_D / 16; ++j) mma_f16_ss(t_sp, q_desc + 2 * j, k_desc + 2 * j, idesc_s, j != 0);
+              tc_commit(&s_full[s]);
+              AS_STAMP_I(n + k, s, 1);
+            }
+          }
+        }
+        n += NCH;
+      }
+    }
+  } else if (warp < 2 + 4 * AS_STREAMS) {
     // ===================== softmax streams =====================
     const int s = (warp - 2) >> 2;
     const int ts = s / NS, sub = s % NS;
@@ -155,37 +207,8 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t t_sp = tmem_base + s * 128 + lane_off;
     const uint32_t t_o = t_sp + 64;
     const bool storer = (threadIdx.x == 64 + ts * NS * 128);   // issues this tile slot's TMA stores
-    const bool leader = (threadIdx.x == 64 + s * 128);         // issues this stream's MMAs
     int pending_slot = -1;                   // Q slot whose output store may still be reading shared memory
     uint32_t it = 0, n = 0;
-    const uint32_t idesc_s = make_idesc(FMT_BF16, AS_BM, AS_CK, 0, 0);   // Q (smem) x K_c (smem) -> 128 x 64 fp32
-    const uint32_t idesc_o = make_idesc(FMT_F16, AS_BM, AS_D, 0, 1);     // P fp16 (TMEM) x V_c fp16 (smem, MN-major)
-    const uint32_t t_sp_mma = tmem_base + s * 128, t_o_mma = t_sp_mma + 64;
-    // S_s = Q K_c^T of chunk k_ of this stream's tile of the CTA's item number it_ (leader only)
-    auto issue_s = [&](uint32_t it_, int k_, uint32_t n_) {
-      const int c = k_ * NS + sub;
-      const uint32_t qn = it_ * TQ + ts;
-      const int qs = qn & 3;
-      if (k_ == 0) mbar_wait(&q_full[qs], (qn >> 2) & 1);
-      mbar_wait(&kv_full[c], it_ & 1);
-      tc_fence_after();
-      const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qs * AS_QBYTES), 16, 1024);
-      const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + c * AS_CBYTES), 16, 1024);
-#pragma unroll
-      for (int j = 0; j < AS_D / 16; ++j) mma_f16_ss(t_sp_mma, q_desc + 2 * j, k_desc + 2 * j, idesc_s, j != 0);
-      tc_commit(&s_full[s]);
-      AS_STAMP_I(n_, s, 1);
-    };
-    if (leader && (int)blockIdx.x < p.num_items) {
-      if (TQ == 2 && ts == 1 && p.skew != 0) {
-        // the second tile slot starts behind the first: the two slots then alternate between their exp2 and MMA phases
-        // (and between compute and epilogue) instead of contending for both in lock step
-        mbar_wait(&s_full[s - NS], 0);
-        if (p.skew > 1) mbar_wait(&s_full[s - NS], 1);
-      }
-      issue_s(0, 0, 0);
-    }
-    __syncwarp();
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int fh = item / p.items_per_head;
       const int frame = fh / p.heads, head = fh - frame * p.heads;
@@ -263,28 +286,9 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         l += s0;
         tmem_st_wait();
         tc_fence_before();
-        asm volatile("bar.sync %0, 128;" ::"r"(8 + s) : "memory");   // the four warps of the stream have written P
-        AS_STAMP_S(n, 2);
-        if (leader) {
-          // ---- O_s (+)= P V_c, then S of the stream's next chunk (in order behind the product that reads P) ----
-          tc_fence_after();
-          const int c = k * NS + sub;
-          // V chunk is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom
-          const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + c * AS_CBYTES), 1024, 1024);
-#pragma unroll
-          for (int j = 0; j < AS_CK / 16; ++j)   // 16 keys per MMA = 8 TMEM columns of P and 2048 B of V
-            mma_f16_ts(t_o_mma, t_sp_mma + 8 * j, v_desc + 128 * j, idesc_o, k > 0 || j > 0);
-          tc_commit(&kv_empty[c]);
-          AS_STAMP_I(n, s, 0);
-          if (k + 1 < NCH) {
-            issue_s(it, k + 1, n + 1);
-          } else {
-            tc_commit(&o_full[s]);
-            // the next tile's first S runs under this tile's epilogue (P of the last chunk is read in order before it)
-            if (item + (int)gridDim.x < p.num_items) issue_s(it + 1, 0, n + 1);
-          }
-        }
         __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+        AS_STAMP_S(n, 2);
         // the output store of this tile slot's previous tile has long finished reading its staging tile: release the Q slot
         if (k == 0 && storer && pending_slot >= 0) {
           bulk_wait_group_read<0>();
@@ -337,8 +341,9 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
         for (int i = 0; i < OC; ++i) acc[i] = fmaf(a, __uint_as_float(ov[i]), acc[i]);
       }
-      tc_fence_before();   // (the accumulators are overwritten by the next tile's first P V product, which its leader
-                           // issues after the named barrier below: every reader is past it)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[ts]);   // the streams' accumulators may be overwritten
       // ---- staging tile = the tile's Q slot (every S product of the tile has retired: o_full is committed behind them) ----
       {
         const uint32_t srow = smem_u32(sQ + qslot * AS_QBYTES) + (uint32_t)row_in_tile * 128u;
@@ -408,8 +413,6 @@ int attn_d64_streams(const void* Q, int64_t ldq, const void* K, int64_t ldk, con
   p.kv_frame_rows = kv_frame_rows;
   p.stats = stats;
   p.dbg = g_attn_streams_dbg;
-  static const int skew_env = [] { const char* e = getenv("RALD_B200_ATTN_SKEW"); return e ? atoi(e) : 2; }();
-  p.skew = skew_env;
   const int q_tiles = Sq / AS_BM;
   const int sms = device_sm_count();
   // tiles per item: rounds x (chunk steps of an item + fill / merge), in units of one chunk step of the four streams
