@@ -9,8 +9,9 @@
 //     S = Q K_c^T (MMA)  ->  row max, lazily raised shift, p = 2^(s c - m) as fp16 pairs over S  ->  O += P V_c (MMA)
 // and while one stream waits for its MMAs the other three keep the exp2 unit busy; the single MMA thread serves the
 // streams round-robin. Row statistics are thread-local (no shuffles, no shared-memory exchange inside a tile).
-//   tq = 2: two query tiles of a (frame, head) in flight, two streams each (even / odd chunks)   [batches that fill the GPU]
-//   tq = 1: one query tile, four streams (chunks c = sub mod 4)                                   [small batches]
+// A query tile is always served by TWO streams (even / odd chunks), so its arithmetic does not depend on the batch:
+//   tq = 2: two query tiles of a (frame, head) in flight = four streams     [batches that fill the GPU]
+//   tq = 1: one query tile, two streams; the other two stay idle             [fewer tiles than SMs]
 // The streams of a tile keep their own (shift, sum, O) and are merged exactly at the end of the tile (as attn.cu merges
 // its key parts). The shift of a stream is the running maximum raised lazily: it moves only when a chunk maximum exceeds
 // it by more than 2^8 (p <= 256 in fp16), which rescales that stream's O in TMEM (rare; exact either way).
@@ -65,7 +66,10 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
 attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                         const AttnStreamParams p) {
-  constexpr int NS = AS_STREAMS / TQ;     // streams per tile
+  // Two streams per tile whatever TQ: a tile's arithmetic (even / odd chunks, merge order) does not depend on the batch,
+  // so a frame computes bit-identical values alone and inside a batch. TQ = 1 leaves streams 2, 3 and MMA warp B idle.
+  constexpr int NS = 2;                   // streams per tile
+  constexpr int ACTIVE = NS * TQ;         // streams in use
   constexpr int NCH = AS_NCH / NS;        // chunks per stream and tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -147,7 +151,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ===================== MMA issuers: warp 1 serves streams 0, 1; the last warp streams 2, 3 =====================
     // (one issuer for all four streams was the pace: an mbarrier probe + four MMAs cost it ~0.3 us, 0.62 us per stream
     // step, 2.5 us per round of the four streams whose softmax takes 0.55 us: tools/attn_streams_phases.py)
-    if (lane == 0) {
+    if (lane == 0 && (TQ == 2 || warp == 1)) {
       const int s_lo = warp == 1 ? 0 : 2;
       const uint32_t idesc_s = make_idesc(FMT_BF16, AS_BM, AS_CK, 0, 0);   // Q (smem) x K_c (smem) -> 128 x 64 fp32
       const uint32_t idesc_o = make_idesc(FMT_F16, AS_BM, AS_D, 0, 1);     // P fp16 (TMEM) x V_c fp16 (smem, MN-major)
@@ -201,6 +205,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ===================== softmax streams =====================
     const int s = (warp - 2) >> 2;
     const int ts = s / NS, sub = s % NS;
+    const bool active = s < ACTIVE;
     const int q = warp & 3;                  // TMEM lane quarter
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -209,7 +214,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const bool storer = (threadIdx.x == 64 + ts * NS * 128);   // issues this tile slot's TMA stores
     int pending_slot = -1;                   // Q slot whose output store may still be reading shared memory
     uint32_t it = 0, n = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; active && item < p.num_items; item += gridDim.x, ++it) {
       const int fh = item / p.items_per_head;
       const int frame = fh / p.heads, head = fh - frame * p.heads;
       const int tile = (item - fh * p.items_per_head) * TQ + ts;
@@ -324,7 +329,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         sp[1] = l_all * ex2_f32(m_all - m_max);
       }
       // ---- O = sum_j w_j O_j / l : this stream normalises output columns [OC sub, OC sub + OC) ----
-      constexpr int OC = AS_D / NS;   // 32 or 16
+      constexpr int OC = AS_D / NS;   // 32
       float acc[OC];
 #pragma unroll
       for (int j = 0; j < OC; ++j) acc[j] = 0.f;
@@ -334,8 +339,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tc_fence_after();
         uint32_t ov[OC];
         const uint32_t t_oj = tmem_base + (ts * NS + j) * 128 + lane_off + 64 + OC * sub;
-        if constexpr (OC == 32) tmem_ld32(t_oj, ov);
-        else tmem_ld16(t_oj, ov);
+        tmem_ld32(t_oj, ov);
         tmem_ld_wait();
         const float a = wgt[j] * inv;
 #pragma unroll
@@ -362,7 +366,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
     }
-    if (storer) bulk_wait_group<0>();   // the staging tiles must outlive the last stores
+    if (active && storer) bulk_wait_group<0>();   // the staging tiles must outlive the last stores
   }
 
   tc_fence_before();
@@ -415,12 +419,13 @@ int attn_d64_streams(const void* Q, int64_t ldq, const void* K, int64_t ldk, con
   p.dbg = g_attn_streams_dbg;
   const int q_tiles = Sq / AS_BM;
   const int sms = device_sm_count();
-  // tiles per item: rounds x (chunk steps of an item + fill / merge), in units of one chunk step of the four streams
+  // tiles per item: rounds x (four chunk rounds of an item + fill / merge); a round of two streams is shorter than a
+  // round of four that share the exp2 unit
   int tq = 1;
   if (q_tiles % 2 == 0) {
     const long fh = (long)frames * heads;
-    const double c1 = (double)((fh * q_tiles + sms - 1) / sms) * (2.0 + 0.7);
-    const double c2 = (double)((fh * (q_tiles / 2) + sms - 1) / sms) * (4.0 + 0.7);
+    const double c1 = (double)((fh * q_tiles + sms - 1) / sms) * (4.0 * 0.7 + 0.7);
+    const double c2 = (double)((fh * (q_tiles / 2) + sms - 1) / sms) * (4.0 * 1.0 + 0.7);
     if (c2 <= c1) tq = 2;
   }
   p.tq = tq;
