@@ -151,8 +151,13 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // ===================== MMA issuers: warp 1 serves streams 0, 1; the last warp streams 2, 3 =====================
     // (one issuer for all four streams was the pace: an mbarrier probe + four MMAs cost it ~0.3 us, 0.62 us per stream
     // step, 2.5 us per round of the four streams whose softmax takes 0.55 us: tools/attn_streams_phases.py)
-    if (lane == 0 && (TQ == 2 || warp == 1)) {
-      const int s_lo = warp == 1 ? 0 : 2;
+    // The whole warp runs this code with warp-uniform values and ONE ELECTED lane issues: with the loop under `lane == 0`
+    // the compiler cannot keep descriptors and addresses in uniform registers and wraps every tcgen05.mma / commit in an
+    // ELECT / R2UR.BROADCAST loop of ~14 instructions (~120 clocks per 48-clock MMA: 0.6 us per issuer step whatever
+    // the number of MMAs or mbarrier probes; tools/attn_streams_phases.py, cuobjdump -sass).
+    if (TQ == 2 || warp == 1) {
+      const int s_lo = __shfl_sync(0xffffffffu, warp == 1 ? 0 : 2, 0);
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc_s = make_idesc(FMT_BF16, AS_BM, AS_CK, 0, 0);   // Q (smem) x K_c (smem) -> 128 x 64 fp32
       const uint32_t idesc_o = make_idesc(FMT_F16, AS_BM, AS_D, 0, 1);     // P fp16 (TMEM) x V_c fp16 (smem, MN-major)
       uint32_t it = 0;
@@ -164,7 +169,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int s2 = 0; s2 < 2; ++s2) {
             const int s = s_lo + s2;
             const int ts = s / NS, sub = s % NS;
-            const uint32_t t_sp = tmem_base + s * 128;   // S / P chunk
+            const uint32_t t_sp = tmem_base_u + s * 128;   // S / P chunk
             const uint32_t t_o = t_sp + 64;              // O accumulator
             if (k >= 1) {
               // ---- O_s (+)= P V_c for the chunk whose probabilities the stream has just written ----
@@ -174,12 +179,15 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               tc_fence_after();
               // V chunk is [key][d] = MN-major B operand: 8-key groups are 1024 B apart (SBO); one 64-wide MN atom
               const uint64_t v_desc = make_sdesc_sw128(smem_u32(sV + c * AS_CBYTES), 1024, 1024);
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < AS_CK / 16; ++j)   // 16 keys per MMA = 8 TMEM columns of P and 2048 B of V
-                mma_f16_ts(t_o, t_sp + 8 * j, v_desc + 128 * j, idesc_o, k > 1 || j > 0);
-              if (k == NCH) tc_commit(&o_full[s]);
-              AS_STAMP_I(n + k - 1, s, 0);
-              tc_commit(&kv_empty[c]);
+                for (int j = 0; j < AS_CK / 16; ++j)   // 16 keys per MMA = 8 TMEM columns of P and 2048 B of V
+                  mma_f16_ts(t_o, t_sp + 8 * j, v_desc + 128 * j, idesc_o, k > 1 || j > 0);
+                if (k == NCH) tc_commit(&o_full[s]);
+                AS_STAMP_I(n + k - 1, s, 0);
+                tc_commit(&kv_empty[c]);
+              }
+              __syncwarp();
             }
             if (k < NCH) {
               // ---- S_s = Q K_c^T of the stream's next chunk (in order behind the P V product that read P) ----
@@ -191,10 +199,13 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               tc_fence_after();
               const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qslot * AS_QBYTES), 16, 1024);
               const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + c * AS_CBYTES), 16, 1024);
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < AS_D / 16; ++j) mma_f16_ss(t_sp, q_desc + 2 * j, k_desc + 2 * j, idesc_s, j != 0);
-              tc_commit(&s_full[s]);
-              AS_STAMP_I(n + k, s, 1);
+                for (int j = 0; j < AS_D / 16; ++j) mma_f16_ss(t_sp, q_desc + 2 * j, k_desc + 2 * j, idesc_s, j != 0);
+                tc_commit(&s_full[s]);
+                AS_STAMP_I(n + k, s, 1);
+              }
+              __syncwarp();
             }
           }
         }
