@@ -46,6 +46,7 @@ struct AttnStreamParams {
   int num_items;
   float scale_log2;    // scale * log2(e)
   int kv_frame_rows;   // rows per frame in the K / V tensors (>= 512; a key CHUNK of a longer context when larger)
+  int skew;            // tq = 2: the second tile slot starts behind the first
   float* stats;        // optional [frames*Sq][heads][2] = (shift, sum) of the keys seen by this call
   unsigned long long* dbg;   // optional %globaltimer stamps of CTA 0 (tools/attn_streams_phases.py): issuers [n < 32][stream]
                              // [PV issued, S issued], streams 256 + [stream][n < 32][S seen, max done, P written]
@@ -162,6 +163,9 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const uint32_t idesc_o = make_idesc(FMT_F16, AS_BM, AS_D, 0, 1);     // P fp16 (TMEM) x V_c fp16 (smem, MN-major)
       uint32_t it = 0;
       uint32_t n = 0;    // chunks issued per stream so far (the streams advance in lock step)
+      // the second tile slot starts half a chunk cycle behind the first: in lock step all four streams are in their
+      // exponentials (XU-bound) and then all wait for their MMAs; shifted, one slot's exponentials run under the other's MMAs
+      if (TQ == 2 && s_lo != 0 && p.skew != 0 && (int)(blockIdx.x + gridDim.x) < p.num_items) mbar_wait(&p_full[0], 0);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
 #pragma unroll 1
         for (int k = 0; k <= NCH; ++k) {
@@ -189,13 +193,16 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               }
               __syncwarp();
             }
-            if (k < NCH) {
-              // ---- S_s = Q K_c^T of the stream's next chunk (in order behind the P V product that read P) ----
-              const int c = k * NS + sub;
-              const uint32_t qn = it * TQ + ts;
+            // ---- S_s = Q K_c^T of the stream's next chunk (in order behind the P V product that read P). The first chunk
+            // of the NEXT item follows the last P V product of this one: it runs under the tile's merge / store ----
+            const bool next_item = (k == NCH) && (item + (int)gridDim.x < p.num_items);
+            if ((k < NCH && (k > 0 || it == 0)) || next_item) {
+              const uint32_t it_s = next_item ? it + 1 : it;
+              const int c = (next_item ? 0 : k) * NS + sub;
+              const uint32_t qn = it_s * TQ + ts;
               const int qslot = qn & 3;
-              if (k == 0 && (sub & 1) == 0) mbar_wait(&q_full[qslot], (qn >> 2) & 1);   // once per issuer and tile
-              mbar_wait(&kv_full[c], it & 1);
+              if ((k == 0 || next_item) && (sub & 1) == 0) mbar_wait(&q_full[qslot], (qn >> 2) & 1);   // once per issuer and tile
+              mbar_wait(&kv_full[c], it_s & 1);
               tc_fence_after();
               const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + qslot * AS_QBYTES), 16, 1024);
               const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + c * AS_CBYTES), 16, 1024);
@@ -203,7 +210,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
                 for (int j = 0; j < AS_D / 16; ++j) mma_f16_ss(t_sp, q_desc + 2 * j, k_desc + 2 * j, idesc_s, j != 0);
                 tc_commit(&s_full[s]);
-                AS_STAMP_I(n + k, s, 1);
+                AS_STAMP_I(n + (next_item ? NCH : k), s, 1);
               }
               __syncwarp();
             }
@@ -428,6 +435,8 @@ int attn_d64_streams(const void* Q, int64_t ldq, const void* K, int64_t ldk, con
   p.kv_frame_rows = kv_frame_rows;
   p.stats = stats;
   p.dbg = g_attn_streams_dbg;
+  static const int skew_env = [] { const char* e = getenv("RALD_B200_ATTN_SKEW"); return e ? atoi(e) : 1; }();
+  p.skew = skew_env;
   const int q_tiles = Sq / AS_BM;
   const int sms = device_sm_count();
   // tiles per item: rounds x (four chunk rounds of an item + fill / merge); a round of two streams is shorter than a
