@@ -318,17 +318,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  int w_pre = 0;            // ring stages whose W tile is already in flight (producer thread only)
-  if (CG == 1 && p.w_static != 0 && threadIdx.x == 0) {
+  int w_pre = 0;            // ring stages whose W tile is already in flight (producer warp only; warp-uniform)
+  if (CG == 1 && p.w_static != 0 && warp == 0) {
     // static weights: the W tiles of this CTA's first SLOTS ring slots do not depend on the preceding kernel
     int tile = t_begin, kb = 0;
     while (w_pre < SLOTS && tile < t_end) {
       int m_blk, n_blk, kb0;
       decode(tile, m_blk, n_blk, kb0);   // (k_splits == 1 here: w_static is off for split-K launches)
-      mbar_arrive_expect_tx(&full_bar[w_pre], SLOT_BYTES);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[w_pre], SLOT_BYTES);
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        load_b(smem + w_pre * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES, &full_bar[w_pre], kb + g, m_blk, n_blk);
+        for (int g = 0; g < G; ++g)
+          load_b(smem + w_pre * SLOT_BYTES + g * Cfg::STAGE_BYTES + Cfg::A_BYTES, &full_bar[w_pre], kb + g, m_blk, n_blk);
+      }
+      __syncwarp();
       ++w_pre;
       kb += G;
       if (kb == num_kb) { kb = 0; tile += t_step; }
@@ -340,8 +343,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      GEMM_STAMP(1);
+    // (whole warp, one elected lane issues: see the MMA issuer — a TMA load under `lane == 0` costs the same
+    // ELECT / R2UR.BROADCAST loop per instruction)
+    {
+      if (elect_one()) GEMM_STAMP(1);
       int s = 0;
       uint32_t ph = 0;
       for (int tile = t_begin; tile < t_end; tile += t_step) {
@@ -350,34 +355,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb0 + num_kb; kb += G) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* slot = smem + s * SLOT_BYTES;
-          if (CG == 2) {
-            // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
-            // to the LEADER's full barrier, on which only the leader arrives
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * SLOT_BYTES);
+          if (elect_one()) {
+            if (CG == 2) {
+              // each CTA loads its own 128 rows of A and its half of the W tile; every byte of the pair is credited
+              // to the LEADER's full barrier, on which only the leader arrives
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * SLOT_BYTES);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
-              tma_load_2d_pair(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * TILE_M + (int)cta_rank * BM);
-              load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
-            }
-          } else if (w_pre > 0) {
-            // transaction bytes announced and W tiles issued before the dependency wait: only A is left
-            --w_pre;
+              for (int g = 0; g < G; ++g) {
+                uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
+                tma_load_2d_pair(sa, &tmA, &full_bar[s], a_col(kb + g), m_blk * TILE_M + (int)cta_rank * BM);
+                load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
+              }
+            } else if (w_pre > 0) {
+              // transaction bytes announced and W tiles issued before the dependency wait: only A is left
 #pragma unroll
-            for (int g = 0; g < G; ++g)
-              load_a(slot + g * Cfg::STAGE_BYTES, &full_bar[s], kb + g, m_blk * BM);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], SLOT_BYTES);
+              for (int g = 0; g < G; ++g)
+                load_a(slot + g * Cfg::STAGE_BYTES, &full_bar[s], kb + g, m_blk * BM);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], SLOT_BYTES);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
-              load_a(sa, &full_bar[s], kb + g, m_blk * BM);
-              load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
+              for (int g = 0; g < G; ++g) {
+                uint8_t* sa = slot + g * Cfg::STAGE_BYTES;
+                load_a(sa, &full_bar[s], kb + g, m_blk * BM);
+                load_b(sa + Cfg::A_BYTES, &full_bar[s], kb + g, m_blk, n_blk);
+              }
             }
           }
+          __syncwarp();
+          if (CG != 2 && w_pre > 0) --w_pre;
           if (++s == SLOTS) {
             s = 0;
-            if (ph == 0) GEMM_STAMP(7);   // first pass over the ring issued (tools/gemm_phases.py: "ring-issued")
+            if (ph == 0 && elect_one()) GEMM_STAMP(7);   // first pass over the ring issued (tools/gemm_phases.py: "ring-issued")
             ph ^= 1;
           }
         }
@@ -385,8 +393,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {
+    // The WHOLE warp runs this loop with warp-uniform values and one ELECTED lane issues. Under `lane == 0` the compiler
+    // cannot keep descriptors and addresses in uniform registers: it wrapped every tcgen05.mma / commit in an ELECT /
+    // R2UR.BROADCAST loop of ~14 instructions (cuobjdump: 3.8 R2UR.BROADCAST per UTCHMMA), ~120 clocks per MMA — hidden
+    // behind a 256-wide MMA, but the pace of every narrower tile (the "0.25 us per k-block whatever the shape" of the
+    // small-batch regime and the "260-clock mbarrier probe" of round 1's microbenchmark were this loop).
+    if (cta_rank == 0) {
       const uint32_t idesc = p.ab_f16 ? make_idesc(FMT_F16, TILE_M, BN, 0, 0) : make_idesc(FMT_BF16, TILE_M, BN, 0, 0);
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -395,33 +410,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base_u + acc * BN;
         for (int kb = 0; kb < num_kb; kb += G) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (it == 0 && kb == 0) GEMM_STAMP(2);
+          if (elect_one()) {
+            if (it == 0 && kb == 0) GEMM_STAMP(2);
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const uint32_t sa = smem_u32(smem + s * SLOT_BYTES + g * Cfg::STAGE_BYTES);
-            const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
-            const uint64_t b_desc = make_sdesc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+            for (int g = 0; g < G; ++g) {
+              const uint32_t sa = smem_u + s * SLOT_BYTES + g * Cfg::STAGE_BYTES;
+              const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
+              const uint64_t b_desc = make_sdesc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k) {
-              // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
-              const uint32_t accum = ((kb + g) | k) != 0 ? 1u : 0u;
-              if (CG == 2) mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
-              else mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+              for (int k = 0; k < GEMM_BK / 16; ++k) {
+                // +32 bytes (= 2 in the >>4 address field) per K=16 step inside the 128-byte swizzle row
+                const uint32_t accum = ((kb + g) | k) != 0 ? 1u : 0u;
+                if (CG == 2) mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+                else mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+              }
             }
+            // frees this ring slot (in both CTAs of a pair) once the MMAs above have read it
+            if (CG == 2) tc_commit_pair(&empty_bar[s]);
+            else tc_commit(&empty_bar[s]);
           }
-          // frees this ring slot (in both CTAs of a pair) once the MMAs above have read it
-          if (CG == 2) tc_commit_pair(&empty_bar[s]);
-          else tc_commit(&empty_bar[s]);
+          __syncwarp();
           if (++s == SLOTS) { s = 0; ph ^= 1; }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if (CG == 2) tc_commit_pair(&tmem_full_bar[acc]);
-        else tc_commit(&tmem_full_bar[acc]);
-        if (it == 0) GEMM_STAMP(3);
+        if (elect_one()) {
+          if (CG == 2) tc_commit_pair(&tmem_full_bar[acc]);
+          else tc_commit(&tmem_full_bar[acc]);
+          if (it == 0) GEMM_STAMP(3);
+        }
+        __syncwarp();
       }
     }
   } else {
