@@ -133,7 +133,7 @@ ae_query_kernel(const __grid_constant__ CUtensorMap tmWpe, const __grid_constant
     // ===================== TMA producer: 4 W_pe tiles then 4 x 8 K' tiles per query tile =====================
     // (this CTA's row slice of every tile, multicast to the whole cluster; the tile is complete in a CTA when all
     // AQ_CLUSTER slices have landed = AQ_STAGE_BYTES on its own full barrier)
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -162,7 +162,7 @@ ae_query_kernel(const __grid_constant__ CUtensorMap tmWpe, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       constexpr uint32_t idesc = make_idesc(FMT_BF16, 128, 128, 0, 0);
       int s = 0;
       uint32_t ph = 0;

@@ -124,7 +124,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       uint32_t kv_ph = 0;
       int qn = 0;  // running tile counter -> Q ring slot / phase
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -155,7 +155,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       const uint32_t idesc_o = make_idesc(FMT_F16, ATT_BM, ATT_D, 0, 1);  // P fp16 (TMEM) x V fp16 (smem)
       const uint32_t idesc_s = make_idesc(FMT_BF16, ATT_BM, p.half, 0, 0);
       uint32_t kv_ph = 0;

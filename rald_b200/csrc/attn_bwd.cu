@@ -125,7 +125,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       const int r_row = frame * p.r_frame_rows + rt * 128;
       mbar_arrive_expect_tx(r_full, 2 * AB_TILE);
       tma_load_2d(sR1, &tmR1, r_full, head * 64, r_row);
@@ -143,7 +143,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       mbar_wait(r_full, 0);
       tc_fence_after();
       const uint64_t r1_desc = make_sdesc_sw128(smem_u32(sR1), 16, 1024);

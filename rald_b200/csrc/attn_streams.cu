@@ -126,7 +126,7 @@ attn_d64_streams_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       uint32_t it = 0;   // items of this CTA
       uint32_t qn = 0;   // query tiles of this CTA
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {

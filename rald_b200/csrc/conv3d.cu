@@ -97,7 +97,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -133,7 +133,7 @@ conv3d_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / coordinates in uniform registers (no ELECT / R2UR.BROADCAST loop per tcgen05 / TMA instruction)
       constexpr uint32_t idesc = make_idesc(FMT_BF16, CV_BM, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;

@@ -590,7 +590,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) release_acc();
           }
           if (live) {
-            if (lane == 0) bulk_wait_group_read<0>();  // the staging tile about to be overwritten was read
+            // (the elected lane — always the same one for the full mask — owns this warp's bulk groups; `lane == 0` would
+            // cost an ELECT / R2UR.BROADCAST loop per TMA store)
+            if (elect_one()) bulk_wait_group_read<0>();  // the staging tile about to be overwritten was read
             __syncwarp();
             const uint32_t sdst = smem_u32(stg + ew * STG_BYTES) + lane * 128;
 #pragma unroll
@@ -598,7 +600,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
               const int ocol = OUT_MODE == 2 ? ((n_blk * BN + acol0) >> 1) : (n_blk * BN + acol0);
               const void* src = stg + ew * STG_BYTES;
               if (EPI == EPI_TMA_REDUCE) tma_reduce_add_2d(&tmO, src, ocol, row0);
@@ -610,7 +612,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (it == 0 && threadIdx.x == 64) GEMM_STAMP(5);
     }
-    if (EPI != EPI_GENERIC && lane == 0) bulk_wait_group<0>();  // smem must outlive the last store
+    if (EPI != EPI_GENERIC && elect_one()) bulk_wait_group<0>();  // smem must outlive the last store
   }
 
   tc_fence_before();

@@ -124,7 +124,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA: its xn rows, its share of the B tiles) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int ut = unit; ut < unit_tiles; ut += num_units) {
@@ -184,7 +184,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (the leader CTA only when CG = 2) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc(FMT_BF16, XA_BM * CG, 256, 0, 0);
       constexpr uint32_t idesc_o = make_idesc(FMT_F16, XA_BM * CG, 128, 0, 0);   // P fp16 (TMEM) x VT fp16 (smem)
       auto commit = [&](uint64_t* bar) {
@@ -360,7 +360,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + bs[j]);
           uint8_t* my_stg = my_stg0 + sbuf * 4096;
-          if (lane == 0) bulk_wait_group_read<1>();   // the store issued two chunks ago has been read
+          if (elect_one()) bulk_wait_group_read<1>();   // the store issued two chunks ago has been read (elected lane: owns the bulk groups)
           __syncwarp();
           const uint32_t sdst = smem_u32(my_stg) + lane * 128;
 #pragma unroll
@@ -368,7 +368,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             st_shared_v4(sdst + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             // (reading the residual chunk into registers ahead of the accumulator and issuing a plain TMA store was
             // measured slower than the L2-side reduction: 69 vs 56 us per launch)
             tma_reduce_add_2d(&tmO, my_stg, q * 128 + c * 32, row0);
@@ -379,7 +379,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       if (warp == 2 && lane == 0) XA_STAMP(14);
     }
-    if (lane == 0) bulk_wait_group<0>();
+    if (elect_one()) bulk_wait_group<0>();
   }
 
   tc_fence_before();
