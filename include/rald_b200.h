@@ -142,7 +142,9 @@ int rald_attn_d64_long(const void* Q, int64_t ldq, const void* K, int64_t ldk, c
 /* out = LN(x) * g + b over rows of 512 fp32 values (eps inside the rsqrt). gamma_plus_one=1 gives the adaLN
  * modulation LN(x)*(1+scale)+shift of AdaLayerNorm.forward (model/models_radar_generation.py:127-131) with
  * gamma/beta = scale/shift of frame f at gamma + f*mod_frame_stride (stride 0 = shared); gamma_plus_one=0 is
- * nn.LayerNorm with affine weights (model/models_ae.py:38-47). out_f32=0 writes bf16. */
+ * nn.LayerNorm with affine weights (model/models_ae.py:38-47). out_f32=0 writes bf16. gamma / beta are fetched BEFORE the
+ * kernel's programmatic-dependency wait (they are constants of a sampling / training step): they must not be written by the
+ * launch that immediately precedes this one on the stream (x may be). */
 int rald_ln_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, int64_t mod_frame_stride,
                  int rows_per_frame, int gamma_plus_one, void* out, int64_t ldo, int out_f32, int64_t rows, int D,
                  float eps, void* stream);

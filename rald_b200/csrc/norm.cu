@@ -19,6 +19,23 @@ ln_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  // The modulation / affine vectors are constants of the step (adaLN table: written at least two launches earlier;
+  // a kernel is only launched once its predecessor is past its own dependency wait, i.e. once everything before THAT
+  // has completed): fetch them for this warp's first row BEFORE the dependency wait. At small batch a warp normalises one
+  // row, and this L2 round trip (after the statistics) was a serial ~0.5 us of each of the 72 LayerNorms of an evaluation.
+  const float one = gamma_plus_one ? 1.0f : 0.0f;
+  float4 g[NCH], b[NCH];
+  int64_t f_held = -1;
+  if (warp_global < rows) {
+    f_held = rows_per_frame > 0 ? warp_global / rows_per_frame : 0;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + f_held * mod_frame_stride);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + f_held * mod_frame_stride);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      g[j] = __ldg(g4 + j * 32 + lane);
+      b[j] = __ldg(b4 + j * 32 + lane);
+    }
+  }
   pdl_wait();
   pdl_launch_dependents();
   for (int64_t row = warp_global; row < rows; row += warps_total) {
@@ -26,6 +43,17 @@ ln_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
     float4 v[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) v[j] = xr[j * 32 + lane];
+    const int64_t f = rows_per_frame > 0 ? row / rows_per_frame : 0;
+    if (f != f_held) {   // warp-uniform
+      f_held = f;
+      const float4* g4 = reinterpret_cast<const float4*>(gamma + f * mod_frame_stride);
+      const float4* b4 = reinterpret_cast<const float4*>(beta + f * mod_frame_stride);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        g[j] = __ldg(g4 + j * 32 + lane);
+        b[j] = __ldg(b4 + j * 32 + lane);
+      }
+    }
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -37,18 +65,12 @@ ln_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
       ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
     }
     const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
-    const int64_t f = rows_per_frame > 0 ? row / rows_per_frame : 0;
-    const float4* g4 = reinterpret_cast<const float4*>(gamma + f * mod_frame_stride);
-    const float4* b4 = reinterpret_cast<const float4*>(beta + f * mod_frame_stride);
-    const float one = gamma_plus_one ? 1.0f : 0.0f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-      const float4 g = __ldg(g4 + j * 32 + lane);
-      const float4 b = __ldg(b4 + j * 32 + lane);
-      const float o0 = v[j].x * rstd * (g.x + one) + b.x;
-      const float o1 = v[j].y * rstd * (g.y + one) + b.y;
-      const float o2 = v[j].z * rstd * (g.z + one) + b.z;
-      const float o3 = v[j].w * rstd * (g.w + one) + b.w;
+      const float o0 = v[j].x * rstd * (g[j].x + one) + b[j].x;
+      const float o1 = v[j].y * rstd * (g[j].y + one) + b[j].y;
+      const float o2 = v[j].z * rstd * (g[j].z + one) + b[j].z;
+      const float o3 = v[j].w * rstd * (g[j].w + one) + b[j].w;
       if (OUT_F32) {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * ldo)[j * 32 + lane] =
             make_float4(o0, o1, o2, o3);
