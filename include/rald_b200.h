@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RALD_ABI_VERSION 4
+#define RALD_ABI_VERSION 5
 
 int rald_abi_version(void);
 const char* rald_last_error(void);
@@ -164,12 +164,22 @@ int rald_dit_mod_table(const float* sigma, int S, const float* freqs, int half, 
  *   mode 2: d' = (x - D)/sigma; x_out = x_base + (sigma - sigma_other)(d_buf/2 + d'/2)  (Heun, :272-273)
  *   mode 3: x_out = x * sigma (:252);  mode 4: nothing (projection only)
  *   then, if h_next != NULL: h_next = proj_in(c_in(sigma_next) * x_out) (:221, :427) for the next evaluation.
- * w_out_t: fp32 [dim][32] (proj_out transposed, zero padded); w_in_t: fp32 [C][dim]. */
+ * w_out_t: fp32 [dim][32] (proj_out transposed, zero padded); w_in_t: fp32 [C][dim]. T and rows-per-frame are
+ * multiples of 16 (the row tile). pack: rald_dit_boundary_pack's image of the four weight arrays, or NULL (the raw
+ * weights are then split and packed by an extra launch in front of every call). The projections multiply split-bf16
+ * operands (hi + lo halves, 16+ mantissa bits) with fp32 accumulation; the update arithmetic is fp32. */
 int rald_dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t,
                       const float* w_in_t, const float* x_in, const float* x_base, float* d_buf, float* x_out,
                       float* h_next, const float* sigma, int64_t sigma_stride, const float* sigma_other,
                       int64_t sigma_other_stride, int mode, int rows_per_frame, int C, int64_t T, int dim,
-                      float sigma_data, void* stream);
+                      float sigma_data, const void* pack, void* stream);
+
+/* The weights of rald_dit_boundary split into bf16 hi + lo halves, packed and laid out in the order the kernel's tensor-core
+ * fragments read them, plus the column sums the algebraic LayerNorm needs: rald_dit_boundary_pack_bytes() bytes at a
+ * 16-byte aligned `pack`. Made once per weight version by the runtimes (rald_dit_weights.boundary_pack). */
+int64_t rald_dit_boundary_pack_bytes(void);
+int rald_dit_boundary_pack(const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t, int C,
+                           void* pack, void* stream);
 
 /* Radar conditioning tokens: Linear(cz -> dim) of the encoder output [B, nr, na, ne, cz] (channels last) plus the
  * range / azimuth / elevation embeddings (model/models_radar_generation.py:390-405). Either output may be NULL. */
@@ -200,6 +210,8 @@ typedef struct rald_dit_weights {
   const float* ln_b;   /* [dim] */
   const float* proj_in_t;   /* [channels][dim]  proj_in.weight transposed */
   const float* proj_out_t;  /* [dim][32]        proj_out.weight transposed, zero padded to 32 */
+  const void* boundary_pack; /* optional: rald_dit_boundary_pack's image of (ln_w, ln_b, proj_out_t, proj_in_t), made once
+                              * per weight version; NULL = the evaluation boundary packs the raw weights on every launch */
 } rald_dit_weights;
 
 typedef struct rald_dit_workspace {

@@ -58,7 +58,9 @@ _SIGNATURES = {
     "rald_dit_mod_table": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "rald_dit_boundary": [c_void_p] * 10 + [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_i64, c_int, c_f32,
-                                            c_void_p],
+                                            c_void_p, c_void_p],
+    "rald_dit_boundary_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "rald_dit_boundary_pack_bytes": [],
     "rald_radar_tokens": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "rald_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_int,
@@ -117,7 +119,8 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"rald_last_error": ctypes.c_char_p, "rald_launch_count_add": None, "rald_launch_count": ctypes.c_uint64,
-             "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64, "rald_chamfer_ws_elems": c_i64}
+             "rald_occupancy_ws_elems": c_i64, "rald_prof_dump": c_i64, "rald_chamfer_ws_elems": c_i64,
+             "rald_dit_boundary_pack_bytes": c_i64}
 
 
 class RaldError(RuntimeError):
@@ -186,6 +189,10 @@ def cur_stream() -> int:
 
 FAMILIES = {"gemm": 0, "attn": 1, "ln": 2, "boundary": 3, "conv3d": 4, "gn": 5, "ae_query": 6, "other": 7, "fps": 8,
             "xattn": 9}
+
+
+def boundary_pack_bytes() -> int:
+    return int(lib().rald_dit_boundary_pack_bytes())
 
 
 def launch_count() -> int:

@@ -71,10 +71,17 @@ int rald_dit_boundary(const float* h, const float* ln_w, const float* ln_b, cons
                       const float* w_in_t, const float* x_in, const float* x_base, float* d_buf, float* x_out,
                       float* h_next, const float* sigma, int64_t sigma_stride, const float* sigma_other,
                       int64_t sigma_other_stride, int mode, int rows_per_frame, int C, int64_t T, int dim,
-                      float sigma_data, void* stream) {
+                      float sigma_data, const void* pack, void* stream) {
   return rald::dit_boundary(h, ln_w, ln_b, w_out_t, w_in_t, x_in, x_base, d_buf, x_out, h_next, sigma, sigma_stride,
                             sigma_other, sigma_other_stride, mode, rows_per_frame, C, T, dim, sigma_data,
-                            static_cast<cudaStream_t>(stream));
+                            static_cast<cudaStream_t>(stream), pack);
+}
+
+int64_t rald_dit_boundary_pack_bytes(void) { return rald::dit_boundary_pack_bytes(); }
+
+int rald_dit_boundary_pack(const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t, int C,
+                           void* pack, void* stream) {
+  return rald::dit_boundary_pack(ln_w, ln_b, w_out_t, w_in_t, C, pack, static_cast<cudaStream_t>(stream));
 }
 
 int rald_radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const float* w, const float* b,

@@ -171,13 +171,13 @@ extern "C" int rald_dit_forward(const rald_dit_weights* w, const rald_dit_worksp
     const float* md = mod + (int64_t)f0 * mod_frame_stride;
     // h = proj_in(c_in(sigma) * x)
     RALD_TRY(dit_boundary(nullptr, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, xin, nullptr, nullptr, nullptr,
-                          ws->h, sg, sigma_stride, nullptr, 0, 4, M, C, T, dim, w->sigma_data, st));
+                          ws->h, sg, sigma_stride, nullptr, 0, 4, M, C, T, dim, w->sigma_data, st, w->boundary_pack));
     RALD_TRY(run_blocks(*w, *ws, md, mod_frame_stride,
                         reinterpret_cast<const __nv_bfloat16*>(ctxkv) + (int64_t)f0 * ctx_rows * w->depth * 2 * dim, nf,
                         f0, st));
     RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, xin, nullptr, nullptr,
                           out + (int64_t)f0 * M * C, nullptr, sg, sigma_stride, nullptr, 0, 0, M, C, T, dim,
-                          w->sigma_data, st));
+                          w->sigma_data, st, w->boundary_pack));
   }
   return 0;
 }
@@ -201,7 +201,7 @@ extern "C" int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspa
     float* d_cur = ws->d_tmp;
     // x_0 = latents * t_0 ; h = proj_in(c_in(t_0) x_0)
     RALD_TRY(dit_boundary(nullptr, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, latents + off, nullptr, nullptr,
-                          x_hat, ws->h, sigmas, 0, nullptr, 0, 3, M, C, T, dim, w->sigma_data, st));
+                          x_hat, ws->h, sigmas, 0, nullptr, 0, 3, M, C, T, dim, w->sigma_data, st, w->boundary_pack));
     for (int i = 0; i < num_steps; ++i) {
       const float* t_cur = sigmas + i;
       const float* t_next = sigmas + i + 1;
@@ -210,12 +210,12 @@ extern "C" int rald_dit_sample(const rald_dit_weights* w, const rald_dit_workspa
       RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)i * mod_step, 0, ctx, nf, f0, st));
       RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, x_hat, nullptr, d_cur,
                             last ? x_hat : x_e, last ? nullptr : ws->h, t_cur, 0, t_next, 0, 1, M, C, T, dim,
-                            w->sigma_data, st));
+                            w->sigma_data, st, w->boundary_pack));
       if (!last) {
         // Heun correction at t_next
         RALD_TRY(run_blocks(*w, *ws, mod + (int64_t)(i + 1) * mod_step, 0, ctx, nf, f0, st));
         RALD_TRY(dit_boundary(ws->h, w->ln_w, w->ln_b, w->proj_out_t, w->proj_in_t, x_e, x_hat, d_cur, x_hat, ws->h,
-                              t_next, 0, t_cur, 0, 2, M, C, T, dim, w->sigma_data, st));
+                              t_next, 0, t_cur, 0, 2, M, C, T, dim, w->sigma_data, st, w->boundary_pack));
       }
       if (trace != nullptr) {
         RALD_CHECK_CUDA(cudaMemcpyAsync(trace + ((int64_t)i * frames * M * C) + off, x_hat, T * C * sizeof(float),

@@ -107,7 +107,11 @@ int dit_mod_table(const float* sigma, int S, const float* freqs, int half, const
 int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t,
                  const float* x_in, const float* x_base, float* d_buf, float* x_out, float* h_next,
                  const float* sigma, int64_t sigma_stride, const float* sigma_other, int64_t sigma_other_stride,
-                 int mode, int rows_per_frame, int C, int64_t T, int dim, float sigma_data, cudaStream_t stream);
+                 int mode, int rows_per_frame, int C, int64_t T, int dim, float sigma_data, cudaStream_t stream,
+                 const void* pack = nullptr);   // pack: dit_boundary_pack's image of the weights (null: packed on the fly)
+int dit_boundary_pack(const float* ln_w, const float* ln_b, const float* w_out_t, const float* w_in_t, int C,
+                      void* pack, cudaStream_t stream);
+int64_t dit_boundary_pack_bytes();
 int radar_tokens(const float* feat, int B, int nr, int na, int ne, int cz, const float* w, const float* b,
                  const float* r_emb, const float* a_emb, const float* e_emb, int dim, float* tok_f32, void* tok_bf16,
                  cudaStream_t stream);

@@ -24,7 +24,8 @@ class DitWeights(ctypes.Structure):
                 ("w_qkv", c_void_p), ("w_o1", c_void_p), ("w_q2", c_void_p), ("w_o2", c_void_p),
                 ("w_ff1", c_void_p), ("w_ff2", c_void_p),
                 ("b_o1", c_void_p), ("b_o2", c_void_p), ("b_ff1", c_void_p), ("b_ff2", c_void_p),
-                ("ln_w", c_void_p), ("ln_b", c_void_p), ("proj_in_t", c_void_p), ("proj_out_t", c_void_p)]
+                ("ln_w", c_void_p), ("ln_b", c_void_p), ("proj_in_t", c_void_p), ("proj_out_t", c_void_p),
+                ("boundary_pack", c_void_p)]
 
 
 class DitWorkspace(ctypes.Structure):
@@ -163,6 +164,10 @@ class DitRuntime(_lib.RuntimeNotCopied):
             pot = torch.zeros(dim, 32, device=dev, dtype=torch.float32)
             pot[:, :C] = m.proj_out.weight.detach().float().t()
             self.proj_out_t = pot
+            # the evaluation boundary's weights, split / packed once per weight version (csrc/dit_misc.cu)
+            self.boundary_pack = torch.empty(_lib.boundary_pack_bytes(), device=dev, dtype=torch.uint8)
+            _lib.call("rald_dit_boundary_pack", self.ln_w.data_ptr(), self.ln_b.data_ptr(), self.proj_out_t.data_ptr(),
+                      self.proj_in_t.data_ptr(), C, self.boundary_pack.data_ptr(), _lib.cur_stream())
             half = m.t_channels // 2
             # frequencies exactly as the reference computes them (models_radar_generation.py:28-30), fp32
             fr = torch.arange(half, dtype=torch.float32, device=dev) / half
@@ -181,7 +186,7 @@ class DitRuntime(_lib.RuntimeNotCopied):
         w.sigma_data = float(self.module.sigma_data)
         w.precise = 1 if self.precise else 0
         for name in ("w_qkv", "w_o1", "w_q2", "w_o2", "w_ff1", "w_ff2", "b_o1", "b_o2", "b_ff1", "b_ff2", "ln_w", "ln_b",
-                     "proj_in_t", "proj_out_t"):
+                     "proj_in_t", "proj_out_t", "boundary_pack"):
             setattr(w, name, getattr(self, name).data_ptr())
         return w
 

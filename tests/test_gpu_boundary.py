@@ -1,0 +1,164 @@
+"""Evaluation-boundary kernel (`rald_dit_boundary`, csrc/dit_misc.cu) through the C ABI against an fp64 torch
+restatement of the reference statements it fuses: final LayerNorm + proj_out (models_radar_generation.py:230-232),
+EDM preconditioning (:422-429), Euler / Heun update (:265-273), x_0 = latents * t_0 (:252) and the next evaluation's
+proj_in(c_in x) (:221, :427). Bar: the kernel multiplies split-bf16 operands (hi + lo halves, 16+ mantissa bits) on the
+tensor cores with fp32 accumulation and does the update arithmetic in fp32 — 3e-5 of the output's scale (measured
+~5e-6; the bf16 network that produces h is at 3e-3); batch invariance is bitwise."""
+import pytest
+import torch
+
+from rald_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+SD = 0.5
+TOL = 3e-5
+
+
+def _weights(C, seed=0, mean_shift=0.0):
+    g = torch.Generator("cuda").manual_seed(seed)
+    ln_w = 1.0 + 0.2 * torch.randn(512, device="cuda", generator=g)
+    ln_b = 0.1 * torch.randn(512, device="cuda", generator=g)
+    w_out = torch.randn(C, 512, device="cuda", generator=g) / 512 ** 0.5      # nn.Linear(512, C).weight
+    w_in = torch.randn(512, C, device="cuda", generator=g) / C ** 0.5         # nn.Linear(C, 512).weight
+    w_out_t = torch.zeros(512, 32, device="cuda")
+    w_out_t[:, :C] = w_out.t()
+    return ln_w, ln_b, w_out, w_in, w_out_t.contiguous(), w_in.t().contiguous()
+
+
+def _reference(mode, h, ln_w, ln_b, w_out, w_in, x, xb, d, sig, sig_o, rows):
+    """fp64 restatement; sig / sig_o per frame [B]."""
+    T, C = x.shape
+    s = sig.double().repeat_interleave(rows)[:, None]
+    so = sig_o.double().repeat_interleave(rows)[:, None]
+    x = x.double()
+    out = {}
+    s_next = s
+    if mode == 3:
+        xo = x * s
+    elif mode == 4:
+        xo = x
+    else:
+        hn = torch.nn.functional.layer_norm(h.double(), (512,), ln_w.double(), ln_b.double(), 1e-5)
+        F = hn @ w_out.double().t()
+        c_skip = SD ** 2 / (s ** 2 + SD ** 2)
+        c_out = s * SD / (s ** 2 + SD ** 2).sqrt()
+        D = c_skip * x + c_out * F
+        if mode == 0:
+            xo = D
+        elif mode == 1:
+            dd = (x - D) / s
+            xo = x + (so - s) * dd
+            out["d"] = dd
+            s_next = so
+        else:
+            dp = (x - D) / s
+            xo = xb.double() + (s - so) * (0.5 * d.double() + 0.5 * dp)
+    out["x"] = xo
+    c_in = 1.0 / (SD ** 2 + s_next ** 2).sqrt()
+    out["h"] = (c_in * xo) @ w_in.double().t()
+    return out
+
+
+def _pack(wts, C):
+    ln_w, ln_b, _, _, w_out_t, w_in_t = wts
+    pack = torch.empty(_lib.boundary_pack_bytes(), device="cuda", dtype=torch.uint8)
+    _lib.call("rald_dit_boundary_pack", ln_w.data_ptr(), ln_b.data_ptr(), w_out_t.data_ptr(), w_in_t.data_ptr(), C,
+              pack.data_ptr(), _lib.cur_stream())
+    return pack
+
+
+def _run(mode, h, wts, x, xb, d, sig, sig_o, rows, C, want_next=True, in_place=False, pack=None):
+    ln_w, ln_b, _, _, w_out_t, w_in_t = wts
+    T = x.shape[0]
+    x_out = torch.full_like(x, float("nan"))
+    d_buf = d.clone() if d is not None else torch.full_like(x, float("nan"))
+    h_next = h if in_place else torch.full((T, 512), float("nan"), device="cuda")
+    _lib.call("rald_dit_boundary", 0 if h is None else h.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+              w_out_t.data_ptr(), w_in_t.data_ptr(), x.data_ptr(), 0 if xb is None else xb.data_ptr(),
+              d_buf.data_ptr(), x_out.data_ptr(), h_next.data_ptr() if want_next else 0,
+              sig.data_ptr(), 1, sig_o.data_ptr(), 1, mode, rows, C, T, 512, SD, 0 if pack is None else pack.data_ptr(),
+              _lib.cur_stream())
+    torch.cuda.synchronize()
+    return x_out, d_buf, h_next
+
+
+def _err(a, ref):
+    ref = ref.double()
+    e = float((a.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    print(f"boundary max-abs error / max |ref| = {e:.2e}")
+    return e
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("frames,C", [(1, 32), (3, 32), (64, 32), (2, 8), (2, 5)])
+def test_boundary_modes_match_fp64(mode, frames, C):
+    rows = 512
+    T = frames * rows
+    g = torch.Generator("cuda").manual_seed(mode * 100 + frames)
+    wts = _weights(C, seed=frames)
+    # residual stream with a row mean several standard deviations from zero and a few massive channels
+    h = torch.randn(T, 512, device="cuda", generator=g) * 3.0 + 4.0 * torch.randn(T, 1, device="cuda", generator=g)
+    h[:, 7] += 60.0
+    h[:, 0] -= 25.0
+    x = torch.randn(T, C, device="cuda", generator=g) * 2.0
+    xb = torch.randn(T, C, device="cuda", generator=g)
+    d = torch.randn(T, C, device="cuda", generator=g)
+    sig = torch.rand(frames, device="cuda", generator=g) * 10 + 0.05
+    sig_o = sig * 0.7
+    ref = _reference(mode, h, wts[0], wts[1], wts[2], wts[3], x, xb, d, sig, sig_o, rows)
+    x_out, d_buf, h_next = _run(mode, None if mode >= 3 else h, wts, x, xb, d if mode == 2 else None, sig, sig_o,
+                                rows, C)
+    assert _err(x_out, ref["x"]) < TOL
+    assert _err(h_next, ref["h"]) < TOL
+    if mode == 1:
+        assert _err(d_buf, ref["d"]) < TOL
+
+
+def test_boundary_in_place_and_without_projection():
+    """Heun step as the sampler issues it (h_next == h, dit.cu) and mode 0 without the next projection."""
+    rows, frames, C = 512, 4, 32
+    T = rows * frames
+    g = torch.Generator("cuda").manual_seed(5)
+    wts = _weights(C, seed=9)
+    h = torch.randn(T, 512, device="cuda", generator=g)
+    x, xb, d = (torch.randn(T, C, device="cuda", generator=g) for _ in range(3))
+    sig = torch.rand(frames, device="cuda", generator=g) + 0.1
+    sig_o = sig * 1.3
+    a = _run(2, h.clone(), wts, x, xb, d, sig, sig_o, rows, C)
+    hh = h.clone()
+    b = _run(2, hh, wts, x, xb, d, sig, sig_o, rows, C, in_place=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], hh)
+    c = _run(0, h.clone(), wts, x, xb, None, sig, sig_o, rows, C, want_next=False)
+    ref = _reference(0, h, wts[0], wts[1], wts[2], wts[3], x, xb, d, sig, sig_o, rows)
+    assert _err(c[0], ref["x"]) < TOL
+    assert torch.isnan(c[2]).all()   # untouched
+
+
+def test_boundary_batch_invariance_bitwise():
+    """A frame's rows get the same bits alone (32 tiles on 32 CTAs) and inside a 64-frame batch (4 tiles in flight
+    per CTA): the sharded multi-GPU job relies on it (bench.py sharding_check)."""
+    rows, frames, C = 512, 64, 32
+    T = rows * frames
+    g = torch.Generator("cuda").manual_seed(11)
+    wts = _weights(C, seed=3)
+    h = torch.randn(T, 512, device="cuda", generator=g) * 2
+    x, xb, d = (torch.randn(T, C, device="cuda", generator=g) for _ in range(3))
+    sig = torch.rand(frames, device="cuda", generator=g) * 5 + 0.1
+    sig_o = sig * 0.8
+    pack = _pack(wts, C)   # the runtimes' path (packed once); the single-frame runs below pack on the fly
+    full = _run(1, h, wts, x, xb, None, sig, sig_o, rows, C, pack=pack)
+    for f in (0, 17, 63):
+        sl = slice(f * rows, (f + 1) * rows)
+        one = _run(1, h[sl].contiguous(), wts, x[sl].contiguous(), xb[sl].contiguous(), None, sig[f:f + 1].contiguous(),
+                   sig_o[f:f + 1].contiguous(), rows, C)
+        for a, b in zip(full, one):
+            assert torch.equal(a[sl], b)
+
+
+def test_boundary_rejects_ragged_tiles():
+    wts = _weights(32)
+    x = torch.zeros(24, 32, device="cuda")
+    sig = torch.ones(1, device="cuda")
+    with pytest.raises(_lib.RaldError):
+        _run(4, None, wts, x, None, None, sig, sig, 24, 32)
