@@ -146,11 +146,10 @@ struct BoundaryParams {
 // Every row's arithmetic is independent of the tile it sits in and of the batch: a frame computes bit-identical values
 // alone and in a batch. Weights sit in shared memory split, packed and in fragment order (hi and lo halves of an
 // element take the 32 bits the fp32 value took: two conflict-free LDS.128 per 6 MMAs).
-constexpr int BD_GROUPS = 4;                 // 16-row tiles in flight per CTA
-constexpr int BD_THREADS = BD_GROUPS * 128;  // four warps per tile
+constexpr int BD_MAX_GROUPS = 4;             // 16-row tiles in flight per CTA (four warps each)
 constexpr int BD_PART = 20;                  // 16 accumulators + 4 moments per lane
 constexpr int BD_PACK_WORDS = 16384 + 16384 + 64;   // W' | W_in | column sums of W' | ln_b W_out^T
-constexpr int BD_SMEM_WORDS = BD_PACK_WORDS + BD_GROUPS * 4 * BD_PART * 32 + BD_GROUPS * 16 * 32 + 4;
+constexpr int BD_SMEM_WORDS = BD_PACK_WORDS + BD_MAX_GROUPS * 4 * BD_PART * 32 + BD_MAX_GROUPS * 16 * 32 + 4;
 // word index of element (k, n) of W' = diag(ln_w) W_out^T: [kb = k/32][nt = n/8][hi | lo][lane = (n%8) 4 + (k%32)/8][e/2],
 // half e%2, e = k%8 — a lane's four hi words (then its four lo words) are one conflict-free LDS.128
 __device__ __forceinline__ int bd_wout_word(int k, int n, int hl) {
@@ -175,12 +174,6 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
   const float l1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(l0, l1);
   lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-__device__ __forceinline__ void mma_split(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
-                                          uint32_t b0h, uint32_t b1h, uint32_t b0l, uint32_t b1l) {
-  mma_bf16(d, alo, b0h, b1h);
-  mma_bf16(d, ahi, b0l, b1l);
-  mma_bf16(d, ahi, b0h, b1h);
 }
 __device__ __forceinline__ void group_barrier(int grp) {
   asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
@@ -251,7 +244,8 @@ __device__ __forceinline__ void boundary_load_rows(BoundaryRows& v, const float*
   v.kb = *reinterpret_cast<const float4*>(pb);
 }
 
-__global__ void __launch_bounds__(BD_THREADS, 1)
+template <int BD_GROUPS>
+__global__ void __launch_bounds__(BD_GROUPS * 128, 1)
 boundary_kernel(const BoundaryParams p) {
   extern __shared__ __align__(128) uint32_t smw[];
   uint32_t* s_wout = smw;              // the pack: W' ...
@@ -259,8 +253,8 @@ boundary_kernel(const BoundaryParams p) {
   const float* s_cs = reinterpret_cast<const float*>(smw + 32768);  // ... [32] column sums of W', [32] ln_b W_out^T
   const float* s_bw = s_cs + 32;
   float* s_part = reinterpret_cast<float*>(smw + BD_PACK_WORDS);    // [group][warp][BD_PART][lane]
-  uint32_t* s_xs = reinterpret_cast<uint32_t*>(s_part + BD_GROUPS * 4 * BD_PART * 32);  // [group][hi/lo 2][row 2][nt 4][lane]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_xs + BD_GROUPS * 16 * 32);
+  uint32_t* s_xs = reinterpret_cast<uint32_t*>(s_part + BD_MAX_GROUPS * 4 * BD_PART * 32);  // [group][hi/lo 2][row 2][nt 4][lane]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_xs + BD_MAX_GROUPS * 16 * 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 2, q = warp & 3, g = lane >> 2, t = lane & 3;
   const bool need_net = p.mode < 3;
@@ -350,14 +344,29 @@ boundary_kernel(const BoundaryParams p) {
           s1B += rb[e];
           s2B = fmaf(rb[e], rb[e], s2B);
         }
+        // consecutive MMAs go to different accumulators (an accumulator's next MMA is four instructions away)
+        uint4 whi[4], wlo[4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const uint4* wp = reinterpret_cast<const uint4*>(s_wout) + (kb * 4 + nt) * 64 + lane;
-          const uint4 whi = wp[0], wlo = wp[32];
-          mma_split(acc[nt], ahi[0], alo[0], whi.x, whi.y, wlo.x, wlo.y);
-          mma_split(acc[nt], ahi[1], alo[1], whi.z, whi.w, wlo.z, wlo.w);
+          whi[nt] = wp[0];
+          wlo[nt] = wp[32];
         }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], alo[0], whi[nt].x, whi[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ahi[0], wlo[nt].x, wlo[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ahi[0], whi[nt].x, whi[nt].y);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], alo[1], whi[nt].z, whi[nt].w);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ahi[1], wlo[nt].z, wlo[nt].w);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[nt], ahi[1], whi[nt].z, whi[nt].w);
       }
+      // ---- the next tile's rows start their way in under the reduction, phase 2 and phase 3 ----
+      if (tile + tile_step < n_tiles) boundary_load_rows(v, p.h, tile + tile_step, g, t, q);
       s1A += __shfl_xor_sync(0xffffffffu, s1A, 1);
       s2A += __shfl_xor_sync(0xffffffffu, s2A, 1);
       s1B += __shfl_xor_sync(0xffffffffu, s1B, 1);
@@ -441,8 +450,6 @@ boundary_kernel(const BoundaryParams p) {
       }
     }
     group_barrier(grp);  // c_in x_next is in shared memory; the partials may be overwritten by the next tile
-    // ---- the next tile's rows start their way in under phase 3 ----
-    if (need_net && tile + tile_step < n_tiles) boundary_load_rows(v, p.h, tile + tile_step, g, t, q);
     if (!need_next) continue;  // uniform over the CTA
     // ---- phase 3: h_next[:, 128 q : 128 q + 128] ----
     uint32_t xhi[2][4], xlo[2][4];   // [k16 step s][a0 .. a3]: channel tiles 2s (rows A, B), 2s + 1 (rows A, B)
@@ -459,33 +466,52 @@ boundary_kernel(const BoundaryParams p) {
     }
     float4* oA = reinterpret_cast<float4*>(p.h_next + rowA * 512) + t;
     float4* oB = reinterpret_cast<float4*>(p.h_next + rowB * 512) + t;
-#pragma unroll 4
-    for (int pp = 0; pp < 8; ++pp) {
+#pragma unroll 2
+    for (int pp = 0; pp < 8; pp += 2) {
+      // two column pairs at once: four independent accumulators
       const int pair = q * 8 + pp;
-      float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint4* wa = reinterpret_cast<const uint4*>(s_win + 16384) + pair * 128 + lane;
-      const uint4 ahi = wa[0], alo = wa[32], bhi = wa[64], blo = wa[96];
-      mma_split(ca, xhi[0], xlo[0], ahi.x, ahi.y, alo.x, alo.y);
-      mma_split(cb, xhi[0], xlo[0], bhi.x, bhi.y, blo.x, blo.y);
-      mma_split(ca, xhi[1], xlo[1], ahi.z, ahi.w, alo.z, alo.w);
-      mma_split(cb, xhi[1], xlo[1], bhi.z, bhi.w, blo.z, blo.w);
-      oA[pair * 4] = make_float4(ca[0], ca[1], cb[0], cb[1]);
-      oB[pair * 4] = make_float4(ca[2], ca[3], cb[2], cb[3]);
+      float c[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) c[a][0] = c[a][1] = c[a][2] = c[a][3] = 0.f;
+      const uint4* wp = reinterpret_cast<const uint4*>(s_win + 16384) + pair * 128 + lane;
+      uint4 whi[4], wlo[4];   // [pair pp: ab 0, 1 | pair pp + 1: ab 0, 1]
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        whi[a] = wp[a * 64];
+        wlo[a] = wp[a * 64 + 32];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xlo[0], whi[a].x, whi[a].y);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xhi[0], wlo[a].x, wlo[a].y);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xhi[0], whi[a].x, whi[a].y);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xlo[1], whi[a].z, whi[a].w);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xhi[1], wlo[a].z, wlo[a].w);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mma_bf16(c[a], xhi[1], whi[a].z, whi[a].w);
+      oA[pair * 4] = make_float4(c[0][0], c[0][1], c[1][0], c[1][1]);
+      oB[pair * 4] = make_float4(c[0][2], c[0][3], c[1][2], c[1][3]);
+      oA[pair * 4 + 4] = make_float4(c[2][0], c[2][1], c[3][0], c[3][1]);
+      oB[pair * 4 + 4] = make_float4(c[2][2], c[2][3], c[3][2], c[3][3]);
     }
   }
 }
 
+template <int GROUPS>
 static int launch_boundary(const BoundaryParams& p, int64_t T, cudaStream_t stream) {
   const int smem = BD_SMEM_WORDS * sizeof(uint32_t);
   static bool configured = false;
   if (!configured) {
-    RALD_CHECK_CUDA(cudaFuncSetAttribute(boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    RALD_CHECK_CUDA(cudaFuncSetAttribute(boundary_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  int64_t blocks = T / 16;  // one tile per CTA until every SM has one, then up to BD_GROUPS tiles in flight per SM
+  int64_t blocks = T / 16;  // one tile per CTA until every SM has one, then up to GROUPS tiles in flight per SM
   const int64_t cap = device_sm_count();
   if (blocks > cap) blocks = cap;
-  RALD_CHECK_CUDA(launch_pdl(boundary_kernel, dim3((unsigned)blocks), dim3(BD_THREADS), smem, stream, p));
+  RALD_CHECK_CUDA(launch_pdl(boundary_kernel<GROUPS>, dim3((unsigned)blocks), dim3(GROUPS * 128), smem, stream, p));
   return 0;
 }
 
@@ -541,7 +567,7 @@ int dit_boundary(const float* h, const float* ln_w, const float* ln_b, const flo
   p.rows_per_frame = rows_per_frame; p.C = C; p.T = T; p.sigma_data = sigma_data;
   ProfScope prof(FAM_BOUNDARY, stream, (double)T * (mode < 3 ? 2048.0 : 0.0) + (h_next ? (double)T * 2048.0 : 0.0) +
                                           (double)T * C * 16.0);
-  RALD_TRY(launch_boundary(p, T, stream));
+  RALD_TRY(launch_boundary<BD_MAX_GROUPS>(p, T, stream));  // three groups (168 registers) measured the same: 45.9 vs 44.9 us
   RALD_LAUNCHED();
   return 0;
 }
