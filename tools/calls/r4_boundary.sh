@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_gpu_boundary.py -x -q > gpurun_out/r4_boundary_test.log 2>&1; echo "rc=$?" >> gpurun_out/r4_boundary_test.log
-tail -3 gpurun_out/r4_boundary_test.log
-timeout 120 python tools/gpu_time_boundary.py 2>&1 | tee gpurun_out/r4_boundary_time.log
+for G in 4 3 4 3; do
+echo "groups=$G"
+RALD_B200_BOUNDARY_GROUPS=$G timeout 120 python tools/gpu_time_boundary.py 2>&1 | tee -a gpurun_out/r4_boundary_time_g$G.log
+done
