@@ -162,19 +162,6 @@ __device__ __forceinline__ int bd_win_word(int c, int col, int hl) {
   return 16384 + ((((((col >> 4) * 2 + ab) * 2 + hl) * 32 + gg * 4 + ((c & 7) >> 1)) << 2) + (c >> 3));
 }
 
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// (x0, x1) -> packed bf16 pairs hi = truncation, lo = round(x - hi); element 0 in the low half
-__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
-  const float l0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
-  const float l1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(l0, l1);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 __device__ __forceinline__ void group_barrier(int grp) {
   asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
 }

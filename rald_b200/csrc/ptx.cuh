@@ -497,6 +497,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-0.5f * fabsf(x), poly * e, fmaxf(x, 0.0f));
 }
 
+// ---- legacy warp-level tensor path (mma.sync), for the HBM-bound kernels whose GEMM side is 32 - 64 columns wide
+// (evaluation boundary, conv_in): operands come straight from registers, no shared-memory operand tiles ----
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x0, x1) -> packed bf16 pairs hi = truncation, lo = round(x - hi); element 0 in the low half
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
+  const float l0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
+  const float l1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(l0, l1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
