@@ -722,7 +722,7 @@ def leg_rooflines(step_fn, peaks, frames):
     gemm_shapes = [{"gflop_per_launch": round(wk / 1e9, 3), "launches": n, "ms": round(t, 3),
                     "tflops": round(wk * n / (t * 1e-3) / 1e12, 1) if t > 0 else None}
                    for wk, (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:8]
-    names = {"gemm": "gemm_bf16_kernel (tcgen05, all denoiser / AE linears)", "attn": "attn_d64_kernel (self-attention)",
+    names = {"gemm": "gemm_bf16_kernel (tcgen05, all denoiser / AE linears)", "attn": "attn_d64_streams_kernel (self-attention, Skv = 512)",
              "xattn": "xattn_fused_kernel (fused cross-attention sub-layer)", "conv3d": "conv3d_kernel (radar encoder)",
              "ae_query": "ae_query_kernel (decoder queries, folded form)", "ln": "ln_rows_kernel (adaLN / LayerNorm)",
              "gn": "gn_stats / gn_apply (GroupNorm + swish)", "boundary": "boundary_kernel (final LN + proj_out + EDM "
