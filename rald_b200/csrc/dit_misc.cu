@@ -136,7 +136,7 @@ struct BoundaryParams {
 //            W' = diag(ln_w) W_out^T, K = a per-row shift (median of three samples of the row) that keeps the
 //            one-pass moments and the split operands well conditioned; the same pass takes sum(h - K) and sum((h - K)^2) in fp32.
 //            LayerNorm is applied algebraically: F = rstd (acc - mean' colsum(W')) + ln_b W_out^T.
-//            The loads of the NEXT tile are issued before phase 3 of the current one.
+//            The loads of the NEXT tile are issued right after this phase, under the reduction and phases 2 / 3.
 //   reduce   the four partial accumulators / moments meet in shared memory; warp q sums (fixed order) channel tile q.
 //   phase 2  warp q: EDM preconditioning + Euler / Heun update on its accumulator fragment (rows g, g+8; channels
 //            8 q + 2t, +1), the fp32 arithmetic of the reference (:422-429, :265-273); c_in x_next goes back through
