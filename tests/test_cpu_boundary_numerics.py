@@ -116,3 +116,21 @@ def test_constant_rows_do_not_blow_up():
     F = kernel_restatement(h, ln_w, ln_b, w_out)
     ref = reference(h, ln_w, ln_b, w_out)
     assert np.isfinite(F).all() and _err(F, ref) < 1e-5
+
+
+def test_conv_in_split_products_meet_their_bar():
+    """conv_in_mma_kernel (csrc/enc_misc.cu): 27 taps of a cube value in [0, 1] times fp32 weights as split-bf16 products
+    (activations hi = truncation, weights hi = round-to-nearest), against fp64 — the 2e-5 rel-L2 bar of
+    tests/test_gpu_encoder.py::test_conv_in_against_torch with an order of magnitude to spare."""
+    rng = np.random.default_rng(11)
+    x = rng.random((4096, 27)).astype(np.float32)                 # im2col rows: one output voxel's 27 taps
+    w = (rng.standard_normal((27, 64)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(64).astype(np.float32)
+    xhi, xlo = _split_act(x)
+    whi, wlo = _split_w(w)
+    out = (xlo.astype(np.float64) @ whi.astype(np.float64) + xhi.astype(np.float64) @ wlo.astype(np.float64)
+           + xhi.astype(np.float64) @ whi.astype(np.float64) + b.astype(np.float64)).astype(np.float32)
+    ref = x.astype(np.float64) @ w.astype(np.float64) + b.astype(np.float64)
+    e = float(np.linalg.norm(out.astype(np.float64) - ref) / np.linalg.norm(ref))
+    print("conv_in split-bf16 rel-L2", f"{e:.2e}")
+    assert e < 5e-6
